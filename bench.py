@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""Benchmark of the kinship hot path: gen.phi (+ fused gen.phiMean) on BASELINE.json's synthetic
+pedigrees.  One "step" = one full pass of the hot path (all generations + the final expansion)
+over one pedigree / proband list.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c5s|tiny] [--impl reference]
+
+Prints ONE JSON line (contract in the task statement): metric = kinship pairs/s, with
+`roofline` (dominant kernel, algorithmic bytes / CUDA-event time / measured HBM peak),
+`cpu_baseline` (the unmodified reference on a bounded sample of the same workload),
+`e2e` (the same metric through the host-buffer C-ABI call gk_phi_f64, copies included),
+`clocks` and `gpu_launches`.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (individuals, generations, probands, seed, founders)  -- SURVEY.md 8(d)
+    "c4": dict(n=2_000_000, gens=20, m=100_000, seed=4, founders=None,
+               desc="synthetic 2M-individual, 20-generation pedigree, 100k probands (BASELINE configs[3])"),
+    "c3": dict(n=200_000, gens=12, m=10_000, seed=3, founders=None,
+               desc="synthetic 200k-individual, 12-generation pedigree, 10k probands (BASELINE configs[2])"),
+    "c5s": dict(n=1_250_000, gens=30, m=12_500, seed=5, founders=500,
+                desc="1/4-scale founder-population pedigree, 30 generations (BASELINE configs[4] shape)"),
+    "tiny": dict(n=20_000, gens=8, m=1_500, seed=3, founders=None, desc="tiny synthetic (debug)"),
+}
+SAMPLE_DIV = 20   # the CPU reference runs a 1/20-width replica of the workload (same generator, same depth)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 7 and r[3 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_workload(name, div=1):
+    import geneakit_b200 as gk
+    w = WORKLOADS[name]
+    n, m = w["n"] // div, w["m"] // div
+    founders = None if w["founders"] is None else max(4, w["founders"] // div)
+    t0 = time.time()
+    ped, pro = gk.synthetic_pedigree(n, w["gens"], m, seed=w["seed"], founders=founders)
+    return ped, pro, time.time() - t0
+
+
+def reference_handle(ped):
+    """The same pedigree inside the unmodified reference (oracle/_ref) or, if that library was not
+    built in this tree, the C port of it (oracle/libgkoracle.so)."""
+    from oracle.api import Oracle, Reference
+    f = np.where(ped.sire >= 0, ped.ids[np.maximum(ped.sire, 0)], 0)
+    d = np.where(ped.dam >= 0, ped.ids[np.maximum(ped.dam, 0)], 0)
+    if Reference.available():
+        R = Reference()
+        return "reference", R, R.genealogy(ped.ids, f, d, ped.sex, sorted=True), R.L.gkref_max_threads()
+    O = Oracle()
+    return "port", O, O.genealogy(ped.ids, f, d, ped.sex, sorted=True), O.L.gko_max_threads()
+
+
+def cpu_sample(workload, repeats=1):
+    ped, pro, _ = make_workload(workload, SAMPLE_DIV)
+    kind, eng, h, cores = reference_handle(ped)
+    best = None
+    for _ in range(repeats):
+        t0 = time.time()
+        eng.phi(h, pro)
+        dt = time.time() - t0
+        best = dt if best is None else min(best, dt)
+    m = len(pro)
+    w = WORKLOADS[workload]
+    return {"value": m * (m + 1) / 2 / best, "unit": "pairs/s", "cores": int(cores), "kind": kind,
+            "seconds": best,
+            "sample": "1/%d-width replica of %s: %d individuals, %d generations, %d probands, full gen.phi"
+                      % (SAMPLE_DIV, workload, w["n"] // SAMPLE_DIV, w["gens"], m)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation, all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ped, pro, _ = make_workload(args.workload, SAMPLE_DIV)
+    kind, eng, h, cores = reference_handle(ped)
+    m = len(pro)
+    for _ in range(args.warmup):
+        eng.phi(h, pro)
+    t0 = time.time()
+    for _ in range(args.steps):
+        eng.phi(h, pro)
+    dt = (time.time() - t0) / max(args.steps, 1)
+    val = m * (m + 1) / 2 / dt
+    w = WORKLOADS[args.workload]
+    sample = ("1/%d-width replica of %s: %d individuals, %d generations, %d probands, full gen.phi"
+              % (SAMPLE_DIV, args.workload, w["n"] // SAMPLE_DIV, w["gens"], m))
+    line = {"impl": "reference", "metric": "kinship pairs/sec for gen.phi", "value": val, "unit": "pairs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": w["desc"], "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": int(cores), "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--compress", type=int, default=-1)
+    ap.add_argument("--tile", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import geneakit_b200 as gk
+    from geneakit_b200 import _lib
+    from geneakit_b200._lib import lib, check
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
+    if world > 1:
+        from geneakit_b200.distributed import bench_sharded
+        return bench_sharded(args, rank, world, local)
+
+    ped, pro, gen_s = make_workload(args.workload)
+    m = len(pro)
+    stream = torch.cuda.current_stream()
+    job = gk.cgeneakit.DevicePhi(ped, pro, compress=args.compress, tile=args.tile, device=local,
+                                 stream=stream.cuda_stream)
+    job.upload()                                   # plan + buffers resident in HBM before timing
+    st = job.stats()
+    for _ in range(max(args.warmup, 3)):
+        job.run()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        job.run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    sampler.stop.set()
+    sampler.join()
+    ms = e0.elapsed_time(e1) / args.steps
+    mean = job.mean()
+    pairs = m * (m + 1) / 2
+    value = pairs / (ms * 1e-3)
+
+    # dominant kernel: phi_step_kernel, one launch per generation; CUDA events recorded by the
+    # library on this same stream around every launch of the LAST timed pass
+    t_ms = job.step_times_ms()
+    b = job.step_bytes()
+    nstep = st["n_steps"]
+    step_ms, step_bytes = sum(t_ms[:nstep]), sum(b[:nstep])
+    peak, peak_src = peaks()
+    achieved = step_bytes / (step_ms * 1e-3) / 1e9 if step_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "phi_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "launches": nstep, "bytes_per_launch_avg": step_bytes / max(nstep, 1),
+                "ms_per_launch_avg": step_ms / max(nstep, 1), "share_of_step": step_ms / ms,
+                "expand_ms": t_ms[nstep] if len(t_ms) > nstep else None,
+                "expand_gbs": (b[nstep] / (t_ms[nstep] * 1e-3) / 1e9) if len(t_ms) > nstep and t_ms[nstep] > 0 else None}
+    tr = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # end to end through the host-buffer C-ABI entry point (plan + H2D + kernels + D2H inside)
+    e2e = None
+    if args.e2e_steps > 0:
+        nbytes = m * m * 8
+        ptr = lib.gk_host_alloc(nbytes)
+        pinned = bool(ptr)
+        if not pinned:
+            host = np.empty((m, m), dtype=np.float64)
+            ptr = host.ctypes.data
+        r = ped.ranks(pro)
+        opts = _lib.make_opts(device=local, compress=args.compress, tile=args.tile)
+        mu = C.c_double()
+        check(lib.gk_phi_f64(len(ped), ped.sire, ped.dam, m, r, ptr, C.byref(mu), C.byref(opts)))   # warm
+        t0 = time.time()
+        for _ in range(args.e2e_steps):
+            check(lib.gk_phi_f64(len(ped), ped.sire, ped.dam, m, r, ptr, C.byref(mu), C.byref(opts)))
+        dt = (time.time() - t0) / args.e2e_steps
+        assert mu.value == mean, (mu.value, mean)
+        e2e = {"value": pairs / dt, "unit": "pairs/s", "seconds_per_step": dt,
+               "h2d_bytes_per_step": int(st["plan_bytes"]),
+               "d2h_bytes_per_step": int(nbytes + 16), "host_buffer": "pinned" if pinned else "pageable",
+               "plan_seconds": st["plan_seconds"], "steps": args.e2e_steps}
+        if pinned:
+            lib.gk_host_free(ptr)
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_sample(args.workload)
+
+    w = WORKLOADS[args.workload]
+    line = {"metric": "kinship pairs/sec for gen.phi", "value": value, "unit": "pairs/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["desc"], "individuals": len(ped), "generations": w["gens"], "probands": m,
+                       "seed": w["seed"], "cuts": job.cut_sizes(), "classes": job.class_sizes(),
+                       "compressed": bool(st["compressed"]), "ranked": bool(st["ranked"]), "tile": st["tile"],
+                       "l2": "inputs larger than L2 (%.1f GB of matrices per pass)" % (st["algorithmic_bytes_device"] / 1e9),
+                       "cells_reference": st["cells_reference"], "cells_device": st["cells_device"],
+                       "phi_mean": mean, "pedigree_build_s": gen_s},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
+            "gpu_launches": int(st["kernel_launches"]) * args.steps,
+            "reference_algorithmic_gbs": st["algorithmic_bytes_reference"] / (ms * 1e-3) / 1e9}
+    job.close()
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

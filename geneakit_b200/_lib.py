@@ -1,0 +1,119 @@
+"""ctypes loader for libgeneakit_b200.so (the C ABI declared in include/geneakit_b200.h).
+
+The library is the product: if it is missing this module raises ImportError -- there is no
+Python or CPU fallback for the compute path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgeneakit_b200.so")
+
+GK_OK, GK_ERR_ARG, GK_ERR_INDEX, GK_ERR_CUDA, GK_ERR_OOM, GK_ERR_STATE = 0, 1, 2, 3, 4, 5
+
+_I = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_D = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_F = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+
+
+class gk_opts(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("verbose", C.c_int32),
+                ("compress", C.c_int32), ("tile", C.c_int32), ("rank", C.c_int32),
+                ("world", C.c_int32), ("reserved0", C.c_int32), ("stream", C.c_void_p)]
+
+
+class gk_phi_stats(C.Structure):
+    _fields_ = [("n_cuts", C.c_int32), ("n_steps", C.c_int32), ("compressed", C.c_int32),
+                ("ranked", C.c_int32), ("tile", C.c_int32), ("m", C.c_int32),
+                ("max_cut", C.c_int64), ("max_classes", C.c_int64),
+                ("cells_reference", C.c_int64), ("cells_device", C.c_int64),
+                ("algorithmic_bytes_reference", C.c_int64), ("algorithmic_bytes_device", C.c_int64),
+                ("device_bytes", C.c_int64), ("kernel_launches", C.c_int64),
+                ("plan_seconds", C.c_double), ("plan_bytes", C.c_int64)]
+
+
+class gk_step_view(C.Structure):
+    _P = C.POINTER(C.c_int32)
+    _fields_ = [("K", C.c_int64), ("ld", C.c_int64), ("K_prev", C.c_int64),
+                ("nt", C.c_int32), ("tile", C.c_int32), ("win", C.c_int32), ("lmax", C.c_int32),
+                ("nr_max", C.c_int32),
+                ("la", _P), ("cls_rank", _P), ("c0", _P), ("nl", _P), ("list", _P), ("rowind", _P),
+                ("hot_off", _P), ("hot_idx", _P)]
+
+
+def make_opts(device=-1, verbose=False, compress=-1, tile=0, rank=0, world=1, stream=None):
+    o = gk_opts()
+    o.struct_size = C.sizeof(gk_opts)
+    o.device, o.verbose, o.compress, o.tile = int(device), int(bool(verbose)), int(compress), int(tile)
+    o.rank, o.world, o.reserved0 = int(rank), int(world), 0
+    o.stream = stream
+    return o
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "geneakit_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    OP = C.POINTER(gk_opts)
+    L.gk_last_error.restype = C.c_char_p
+    L.gk_abi_version.restype = i32
+    L.gk_host_alloc.argtypes = [C.c_uint64]; L.gk_host_alloc.restype = vp
+    L.gk_host_free.argtypes = [vp]
+    L.gk_phi_f64.argtypes = [i32, _I, _I, i32, _I, vp, C.POINTER(C.c_double), OP]
+    L.gk_gc_f64.argtypes = [i32, _I, _I, i32, _I, i32, _I, vp, OP]
+    L.gk_phi_required_gb.argtypes = [i32, _I, _I, i32, _I]; L.gk_phi_required_gb.restype = C.c_double
+    L.gk_childless.argtypes = [i32, _I, _I, vp]; L.gk_childless.restype = i32
+    L.gk_parentless.argtypes = [i32, _I, _I, vp]; L.gk_parentless.restype = i32
+    L.gk_dfs_order.argtypes = [i32, _I, _I, _I]
+    L.gk_cut_sizes.argtypes = [i32, _I, _I, i32, _I, _I, i32]; L.gk_cut_sizes.restype = i32
+    L.gk_phi_plan.argtypes = [i32, _I, _I, i32, _I, OP, C.POINTER(vp)]
+    for name in ("gk_phi_upload", "gk_phi_run", "gk_phi_sync"):
+        getattr(L, name).argtypes = [vp]
+    L.gk_phi_mean.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.gk_phi_copy_out.argtypes = [vp, vp]
+    L.gk_phi_device_result.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+    L.gk_phi_get_stats.argtypes = [vp, C.POINTER(gk_phi_stats)]
+    L.gk_phi_cut_sizes.argtypes = [vp, _I, i32]
+    L.gk_phi_class_sizes.argtypes = [vp, _I, i32]
+    L.gk_phi_step_times.argtypes = [vp, _F, i32]
+    L.gk_phi_step_bytes.argtypes = [vp, np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), i32]
+    L.gk_phi_step_view.argtypes = [vp, i32, C.POINTER(gk_step_view)]
+    L.gk_phi_final_view.argtypes = [vp, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32)),
+                                    C.POINTER(i64)]
+    L.gk_phi_initial_classes.argtypes = [vp, C.POINTER(i64)]
+    L.gk_phi_free.argtypes = [vp]; L.gk_phi_free.restype = None
+    return L
+
+
+lib = _load()
+
+EXPORTS = [
+    "gk_phi_f64", "gk_gc_f64", "gk_phi_required_gb", "gk_childless", "gk_parentless", "gk_dfs_order",
+    "gk_cut_sizes", "gk_last_error", "gk_abi_version", "gk_host_alloc", "gk_host_free",
+    "gk_phi_plan", "gk_phi_upload", "gk_phi_run", "gk_phi_sync", "gk_phi_mean", "gk_phi_copy_out",
+    "gk_phi_device_result", "gk_phi_get_stats", "gk_phi_cut_sizes", "gk_phi_class_sizes",
+    "gk_phi_step_times", "gk_phi_step_bytes", "gk_phi_free", "gk_phi_step_view", "gk_phi_final_view", "gk_phi_initial_classes",
+]
+
+
+class GkError(RuntimeError):
+    pass
+
+
+def check(rc):
+    """0 -> ok; otherwise raise the exception type the reference's binding would surface."""
+    if rc == GK_OK:
+        return
+    msg = (lib.gk_last_error() or b"").decode()
+    if rc == GK_ERR_INDEX:
+        raise IndexError(msg)            # nanobind maps std::out_of_range -> IndexError
+    if rc == GK_ERR_OOM:
+        raise MemoryError(msg)
+    if rc == GK_ERR_ARG:
+        raise ValueError(msg)
+    raise GkError("geneakit_b200 error %d: %s" % (rc, msg))

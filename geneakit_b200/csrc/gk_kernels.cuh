@@ -1,0 +1,60 @@
+// Device-side interface of the kinship kernels (sm_100a).  See gk_kernels.cu.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gk {
+
+// Everything one recurrence step needs, by value (fits the 4 KB kernel-parameter space).
+struct StepDev {
+    const double *Gprev;     // K_prev x ld_prev class matrix of cut g-1 (row-major, symmetric)
+    const double *dprev;     // self kinship of each class of cut g-1
+    double *Gnew;            // K x ld class matrix of cut g
+    double *dnew;            // self kinship of each class of cut g
+    int64_t ld_prev, ld_new;
+    int64_t K_prev, K;
+    const int32_t *la;       // K: local parent indices la0 | la1 << 16 (0xFFFF = unknown parent)
+    const int32_t *cls_rank; // K: rank of the class's individual (RANKED only)
+    const int32_t *c0;       // nt: window start column in Gprev (multiple of 4)
+    const int32_t *nl;       // nt: list length
+    const int32_t *list;     // nt * LMAX: scattered parent rows in Gprev
+    const int32_t *rowind;   // nt * (W + LMAX): individual occupying each local row, -1 none
+    const int32_t *hot_off;  // nt + 1
+    const int32_t *hot_idx;  // local rows whose individual is a parent in more than one tile
+    int32_t nt;
+    int32_t pitch;           // shared-memory pitch (doubles) of the staged block
+};
+
+struct ExpandDev {
+    const double *G;         // K_last x ld last class matrix
+    const double *d;         // self kinship per class
+    int64_t ld;
+    const int32_t *cls;      // m: class row of caller entry i
+    const int32_t *ind;      // m: individual of caller entry i
+    double *out;             // m x m, row-major, caller order
+    int64_t m;
+    double *partials;        // gridDim.x*gridDim.y*2 : per-CTA (sum all, sum diag)
+    int32_t single_cut;      // 1: every proband is a top founder -> 0.5*I (lib/compute.cpp:655-661)
+};
+
+size_t step_smem_bytes(int tile, int nr_max, bool ranked, int *pitch_out);
+cudaError_t launch_step(const StepDev &s, int tile, bool ranked, size_t smem, cudaStream_t st);
+cudaError_t launch_init(double *G0, double *d0, int64_t K0, int64_t ld0, cudaStream_t st);
+cudaError_t launch_expand(const ExpandDev &e, int *nblocks_out, cudaStream_t st);
+cudaError_t launch_mean_finish(const double *partials, int nblocks, double *sums /*2*/, cudaStream_t st);
+cudaError_t configure_kernels();   // cudaFuncSetAttribute for large dynamic shared memory
+
+// gen.gc propagation: out row = 0.5*w0*row(p0) + 0.5*w1*row(p1), then seed own ancestor columns.
+struct GcStepDev {
+    const double *Vprev; double *Vnew;
+    int64_t ld;              // columns (ancestors, padded)
+    int64_t rows;            // members of the new cut
+    const int32_t *p0, *p1;  // parent row in Vprev or -1 (kept: p0 = own old row, p1 = -2)
+    const int32_t *seed_off; // rows + 1 : CSR of ancestor columns equal to this individual
+    const int32_t *seed_col;
+};
+cudaError_t launch_gc_step(const GcStepDev &g, cudaStream_t st);
+cudaError_t launch_gc_gather(const double *V, int64_t ld, const int32_t *row_of /*m, -1 = zero row*/,
+                             double *out, int64_t m, int64_t a, cudaStream_t st);
+
+}  // namespace gk

@@ -1,0 +1,163 @@
+/* geneakit_b200 -- C ABI of the B200-native dense-kinship hot path.
+ *
+ * This is the drop-in boundary behind the reference's `cgeneakit` binding.  Every entry point
+ * takes plain pointers and sizes (no C++/torch types) and names the reference interface it
+ * replaces (paths relative to the reference repository, geneakit/...).
+ *
+ * Index space: RANK space.  Individual k is the k-th entry of Pedigree::ids, which the
+ * reference keeps topologically ordered with Individual::rank == k (include/pedigree.hpp:34-44).
+ * sire[k] / dam[k] = rank of the father / mother, or -1 when unknown.  The binding flattens
+ * its Pedigree once and validates ids (so IndexError behaviour is unchanged).
+ *
+ * Errors: no exception crosses this boundary.  0 = GK_OK, otherwise a GK_ERR_* code; the
+ * message is available from gk_last_error() (thread-local).  There is NO CPU fallback:
+ * without a usable CUDA device every compute entry point returns GK_ERR_CUDA.
+ */
+#ifndef GENEAKIT_B200_H
+#define GENEAKIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GK_OK            0
+#define GK_ERR_ARG       1   /* bad argument (null pointer, negative size, parent not before child) */
+#define GK_ERR_INDEX     2   /* proband / ancestor rank out of range (reference: std::out_of_range, lib/compute.cpp:649) */
+#define GK_ERR_CUDA      3   /* CUDA runtime error or no device */
+#define GK_ERR_OOM       4   /* device (or host) memory exhausted */
+#define GK_ERR_STATE     5   /* call order violated on a job handle */
+
+#define GK_ABI_VERSION   1
+
+typedef struct gk_opts {
+    int32_t struct_size;   /* sizeof(gk_opts); lets the ABI grow */
+    int32_t device;        /* CUDA device ordinal, -1 = current device */
+    int32_t verbose;       /* 1: print the cut sizes / "Cut k out of n" lines of lib/compute.cpp:662-676 */
+    int32_t compress;      /* -1 auto (default), 0 one matrix row per individual, 1 one row per sibship */
+    int32_t tile;          /* 0 auto; 32 or 64: classes per tile */
+    int32_t rank;          /* column shard owned by this process (multi-GPU), 0 .. world-1 */
+    int32_t world;         /* number of column shards, 0/1 = single GPU */
+    int32_t reserved0;
+    void   *stream;        /* cudaStream_t to enqueue on, NULL = the library's own stream */
+} gk_opts;
+
+/* ---- one-shot entry points: what the binding lambdas call -------------------------------- */
+
+/* Replaces compute_kinships(Pedigree<>&, std::vector<int> proband_ids, bool verbose)
+ * (include/compute.hpp:114-116, lib/compute.cpp:638-700) behind the lambda at
+ * lib/cgeneakit.cpp:411-431.  pro[0..m) = proband ranks in CALLER order (duplicates allowed);
+ * out = m*m doubles, row-major, caller-owned HOST memory (pageable or pinned).
+ * mean_or_null, when non-NULL, receives gen.phiMean of the result (geneakit/compute.py:124-132)
+ * from the fused device reduction: (sum(all) - sum(diag)) / (m*m - m). */
+int gk_phi_f64(int32_t n, const int32_t *sire, const int32_t *dam,
+               int32_t m, const int32_t *pro,
+               double *out, double *mean_or_null, const gk_opts *opts);
+
+/* Replaces compute_genetic_contributions(Pedigree<>&, proband_ids, ancestor_ids)
+ * (include/compute.hpp:130-131, lib/compute.cpp:832-862) behind lib/cgeneakit.cpp:491-511.
+ * out = m*a doubles, row-major: rows = probands (caller order), columns = ancestors. */
+int gk_gc_f64(int32_t n, const int32_t *sire, const int32_t *dam,
+              int32_t m, const int32_t *pro, int32_t a, const int32_t *anc,
+              double *out, const gk_opts *opts);
+
+/* Replaces get_required_memory_for_kinships (include/compute.hpp:110-111,
+ * lib/compute.cpp:591-635): GB of the two largest adjacent cut matrices.  Host only.
+ * Returns a negative value on error. */
+double gk_phi_required_gb(int32_t n, const int32_t *sire, const int32_t *dam,
+                          int32_t m, const int32_t *pro);
+
+/* Replace get_proband_ids / get_founder_ids (lib/identify.cpp:55-65, :28-38) in rank space:
+ * ranks of childless / parentless individuals, ascending rank; the binding maps to ids and
+ * sorts by id.  Return the count; out may be NULL to query it.  Host only. */
+int32_t gk_childless(int32_t n, const int32_t *sire, const int32_t *dam, int32_t *out);
+int32_t gk_parentless(int32_t n, const int32_t *sire, const int32_t *dam, int32_t *out);
+
+/* Replaces the DFS topological sort of the loader (lib/create.cpp:121-155,
+ * convert_pedigree :158-199 with sorted=false).  fidx/midx = FILE position of each parent or
+ * -1; order[r] = file position of the individual that gets rank r.  Host only. */
+int gk_dfs_order(int32_t n, const int32_t *fidx, const int32_t *midx, int32_t *order);
+
+/* Sizes of the vertex cuts (lib/compute.cpp:119-135) for these probands; returns the number
+ * of cuts G (sizes[0..min(G,cap))) or a negative GK_ERR_*.  Host only. */
+int32_t gk_cut_sizes(int32_t n, const int32_t *sire, const int32_t *dam,
+                     int32_t m, const int32_t *pro, int32_t *sizes, int32_t cap);
+
+const char *gk_last_error(void);
+int32_t gk_abi_version(void);
+
+/* Pinned host memory for result matrices (the binding owns it through its capsule deleter,
+ * lib/cgeneakit.cpp:420-423); device->host copies into it run at full PCIe rate. */
+void *gk_host_alloc(uint64_t bytes);
+void  gk_host_free(void *p);
+
+/* ---- device-resident job API: plan once, keep everything in HBM ---------------------------
+ * Used by the benchmark, by phiMean-only callers that never need the matrix on the host, and
+ * by the multi-GPU driver.  Lifetime: gk_phi_plan -> gk_phi_upload -> gk_phi_run (repeatable)
+ * -> gk_phi_mean / gk_phi_copy_out / gk_phi_device_result -> gk_phi_free. */
+typedef struct gk_phi_job gk_phi_job;
+
+typedef struct gk_phi_stats {
+    int32_t  n_cuts;            /* G */
+    int32_t  n_steps;           /* G - 1 recurrence steps */
+    int32_t  compressed;        /* 1 if sibship classes are used */
+    int32_t  ranked;            /* 1 if the rank-ordered rounding rule is applied per pair (G-1 > 26) */
+    int32_t  tile;
+    int32_t  m;                 /* probands (caller entries) */
+    int64_t  max_cut;           /* largest |cut_g| */
+    int64_t  max_classes;       /* largest matrix dimension actually stored */
+    int64_t  cells_reference;   /* sum_{g>=1} |cut_g|^2 : cells the reference's loop nest updates */
+    int64_t  cells_device;      /* sum_{g>=1} K_g^2 (+ m*m for the final expansion) */
+    int64_t  algorithmic_bytes_reference;  /* 8*sum(P_g*|cut_{g-1}| + |cut_g|^2 - k_g^2) */
+    int64_t  algorithmic_bytes_device;     /* 8*(sum_g reads(K_{g-1} rows needed) + K_g^2) + 8*m*m */
+    int64_t  device_bytes;      /* HBM allocated for matrices + plan */
+    int64_t  kernel_launches;   /* launches one gk_phi_run enqueues */
+    double   plan_seconds;      /* host planning time */
+    int64_t  plan_bytes;        /* int32 tile-plan arrays copied host->device by gk_phi_upload */
+} gk_phi_stats;
+
+int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam,
+                int32_t m, const int32_t *pro, const gk_opts *opts, gk_phi_job **job);
+int gk_phi_upload(gk_phi_job *job);                 /* allocate HBM, copy the plan (H2D) */
+int gk_phi_run(gk_phi_job *job);                    /* enqueue init + all steps + expansion; async */
+int gk_phi_sync(gk_phi_job *job);                   /* wait for the job's stream */
+int gk_phi_mean(gk_phi_job *job, double *sum_all, double *sum_diag, double *mean);
+int gk_phi_copy_out(gk_phi_job *job, double *host_out);            /* m*m doubles */
+int gk_phi_device_result(gk_phi_job *job, double **dev, int64_t *ld); /* final m x m matrix in HBM */
+int gk_phi_get_stats(gk_phi_job *job, gk_phi_stats *stats);
+int gk_phi_cut_sizes(gk_phi_job *job, int32_t *sizes, int32_t cap);   /* |cut_g| as the reference counts them */
+int gk_phi_class_sizes(gk_phi_job *job, int32_t *sizes, int32_t cap); /* K_g actually stored */
+/* Average device time of the dominant kernel over the last gk_phi_run, from CUDA events
+ * recorded on the job's stream around every step launch (ms per step, n_steps entries). */
+int gk_phi_step_times(gk_phi_job *job, float *ms, int32_t cap);
+/* ALGORITHMIC bytes of each launch timed by gk_phi_step_times (same indexing): for step g
+ * 8*(P_g*K_{g-1} + K_g^2 - k_g^2) -- SURVEY 8(d)'s formula on the matrices actually stored
+ * (16 B per updated cell on discrete-generation pedigrees) -- and 8*(m^2 + min(m,K)^2) for the
+ * final expansion. */
+int gk_phi_step_bytes(gk_phi_job *job, int64_t *bytes, int32_t cap);
+void gk_phi_free(gk_phi_job *job);
+
+/* Plan introspection for tests (host arrays, valid until gk_phi_free): the per-step tile
+ * plan that the kernels consume.  See DESIGN.md "Plan layout". */
+typedef struct gk_step_view {
+    int64_t K, ld, K_prev;
+    int32_t nt, tile, win, lmax, nr_max;
+    const int32_t *la;        /* K entries: la0 | (la1 << 16), 0xFFFF = missing parent */
+    const int32_t *cls_rank;  /* K entries (ranked mode) or NULL */
+    const int32_t *c0;        /* nt */
+    const int32_t *nl;        /* nt */
+    const int32_t *list;      /* nt * lmax : class index in the previous matrix */
+    const int32_t *rowind;    /* nt * (win + lmax) : individual (rank) occupying each local row, -1 none */
+    const int32_t *hot_off;   /* nt + 1 */
+    const int32_t *hot_idx;   /* local rows whose individual is a parent in more than one tile */
+} gk_step_view;
+int gk_phi_step_view(gk_phi_job *job, int32_t step, gk_step_view *view);  /* step = 1 .. G-1 */
+/* Final expansion map: for caller entry i the class row in the last matrix and the individual. */
+int gk_phi_final_view(gk_phi_job *job, const int32_t **cls, const int32_t **ind, int64_t *K_last);
+int gk_phi_initial_classes(gk_phi_job *job, int64_t *K0);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENEAKIT_B200_H */

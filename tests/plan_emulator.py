@@ -1,0 +1,118 @@
+"""Test helper: a numpy interpreter of the TILE PLAN (DESIGN.md "Plan layout").
+
+It executes, on the CPU and tile pair by tile pair, exactly what phi_step_kernel does with the
+plan arrays exposed by gk_phi_step_view -- including the symmetric fetch of the window x list
+block, the "same individual" patch and the mirror store -- so the host planner can be checked
+against the oracle without a GPU.  It is NOT a product path (it lives under tests/)."""
+import ctypes as C
+
+import numpy as np
+
+from geneakit_b200 import _lib
+from geneakit_b200._lib import lib, check
+
+MISS = 0xFFFF
+
+
+def _arr(ptr, n):
+    if n == 0:
+        return np.zeros(0, dtype=np.int32)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+
+
+def step_view(job, g):
+    v = _lib.gk_step_view()
+    check(lib.gk_phi_step_view(job._h, g, C.byref(v)))
+    nt, W, LMAX = v.nt, v.win, v.lmax
+    d = dict(K=v.K, ld=v.ld, K_prev=v.K_prev, nt=nt, T=v.tile, W=W, LMAX=LMAX, nr_max=v.nr_max)
+    d["la"] = _arr(v.la, v.K)
+    d["cls_rank"] = _arr(v.cls_rank, v.K) if v.cls_rank else None
+    d["c0"], d["nl"] = _arr(v.c0, nt), _arr(v.nl, nt)
+    d["list"] = _arr(v.list, nt * LMAX).reshape(nt, LMAX)
+    d["rowind"] = _arr(v.rowind, nt * (W + LMAX)).reshape(nt, W + LMAX)
+    d["hot_off"] = _arr(v.hot_off, nt + 1)
+    d["hot_idx"] = _arr(v.hot_idx, int(d["hot_off"][-1]))
+    return d
+
+
+def emulate(job):
+    st = job.stats()
+    G, m = st["n_cuts"], st["m"]
+    cls_p, ind_p, klast = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)(), C.c_int64()
+    check(lib.gk_phi_final_view(job._h, C.byref(cls_p), C.byref(ind_p), C.byref(klast)))
+    fcls, find = _arr(cls_p, m), _arr(ind_p, m)
+    if G == 1:
+        return 0.5 * np.eye(m)
+    k0 = C.c_int64()
+    check(lib.gk_phi_initial_classes(job._h, C.byref(k0)))
+    Gp = np.zeros((k0.value, k0.value))
+    dp = np.full(k0.value, 0.5)
+    for g in range(1, G):
+        v = step_view(job, g)
+        K, T, W, nt = v["K"], v["T"], v["W"], v["nt"]
+        assert v["K_prev"] == Gp.shape[0]
+        Gn = np.full((K, K), np.nan)
+        dn = np.full(K, np.nan)
+        la0, la1 = v["la"] & 0xFFFF, (v["la"] >> 16) & 0xFFFF
+        last = Gp.shape[0] - 1
+
+        def local_classes(t):
+            nl = v["nl"][t]
+            win = np.minimum(v["c0"][t] + np.arange(W), last)
+            return np.concatenate([win, v["list"][t, :nl]]).astype(np.int64), nl
+
+        for I in range(nt):
+            rI, nlI = local_classes(I)
+            for J in range(I + 1):
+                cJ, nlJ = local_classes(J)
+                S = np.empty((W + nlI, W + nlJ))
+                S[:, :W] = Gp[np.ix_(rI, cJ[:W])]                      # rows x window columns
+                S[:W, W:] = Gp[np.ix_(cJ[W:], rI[:W])].T               # window rows x list cols via symmetry
+                S[W:, W:] = Gp[np.ix_(rI[W:], cJ[W:])]                 # list x list
+                indI, indJ = v["rowind"][I], v["rowind"][J]
+                if I == J:
+                    for r in range(W + nlI):
+                        if indI[r] >= 0:
+                            S[r, r] = dp[rI[r]]
+                else:
+                    hI = v["hot_idx"][v["hot_off"][I]:v["hot_off"][I + 1]]
+                    hJ = v["hot_idx"][v["hot_off"][J]:v["hot_off"][J + 1]]
+                    for hi in hI:
+                        for hj in hJ:
+                            if indI[hi] == indJ[hj]:
+                                S[hi, hj] = dp[rI[hi]]
+                a_lo, a_hi = I * T, min(K, I * T + T)
+                b_lo, b_hi = J * T, min(K, J * T + T)
+                A0, A1 = la0[a_lo:a_hi], la1[a_lo:a_hi]
+                B0, B1 = la0[b_lo:b_hi], la1[b_lo:b_hi]
+
+                def take(ra, cb):
+                    ok = (ra[:, None] != MISS) & (cb[None, :] != MISS)
+                    rr = np.where(ra == MISS, 0, ra)
+                    cc = np.where(cb == MISS, 0, cb)
+                    assert rr.max(initial=0) < S.shape[0] and cc.max(initial=0) < S.shape[1]
+                    return np.where(ok, S[np.ix_(rr, cc)], 0.0)
+
+                p, q, r, s = take(A0, B0), take(A1, B0), take(A0, B1), take(A1, B1)
+                if v["cls_rank"] is not None:
+                    lower = v["cls_rank"][a_lo:a_hi][:, None] < v["cls_rank"][b_lo:b_hi][None, :]
+                    out = np.where(lower, 0.25 * ((p + q) + (r + s)), 0.25 * ((p + r) + (q + s)))
+                else:
+                    out = 0.25 * ((p + q) + (r + s))
+                Gn[a_lo:a_hi, b_lo:b_hi] = out
+                if I != J:
+                    Gn[b_lo:b_hi, a_lo:a_hi] = out.T
+                else:
+                    for k in range(a_hi - a_lo):
+                        x0, x1 = A0[k], A1[k]
+                        if x0 != MISS and x0 == x1:
+                            dn[a_lo + k] = S[x0, x0]
+                        elif x0 != MISS and x1 != MISS:
+                            dn[a_lo + k] = 0.5 + 0.5 * S[x0, x1]
+                        else:
+                            dn[a_lo + k] = 0.5
+        assert not np.isnan(Gn).any() and not np.isnan(dn).any()
+        Gp, dp = Gn, dn
+    out = Gp[np.ix_(fcls, fcls)]
+    same = find[:, None] == find[None, :]
+    return np.where(same, dp[fcls][:, None] * np.ones((1, m)), out)
