@@ -180,7 +180,8 @@ def main():
 
     ped, pro, gen_s = make_workload(args.workload)
     m = len(pro)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real stream: the default stream's handle is NULL
+    torch.cuda.set_stream(stream)
     job = gk.cgeneakit.DevicePhi(ped, pro, compress=args.compress, tile=args.tile, device=local,
                                  stream=stream.cuda_stream)
     job.upload()                                   # plan + buffers resident in HBM before timing

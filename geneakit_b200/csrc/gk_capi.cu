@@ -32,7 +32,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 
 constexpr int64_t kPadDoubles = 256;   // slack after every matrix: window reads may run past the last row
 
-struct StepOffsets { size_t la, rank, c0, nl, list, rowind, hot_off, hot_idx; };
+struct StepOffsets { size_t la, pind, rank, desc; };
 
 }  // namespace
 
@@ -206,6 +206,17 @@ int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, c
         delete j;
         return fail(code, msg);
     }
+    // a 64-class tile plan whose staged block would not fit in shared memory falls back to 32
+    if (j->plan.tile == 64) {
+        bool fits = true;
+        for (int g = 1; g < j->plan.G; g++)
+            if (gk::step_smem_bytes(64, j->plan.steps[g].nr_max, j->plan.ranked, nullptr) > 200 * 1024) fits = false;
+        if (!fits && !gk::build_phi_plan(n, sire, dam, m, pro, j->opts.compress, 32, j->plan)) {
+            std::string msg = j->plan.error;
+            delete j;
+            return fail(GK_ERR_ARG, msg);
+        }
+    }
     *job = j;
     return GK_OK;
 }
@@ -236,8 +247,7 @@ int gk_phi_upload(gk_phi_job *j) {
     for (int g = 1; g < G; g++) {
         gk::StepPlan &S = P.steps[g];
         StepOffsets &o = j->off[g];
-        o.la = push(S.la); o.rank = push(S.cls_rank); o.c0 = push(S.c0); o.nl = push(S.nl);
-        o.list = push(S.list); o.rowind = push(S.rowind); o.hot_off = push(S.hot_off); o.hot_idx = push(S.hot_idx);
+        o.la = push(S.la); o.pind = push(S.pind); o.rank = push(S.cls_rank); o.desc = push(S.desc);
         j->smem[g] = gk::step_smem_bytes(T, S.nr_max, P.ranked, &j->pitch[g]);
         if (j->smem[g] > 227 * 1024) return fail(GK_ERR_ARG, "tile plan needs more than 227 KB of shared memory; use tile=32");
     }
@@ -313,9 +323,8 @@ int gk_phi_run(gk_phi_job *j) {
             d.Gnew = j->buf[g & 1]; d.dnew = j->dvec[g & 1];
             d.ld_prev = P.steps[g - 1].ld; d.ld_new = S.ld;
             d.K_prev = S.K_prev; d.K = S.K;
-            d.la = j->ints + o.la; d.cls_rank = j->ints + o.rank; d.c0 = j->ints + o.c0; d.nl = j->ints + o.nl;
-            d.list = j->ints + o.list; d.rowind = j->ints + o.rowind;
-            d.hot_off = j->ints + o.hot_off; d.hot_idx = j->ints + o.hot_idx;
+            d.la = j->ints + o.la; d.pind = j->ints + o.pind; d.cls_rank = j->ints + o.rank;
+            d.desc = j->ints + o.desc;
             d.nt = S.nt; d.pitch = j->pitch[g];
             GK_CUDA(cudaEventRecord(j->ev[g], st));
             GK_CUDA(gk::launch_step(d, P.tile, P.ranked, j->smem[g], st));
@@ -403,8 +412,7 @@ int gk_phi_get_stats(gk_phi_job *j, gk_phi_stats *s) {
     int64_t ints = (int64_t) P.final_cls.size() + (int64_t) P.final_ind.size();
     for (int g = 1; g < P.G; g++) {
         const gk::StepPlan &S = P.steps[g];
-        ints += (int64_t) (S.la.size() + S.cls_rank.size() + S.c0.size() + S.nl.size() + S.list.size() +
-                           S.rowind.size() + S.hot_off.size() + S.hot_idx.size());
+        ints += (int64_t) (S.la.size() + S.pind.size() + S.cls_rank.size() + S.desc.size());
     }
     s->plan_bytes = ints * 4;
     return GK_OK;
@@ -450,9 +458,8 @@ int gk_phi_step_view(gk_phi_job *j, int32_t step, gk_step_view *v) {
     const gk::StepPlan &S = P.steps[step];
     v->K = S.K; v->ld = S.ld; v->K_prev = S.K_prev; v->nt = S.nt; v->tile = P.tile; v->win = P.win;
     v->lmax = P.lmax; v->nr_max = S.nr_max;
-    v->la = S.la.data(); v->cls_rank = P.ranked ? S.cls_rank.data() : nullptr;
-    v->c0 = S.c0.data(); v->nl = S.nl.data(); v->list = S.list.data(); v->rowind = S.rowind.data();
-    v->hot_off = S.hot_off.data(); v->hot_idx = S.hot_idx.data();
+    v->la = S.la.data(); v->pind = S.pind.data(); v->cls_rank = P.ranked ? S.cls_rank.data() : nullptr;
+    v->desc = S.desc.data(); v->desc_words = gk::desc_words(P.tile); v->conf_max = gk::kConfMax;
     return GK_OK;
 }
 int gk_phi_final_view(gk_phi_job *j, const int32_t **cls, const int32_t **ind, int64_t *K_last) {

@@ -38,149 +38,171 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+constexpr int kConf = 12;      // == gk::kConfMax (gk_plan.hpp)
+
+// E(x, y) of the previous cut for one (row parent, column parent) pair, applying
+// "same individual -> self kinship" (lib/compute.cpp:522-528) when the CTA is on the slow path.
+template <bool CHECK>
+__device__ __forceinline__ double fetch_e(const double *S, int pitch, int ra, int cb, int ia, int ib,
+                                          const double *dprev, int cls_a) {
+    if (ra == kMiss || cb == kMiss) return 0.0;
+    if (CHECK && ia == ib) return dprev[cls_a];
+    return S[(size_t) ra * pitch + cb];
+}
+
 template <int T, bool RANKED>
 __global__ void __launch_bounds__(kThreads) phi_step_kernel(const StepDev s) {
-    constexpr int W = T, LMAX = 2 * T, NRMAX = W + LMAX;
+    constexpr int W = T, LMAX = 2 * T, DW = 4 + LMAX + kConf;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
-    // ---- which tile pair -------------------------------------------------------------------
+    // ---- which tile pair (I-major: CTAs resident together share rows(I) -> L2 reuse) ----------
     const long long bid = blockIdx.x;
     int I = (int) ((sqrt(8.0 * (double) bid + 1.0) - 1.0) * 0.5);
     while ((long long) I * (I + 1) / 2 > bid) --I;
     while ((long long) (I + 1) * (I + 2) / 2 <= bid) ++I;
     const int J = (int) (bid - (long long) I * (I + 1) / 2);
     const int tid = threadIdx.x;
-
-    const int nlI = s.nl[I], nlJ = s.nl[J];
-    const int nrI = W + nlI, ncJ = W + nlJ;
-    const int c0I = s.c0[I], c0J = s.c0[J];
     const int pitch = s.pitch;
 
-    // ---- shared memory carve-up --------------------------------------------------------------
-    double *S = reinterpret_cast<double *>(smem_raw);                  // nr_max x pitch
-    double *O = S + (size_t) pitch * (size_t) pitch;                     // T x (T+1); pitch >= nr_max
-    int32_t *ibase = reinterpret_cast<int32_t *>(O + T * (T + 1));
-    int32_t *listI = ibase;                 // LMAX
-    int32_t *listJ = listI + LMAX;          // LMAX
-    int32_t *rowI = listJ + LMAX;           // NRMAX
-    int32_t *rowJ = rowI + NRMAX;           // NRMAX
-    int32_t *laI = rowJ + NRMAX;            // T
-    int32_t *laJ = laI + T;                 // T
-    int32_t *rkI = laJ + T;                 // T (RANKED)
-    int32_t *rkJ = rkI + T;                 // T (RANKED)
+    // ---- shared memory carve-up ----------------------------------------------------------------
+    double *S = reinterpret_cast<double *>(smem_raw);                    // nr_max x pitch; reused as O (T x (T+1))
+    int32_t *dI = reinterpret_cast<int32_t *>(S + (size_t) pitch * pitch); // DW: descriptor of tile I
+    int32_t *dJ = dI + DW;                                                // DW
+    int32_t *laI = dJ + DW;                                               // T
+    int32_t *laJ = laI + T;                                               // T
+    int32_t *piI = laJ + T;                                               // 2T parent individuals
+    int32_t *piJ = piI + 2 * T;                                           // 2T
+    int32_t *rkI = piJ + 2 * T;                                           // T (RANKED)
+    int32_t *rkJ = rkI + T;                                               // T (RANKED)
 
-    for (int i = tid; i < nlI; i += kThreads) listI[i] = s.list[(size_t) I * LMAX + i];
-    for (int i = tid; i < nlJ; i += kThreads) listJ[i] = s.list[(size_t) J * LMAX + i];
-    for (int i = tid; i < nrI; i += kThreads) rowI[i] = s.rowind[(size_t) I * NRMAX + i];
-    for (int i = tid; i < ncJ; i += kThreads) rowJ[i] = s.rowind[(size_t) J * NRMAX + i];
-    for (int i = tid; i < T; i += kThreads) {
-        const long long a = (long long) I * T + i, b = (long long) J * T + i;
-        laI[i] = a < s.K ? s.la[a] : (kMiss | (kMiss << 16));
-        laJ[i] = b < s.K ? s.la[b] : (kMiss | (kMiss << 16));
-        if (RANKED) {
-            rkI[i] = a < s.K ? s.cls_rank[a] : 0;
-            rkJ[i] = b < s.K ? s.cls_rank[b] : 0;
-        }
+    // ---- phase 0: ONE round trip for every index the CTA needs (fixed-size descriptors) --------
+    for (int i = tid; i < 2 * DW; i += kThreads) {
+        const int t = i < DW ? I : J, w = i < DW ? i : i - DW;
+        dI[i] = s.desc[(size_t) t * DW + w];
+    }
+    for (int i = tid; i < 2 * T; i += kThreads) {
+        const int t = i < T ? I : J, k = i < T ? i : i - T;
+        const long long c = (long long) t * T + k;
+        const bool ok = c < s.K;
+        laI[i] = ok ? s.la[c] : (kMiss | (kMiss << 16));
+        piI[2 * i] = ok ? s.pind[2 * c] : -1;
+        piI[2 * i + 1] = ok ? s.pind[2 * c + 1] : -1;
+        if (RANKED) rkI[i] = ok ? s.cls_rank[c] : 0;
     }
     __syncthreads();
+    const int c0I = dI[0], nlI = dI[1], c0J = dJ[0], nlJ = dJ[1];
+    const int32_t *listI = dI + 4, *listJ = dJ + 4;
+    const int nrI = W + nlI;
+    // slow path <=> the two tiles share a parent individual (or it is a diagonal tile)
+    bool slow = (I == J) || dI[2] < 0 || dJ[2] < 0;
+    if (!slow)
+        for (int k = 0; k < dI[2]; k++) slow |= (dI[4 + LMAX + k] == J);
 
-    // ---- 1. stage E[rows(I)][cols(J)] --------------------------------------------------------
+    // ---- phase 1: stage E[rows(I)][cols(J)] with cp.async (second and last global round trip) --
     const double *__restrict__ Gp = s.Gprev;
     const long long ldp = s.ld_prev;
     const int lastrow = (int) (s.K_prev - 1);
-    // (a) all rows x window columns of J: 16-byte chunks, coalesced along the row segment
-    {
+    {   // (a) all rows x window columns of J: 16-byte chunks, half a warp (T=32) per 256-byte segment
         constexpr int CH = W / 2;
-        const int total = nrI * CH;
-        for (int idx = tid; idx < total; idx += kThreads) {
-            const int r = idx / CH, ch = idx - r * CH;
+        for (int r = tid / CH; r < nrI; r += kThreads / CH) {
+            const int ch = tid % CH;
             int row = r < W ? c0I + r : listI[r - W];
             row = row > lastrow ? lastrow : row;
             cp_async16(S + (size_t) r * pitch + 2 * ch, Gp + (long long) row * ldp + c0J + 2 * ch);
         }
     }
-    // (b) window rows of I x list columns of J, through the symmetric entry (list row, window col)
-    {
-        const int total = nlJ * W;
-        for (int idx = tid; idx < total; idx += kThreads) {
-            const int j = idx / W, r = idx - j * W;
+    {   // (b) window rows of I x list columns of J through the symmetric entry (list row, window col)
+        for (int j = tid / W; j < nlJ; j += kThreads / W) {
+            const int r = tid % W;
             cp_async8(S + (size_t) r * pitch + W + j, Gp + (long long) listJ[j] * ldp + c0I + r);
         }
     }
-    // (c) list rows of I x list columns of J: 8-byte gathers (served by L2 across the I sweep)
-    {
-        const int total = nlI * nlJ;
-        for (int idx = tid; idx < total; idx += kThreads) {
-            const int r = idx / nlJ, j = idx - r * nlJ;
-            cp_async8(S + (size_t) (W + r) * pitch + W + j, Gp + (long long) listI[r] * ldp + listJ[j]);
+    {   // (c) list rows of I x list columns of J: 8-byte gathers (L2-resident across the I sweep)
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int j0 = 0; j0 < nlJ; j0 += 32) {
+            const int j = j0 + lane;
+            if (j < nlJ) {
+                const long long col = listJ[j];
+                for (int r = warp; r < nlI; r += kThreads / 32)
+                    cp_async8(S + (size_t) (W + r) * pitch + W + j, Gp + (long long) listI[r] * ldp + col);
+            }
         }
     }
     cp_async_wait_all();
     __syncthreads();
 
-    // ---- 2. same individual on both sides -> self kinship (lib/compute.cpp:522-528) ----------
-    if (I == J) {
-        for (int r = tid; r < nrI; r += kThreads)
-            if (rowI[r] >= 0) {
-                const int c = r < W ? c0I + r : listI[r - W];
-                S[(size_t) r * pitch + r] = s.dprev[c];
-            }
-    } else {
-        const int oI = s.hot_off[I], nhI = s.hot_off[I + 1] - oI;
-        const int oJ = s.hot_off[J], nhJ = s.hot_off[J + 1] - oJ;
-        const int total = nhI * nhJ;
-        for (int idx = tid; idx < total; idx += kThreads) {
-            const int hi = s.hot_idx[oI + idx / nhJ], hj = s.hot_idx[oJ + idx % nhJ];
-            if (rowI[hi] == rowJ[hj]) {
-                const int c = hi < W ? c0I + hi : listI[hi - W];
-                S[(size_t) hi * pitch + hj] = s.dprev[c];
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- 3. gather-average from shared memory; 4. store tile (I,J) ----------------------------
-    const long long ldn = s.ld_new;
-    for (int cell = tid; cell < T * T; cell += kThreads) {
-        const int a = cell / T, b = cell - a * T;
+    // ---- phase 2: gather-average from shared memory -----------------------------------------
+    constexpr int CPT = T * T / kThreads;      // cells per thread
+    double v[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const int cell = tid + k * kThreads;
+        const int a = cell / T, b = cell % T;
         const int la = laI[a], lb = laJ[b];
         const int a0 = la & 0xFFFF, a1 = (la >> 16) & 0xFFFF;
         const int b0 = lb & 0xFFFF, b1 = (lb >> 16) & 0xFFFF;
-        const double p = (a0 != kMiss && b0 != kMiss) ? S[(size_t) a0 * pitch + b0] : 0.0;
-        const double q = (a1 != kMiss && b0 != kMiss) ? S[(size_t) a1 * pitch + b0] : 0.0;
-        const double r = (a0 != kMiss && b1 != kMiss) ? S[(size_t) a0 * pitch + b1] : 0.0;
-        const double t = (a1 != kMiss && b1 != kMiss) ? S[(size_t) a1 * pitch + b1] : 0.0;
-        double v;
+        double p, q, r, t;
+        if (!slow) {
+            p = fetch_e<false>(S, pitch, a0, b0, 0, 0, nullptr, 0);
+            q = fetch_e<false>(S, pitch, a1, b0, 0, 0, nullptr, 0);
+            r = fetch_e<false>(S, pitch, a0, b1, 0, 0, nullptr, 0);
+            t = fetch_e<false>(S, pitch, a1, b1, 0, 0, nullptr, 0);
+        } else {
+            const int ia0 = piI[2 * a], ia1 = piI[2 * a + 1], ib0 = piJ[2 * b], ib1 = piJ[2 * b + 1];
+            const int ca0 = a0 == kMiss ? 0 : (a0 < W ? c0I + a0 : listI[a0 - W]);
+            const int ca1 = a1 == kMiss ? 0 : (a1 < W ? c0I + a1 : listI[a1 - W]);
+            p = fetch_e<true>(S, pitch, a0, b0, ia0, ib0, s.dprev, ca0);
+            q = fetch_e<true>(S, pitch, a1, b0, ia1, ib0, s.dprev, ca1);
+            r = fetch_e<true>(S, pitch, a0, b1, ia0, ib1, s.dprev, ca0);
+            t = fetch_e<true>(S, pitch, a1, b1, ia1, ib1, s.dprev, ca1);
+        }
         if (RANKED) {
             // lib/compute.cpp:529-548: the higher-ranked individual is expanded first, so the
             // inner sums run over the LOWER-ranked one's parents.
-            v = (rkI[a] < rkJ[b]) ? 0.25 * (__dadd_rn(p, q) + __dadd_rn(r, t))
-                                  : 0.25 * (__dadd_rn(p, r) + __dadd_rn(q, t));
+            v[k] = (rkI[a] < rkJ[b]) ? 0.25 * (__dadd_rn(p, q) + __dadd_rn(r, t))
+                                     : 0.25 * (__dadd_rn(p, r) + __dadd_rn(q, t));
         } else {
-            v = 0.25 * ((p + q) + (r + t));
+            v[k] = 0.25 * ((p + q) + (r + t));
         }
-        O[a * (T + 1) + b] = v;
-        const long long ga = (long long) I * T + a, gb = (long long) J * T + b;
-        if (ga < s.K && gb < s.K) s.Gnew[ga * ldn + gb] = v;
     }
     if (I == J) {
-        // self kinship of the new classes: kept -> copy (== 0.5 + 0.5*phi(f,m) recomputed, bitwise);
-        // new -> 0.5 + 0.5*phi(father, mother) iff both known (lib/compute.cpp:553-568)
+        // self kinship of the new classes (lib/compute.cpp:553-568): a kept individual copies its
+        // value (bitwise what the reference recomputes); a new one gets 1/2 + 1/2 phi(father, mother)
         for (int a = tid; a < T; a += kThreads) {
             const long long ga = (long long) I * T + a;
             if (ga < s.K) {
                 const int la = laI[a];
                 const int a0 = la & 0xFFFF, a1 = (la >> 16) & 0xFFFF;
+                const int i0 = piI[2 * a], i1 = piI[2 * a + 1];
                 double d = 0.5;
-                if (a0 != kMiss && a0 == a1) d = S[(size_t) a0 * pitch + a0];
+                if (a0 != kMiss && i0 == i1) d = s.dprev[a0 < W ? c0I + a0 : listI[a0 - W]];
                 else if (a0 != kMiss && a1 != kMiss) d = 0.5 + 0.5 * S[(size_t) a0 * pitch + a1];
                 s.dnew[ga] = d;
             }
         }
-    } else {
+    }
+    // ---- phase 3: store tile (I,J) from registers; mirror (J,I) transposed through smem --------
+    const long long ldn = s.ld_new;
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        const int cell = tid + k * kThreads;
+        const int a = cell / T, b = cell % T;
+        const long long ga = (long long) I * T + a, gb = (long long) J * T + b;
+        if (ga < s.K && gb < s.K) s.Gnew[ga * ldn + gb] = v[k];
+    }
+    if (I != J) {
+        __syncthreads();                       // everyone is done reading S
+        double *O = S;
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int cell = tid + k * kThreads;
+            O[(cell / T) * (T + 1) + cell % T] = v[k];
+        }
         __syncthreads();
-        for (int cell = tid; cell < T * T; cell += kThreads) {
-            const int b = cell / T, a = cell - b * T;        // lanes run along a -> coalesced mirror rows
+#pragma unroll
+        for (int k = 0; k < CPT; k++) {
+            const int cell = tid + k * kThreads;
+            const int b = cell / T, a = cell % T;          // lanes run along a -> coalesced mirror rows
             const long long ga = (long long) I * T + a, gb = (long long) J * T + b;
             if (ga < s.K && gb < s.K) s.Gnew[gb * ldn + ga] = O[a * (T + 1) + b];
         }
@@ -299,14 +321,13 @@ cudaError_t launch_step_t(const StepDev &s, size_t smem, cudaStream_t st) {
 
 size_t step_smem_bytes(int tile, int nr_max, bool ranked, int *pitch_out) {
     (void) ranked;
-    const int W = tile, LMAX = 2 * tile, NRMAX = W + LMAX;
+    const int W = tile, LMAX = 2 * tile, DW = 4 + LMAX + kConf;
     int pitch = (nr_max + 1) & ~1;
-    if (pitch < W) pitch = W;
+    if (pitch < W + 2) pitch = W + 2;          // also large enough for the T x (T+1) transpose buffer
     while (pitch % 4 != 2) pitch += 2;         // even (16-byte rows) and 2 mod 4 (transposed stores: 2-way at worst)
     if (pitch_out) *pitch_out = pitch;
     size_t bytes = (size_t) pitch * pitch * sizeof(double);
-    bytes += (size_t) tile * (tile + 1) * sizeof(double);
-    bytes += (size_t) (2 * LMAX + 2 * NRMAX + 4 * tile) * sizeof(int32_t);
+    bytes += (size_t) (2 * DW + 2 * tile + 4 * tile + 2 * tile) * sizeof(int32_t);
     return bytes;
 }
 

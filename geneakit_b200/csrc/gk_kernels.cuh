@@ -13,14 +13,10 @@ struct StepDev {
     double *dnew;            // self kinship of each class of cut g
     int64_t ld_prev, ld_new;
     int64_t K_prev, K;
-    const int32_t *la;       // K: local parent indices la0 | la1 << 16 (0xFFFF = unknown parent)
+    const int32_t *la;       // K: local parent rows la0 | la1 << 16 (0xFFFF = unknown parent)
+    const int32_t *pind;     // 2K: parent individuals (identity rule), -1 unknown
     const int32_t *cls_rank; // K: rank of the class's individual (RANKED only)
-    const int32_t *c0;       // nt: window start column in Gprev (multiple of 4)
-    const int32_t *nl;       // nt: list length
-    const int32_t *list;     // nt * LMAX: scattered parent rows in Gprev
-    const int32_t *rowind;   // nt * (W + LMAX): individual occupying each local row, -1 none
-    const int32_t *hot_off;  // nt + 1
-    const int32_t *hot_idx;  // local rows whose individual is a parent in more than one tile
+    const int32_t *desc;     // nt * (4 + LMAX + kConf): c0, nl, nconf, 0, list[LMAX], conf[kConf]
     int32_t nt;
     int32_t pitch;           // shared-memory pitch (doubles) of the staged block
 };

@@ -15,9 +15,10 @@
 //   * order: classes are stored sorted by the class index of their first known parent in the
 //     previous matrix, so that the parents of T consecutive classes form a contiguous WINDOW
 //     of T columns (coalesced / bulk-copied) plus a LIST of scattered rows (the other parent).
-//   * tiles: per tile of T classes: window start, list, the individual occupying each local
-//     row (for the "same individual -> self kinship" rule of lib/compute.cpp:522-528) and the
-//     local indices of each class's two parents.
+//   * tiles: per tile of T classes one fixed-size DESCRIPTOR (window start, list of scattered
+//     parent rows, and the few other tiles that share a parent INDIVIDUAL with it: only those
+//     tile pairs need the "same individual -> self kinship" rule of lib/compute.cpp:522-528),
+//     and per class the local indices + individual ids of its two parents.
 //
 // Rounding: for G-1 <= 26 cuts below the founders every value is a dyadic rational that FP64
 // holds exactly, so any evaluation order is bit-identical to the reference.  Deeper pedigrees
@@ -33,6 +34,8 @@
 namespace gk {
 
 constexpr int kMissing = 0xFFFF;   // la half-word for "parent unknown"
+constexpr int kConfMax = 12;       // conflicting tiles stored inline per descriptor
+inline int desc_words(int tile) { return 4 + 2 * tile + kConfMax; }
 
 struct StepPlan {
     int64_t K = 0, ld = 0, K_prev = 0;
@@ -42,13 +45,10 @@ struct StepPlan {
     int64_t P_ref = 0;        // distinct individuals of cut g-1 that are a parent of a NEW member
     int64_t P_cls = 0;        // distinct rows of matrix g-1 read by this step
     int64_t kept_cls = 0;     // singleton classes of kept individuals
-    std::vector<int32_t> la;        // K : la0 | la1 << 16
+    std::vector<int32_t> la;        // K : la0 | la1 << 16 (local row of each parent's class, 0xFFFF unknown)
+    std::vector<int32_t> pind;      // 2K : parent individuals (pi0, pi1), -1 unknown; kept: both = the individual
     std::vector<int32_t> cls_rank;  // K (ranked mode only)
-    std::vector<int32_t> c0, nl;    // nt
-    std::vector<int32_t> list;      // nt * lmax
-    std::vector<int32_t> rowind;    // nt * (win + lmax)
-    std::vector<int32_t> hot_off;   // nt + 1
-    std::vector<int32_t> hot_idx;
+    std::vector<int32_t> desc;      // nt * desc_words : [c0, nl, nconf(-1 = always check), 0, list[lmax], conf[kConfMax]]
 };
 
 struct PhiPlan {
@@ -164,12 +164,11 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
 
     std::vector<int32_t> cls_prev(n, -1), cls_cur(n, -1);
     std::vector<int32_t> win_stamp(n, -1);            // step stamp: individual is a window parent for the next cut
-    std::vector<int64_t> loc_stamp(n, -1);            // (step << 32 | tile) stamp for local row assignment
-    std::vector<int32_t> loc_idx(n, 0);
-    std::vector<int32_t> use_stamp(n, -1), use_tile(n, 0);
-    std::vector<uint8_t> use_multi(n, 0);
+    std::vector<int64_t> use_stamp(n, -1);            // (step << 32 | tile): individual already recorded for this tile
+    std::vector<std::pair<int32_t, int32_t>> use_pairs, conf_pairs;
     std::vector<int32_t> par_stamp(n, -1);            // distinct-parent counting
     std::vector<int32_t> prow_stamp;                  // distinct parent rows of previous matrix
+    std::vector<int32_t> row_tile_stamp, row_loc;     // per previous-matrix row: local list slot in the current tile
 
     std::vector<int32_t> cur;                         // members of the current cut (individuals)
     std::vector<MemberRec> mem;
@@ -266,11 +265,14 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
 
         // ---- tiles (only steps that read a previous matrix) -------------------------------
         if (g > 0) {
+            const int DW = desc_words(T);
             S.la.assign(K, 0);
-            S.c0.assign(S.nt, 0); S.nl.assign(S.nt, 0);
-            S.list.assign((size_t) S.nt * LMAX, 0);
-            S.rowind.assign((size_t) S.nt * (W + LMAX), -1);
+            S.pind.assign((size_t) 2 * K, -1);
+            S.desc.assign((size_t) S.nt * DW, 0);
             prow_stamp.assign((size_t) S.K_prev, -1);
+            row_tile_stamp.assign((size_t) S.K_prev, -1);
+            row_loc.assign((size_t) S.K_prev, 0);
+            use_pairs.clear();
             int64_t pcls = 0, keptc = 0;
             for (int t = 0; t < S.nt; t++) {
                 const int64_t lo = (int64_t) t * T, hi = std::min<int64_t>(K, lo + T);
@@ -279,47 +281,60 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
                     const ClassRec &c = cls[order[pos]];
                     if (c.pc0 >= 0 && (cmin < 0 || c.pc0 < cmin)) cmin = c.pc0;
                 }
-                const int32_t c0 = cmin < 0 ? 0 : (cmin & ~3);
-                S.c0[t] = c0;
-                int32_t *rowind = &S.rowind[(size_t) t * (W + LMAX)];
-                int32_t *list = &S.list[(size_t) t * LMAX];
+                const int32_t c0 = cmin < 0 ? 0 : (cmin & ~1);      // even: 16-byte aligned row segments
+                int32_t *desc = &S.desc[(size_t) t * DW];
+                int32_t *list = desc + 4;
                 int nl = 0;
-                const int64_t stamp = ((int64_t) g << 32) | (uint32_t) t;
                 for (int64_t pos = lo; pos < hi; pos++) {
                     const ClassRec &c = cls[order[pos]];
                     if (c.kept) keptc++;
                     int la[2] = { kMissing, kMissing };
                     for (int q = 0; q < 2; q++) {
                         const int32_t pi = q ? c.pi1 : c.pi0, pc = q ? c.pc1 : c.pc0;
+                        S.pind[2 * pos + q] = pi;
                         if (pi < 0) continue;
                         if (prow_stamp[pc] != g) { prow_stamp[pc] = g; pcls++; }
-                        if (loc_stamp[pi] == stamp) { la[q] = loc_idx[pi]; continue; }
-                        int loc;
-                        if (pc >= c0 && pc < c0 + W && rowind[pc - c0] < 0) {
-                            loc = pc - c0;
-                        } else {
-                            loc = W + nl;
+                        if (use_stamp[pi] != ((int64_t) g << 32 | (uint32_t) t)) {
+                            use_stamp[pi] = ((int64_t) g << 32 | (uint32_t) t);
+                            use_pairs.emplace_back(pi, t);
+                        }
+                        if (pc >= c0 && pc < c0 + W) { la[q] = pc - c0; continue; }
+                        if (row_tile_stamp[pc] != t) {
+                            row_tile_stamp[pc] = t; row_loc[pc] = W + nl;
                             list[nl++] = pc;
                         }
-                        rowind[loc] = pi;
-                        loc_stamp[pi] = stamp; loc_idx[pi] = loc;
-                        la[q] = loc;
-                        if (use_stamp[pi] != g) { use_stamp[pi] = g; use_tile[pi] = t; use_multi[pi] = 0; }
-                        else if (use_tile[pi] != t) use_multi[pi] = 1;
+                        la[q] = row_loc[pc];
                     }
                     S.la[pos] = la[0] | (la[1] << 16);
                 }
-                S.nl[t] = nl;
+                desc[0] = c0; desc[1] = nl; desc[2] = 0; desc[3] = 0;
                 S.nr_max = std::max(S.nr_max, W + nl);
             }
             S.P_cls = pcls; S.kept_cls = keptc;
-            S.hot_off.assign(S.nt + 1, 0);
-            for (int t = 0; t < S.nt; t++) {
-                const int32_t *rowind = &S.rowind[(size_t) t * (W + LMAX)];
-                const int nr = W + S.nl[t];
-                for (int i = 0; i < nr; i++)
-                    if (rowind[i] >= 0 && use_multi[rowind[i]]) S.hot_idx.push_back(i);
-                S.hot_off[t + 1] = (int32_t) S.hot_idx.size();
+            // tiles that share a parent individual: only those pairs apply the identity rule
+            std::sort(use_pairs.begin(), use_pairs.end());
+            conf_pairs.clear();
+            for (size_t i = 0; i < use_pairs.size();) {
+                size_t j = i + 1;
+                while (j < use_pairs.size() && use_pairs[j].first == use_pairs[i].first) j++;
+                for (size_t a = i; a < j; a++)
+                    for (size_t b = i; b < j; b++)
+                        if (a != b) conf_pairs.emplace_back(use_pairs[a].second, use_pairs[b].second);
+                i = j;
+            }
+            std::sort(conf_pairs.begin(), conf_pairs.end());
+            conf_pairs.erase(std::unique(conf_pairs.begin(), conf_pairs.end()), conf_pairs.end());
+            for (size_t i = 0; i < conf_pairs.size();) {
+                size_t j = i;
+                const int t = conf_pairs[i].first;
+                while (j < conf_pairs.size() && conf_pairs[j].first == t) j++;
+                int32_t *desc = &S.desc[(size_t) t * DW];
+                if ((int) (j - i) > kConfMax) desc[2] = -1;
+                else {
+                    desc[2] = (int32_t) (j - i);
+                    for (size_t q = i; q < j; q++) desc[4 + LMAX + (q - i)] = conf_pairs[q].second;
+                }
+                i = j;
             }
         }
         cur.swap(nxt);

@@ -142,15 +142,11 @@ void gk_phi_free(gk_phi_job *job);
  * plan that the kernels consume.  See DESIGN.md "Plan layout". */
 typedef struct gk_step_view {
     int64_t K, ld, K_prev;
-    int32_t nt, tile, win, lmax, nr_max;
-    const int32_t *la;        /* K entries: la0 | (la1 << 16), 0xFFFF = missing parent */
+    int32_t nt, tile, win, lmax, nr_max, desc_words, conf_max, reserved;
+    const int32_t *la;        /* K entries: local parent rows la0 | (la1 << 16), 0xFFFF = missing parent */
+    const int32_t *pind;      /* 2K entries: parent individuals (ranks), -1 = missing; kept member: both = itself */
     const int32_t *cls_rank;  /* K entries (ranked mode) or NULL */
-    const int32_t *c0;        /* nt */
-    const int32_t *nl;        /* nt */
-    const int32_t *list;      /* nt * lmax : class index in the previous matrix */
-    const int32_t *rowind;    /* nt * (win + lmax) : individual (rank) occupying each local row, -1 none */
-    const int32_t *hot_off;   /* nt + 1 */
-    const int32_t *hot_idx;   /* local rows whose individual is a parent in more than one tile */
+    const int32_t *desc;      /* nt * desc_words: [c0, nl, nconf (-1: always check), 0, list[lmax], conf[conf_max]] */
 } gk_step_view;
 int gk_phi_step_view(gk_phi_job *job, int32_t step, gk_step_view *view);  /* step = 1 .. G-1 */
 /* Final expansion map: for caller entry i the class row in the last matrix and the individual. */

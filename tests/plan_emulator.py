@@ -2,8 +2,9 @@
 
 It executes, on the CPU and tile pair by tile pair, exactly what phi_step_kernel does with the
 plan arrays exposed by gk_phi_step_view -- including the symmetric fetch of the window x list
-block, the "same individual" patch and the mirror store -- so the host planner can be checked
-against the oracle without a GPU.  It is NOT a product path (it lives under tests/)."""
+block, the conflict-list gated "same individual" rule and the mirror store -- so the host
+planner can be checked against the oracle without a GPU.  It is NOT a product path (it lives
+under tests/)."""
 import ctypes as C
 
 import numpy as np
@@ -15,7 +16,7 @@ MISS = 0xFFFF
 
 
 def _arr(ptr, n):
-    if n == 0:
+    if n == 0 or not ptr:
         return np.zeros(0, dtype=np.int32)
     return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
 
@@ -23,15 +24,16 @@ def _arr(ptr, n):
 def step_view(job, g):
     v = _lib.gk_step_view()
     check(lib.gk_phi_step_view(job._h, g, C.byref(v)))
-    nt, W, LMAX = v.nt, v.win, v.lmax
-    d = dict(K=v.K, ld=v.ld, K_prev=v.K_prev, nt=nt, T=v.tile, W=W, LMAX=LMAX, nr_max=v.nr_max)
+    nt, W, LMAX, DW = v.nt, v.win, v.lmax, v.desc_words
+    d = dict(K=v.K, ld=v.ld, K_prev=v.K_prev, nt=nt, T=v.tile, W=W, LMAX=LMAX, nr_max=v.nr_max,
+             conf_max=v.conf_max)
     d["la"] = _arr(v.la, v.K)
+    d["pind"] = _arr(v.pind, 2 * v.K).reshape(-1, 2)
     d["cls_rank"] = _arr(v.cls_rank, v.K) if v.cls_rank else None
-    d["c0"], d["nl"] = _arr(v.c0, nt), _arr(v.nl, nt)
-    d["list"] = _arr(v.list, nt * LMAX).reshape(nt, LMAX)
-    d["rowind"] = _arr(v.rowind, nt * (W + LMAX)).reshape(nt, W + LMAX)
-    d["hot_off"] = _arr(v.hot_off, nt + 1)
-    d["hot_idx"] = _arr(v.hot_idx, int(d["hot_off"][-1]))
+    desc = _arr(v.desc, nt * DW).reshape(nt, DW)
+    d["c0"], d["nl"], d["nconf"] = desc[:, 0], desc[:, 1], desc[:, 2]
+    d["list"] = desc[:, 4:4 + LMAX]
+    d["conf"] = desc[:, 4 + LMAX:]
     return d
 
 
@@ -54,6 +56,7 @@ def emulate(job):
         Gn = np.full((K, K), np.nan)
         dn = np.full(K, np.nan)
         la0, la1 = v["la"] & 0xFFFF, (v["la"] >> 16) & 0xFFFF
+        pind = v["pind"]
         last = Gp.shape[0] - 1
 
         def local_classes(t):
@@ -69,31 +72,30 @@ def emulate(job):
                 S[:, :W] = Gp[np.ix_(rI, cJ[:W])]                      # rows x window columns
                 S[:W, W:] = Gp[np.ix_(cJ[W:], rI[:W])].T               # window rows x list cols via symmetry
                 S[W:, W:] = Gp[np.ix_(rI[W:], cJ[W:])]                 # list x list
-                indI, indJ = v["rowind"][I], v["rowind"][J]
-                if I == J:
-                    for r in range(W + nlI):
-                        if indI[r] >= 0:
-                            S[r, r] = dp[rI[r]]
-                else:
-                    hI = v["hot_idx"][v["hot_off"][I]:v["hot_off"][I + 1]]
-                    hJ = v["hot_idx"][v["hot_off"][J]:v["hot_off"][J + 1]]
-                    for hi in hI:
-                        for hj in hJ:
-                            if indI[hi] == indJ[hj]:
-                                S[hi, hj] = dp[rI[hi]]
+                slow = I == J or v["nconf"][I] < 0 or v["nconf"][J] < 0 or \
+                    J in [int(x) for x in v["conf"][I, :max(v["nconf"][I], 0)]]
                 a_lo, a_hi = I * T, min(K, I * T + T)
                 b_lo, b_hi = J * T, min(K, J * T + T)
-                A0, A1 = la0[a_lo:a_hi], la1[a_lo:a_hi]
-                B0, B1 = la0[b_lo:b_hi], la1[b_lo:b_hi]
+                A = [la0[a_lo:a_hi], la1[a_lo:a_hi]]
+                B = [la0[b_lo:b_hi], la1[b_lo:b_hi]]
+                IA = [pind[a_lo:a_hi, 0], pind[a_lo:a_hi, 1]]
+                IB = [pind[b_lo:b_hi, 0], pind[b_lo:b_hi, 1]]
 
-                def take(ra, cb):
+                def take(qa, qb):
+                    ra, cb = A[qa], B[qb]
                     ok = (ra[:, None] != MISS) & (cb[None, :] != MISS)
                     rr = np.where(ra == MISS, 0, ra)
                     cc = np.where(cb == MISS, 0, cb)
                     assert rr.max(initial=0) < S.shape[0] and cc.max(initial=0) < S.shape[1]
-                    return np.where(ok, S[np.ix_(rr, cc)], 0.0)
+                    val = S[np.ix_(rr, cc)]
+                    same = IA[qa][:, None] == IB[qb][None, :]
+                    if not slow:
+                        assert not (ok & same).any(), "identity needed on a fast-path tile pair"
+                    else:
+                        val = np.where(same, dp[rI[rr]][:, None], val)
+                    return np.where(ok, val, 0.0)
 
-                p, q, r, s = take(A0, B0), take(A1, B0), take(A0, B1), take(A1, B1)
+                p, q, r, s = take(0, 0), take(1, 0), take(0, 1), take(1, 1)
                 if v["cls_rank"] is not None:
                     lower = v["cls_rank"][a_lo:a_hi][:, None] < v["cls_rank"][b_lo:b_hi][None, :]
                     out = np.where(lower, 0.25 * ((p + q) + (r + s)), 0.25 * ((p + r) + (q + s)))
@@ -104,9 +106,9 @@ def emulate(job):
                     Gn[b_lo:b_hi, a_lo:a_hi] = out.T
                 else:
                     for k in range(a_hi - a_lo):
-                        x0, x1 = A0[k], A1[k]
-                        if x0 != MISS and x0 == x1:
-                            dn[a_lo + k] = S[x0, x0]
+                        x0, x1 = A[0][k], A[1][k]
+                        if x0 != MISS and IA[0][k] == IA[1][k]:
+                            dn[a_lo + k] = dp[rI[x0]]
                         elif x0 != MISS and x1 != MISS:
                             dn[a_lo + k] = 0.5 + 0.5 * S[x0, x1]
                         else:
