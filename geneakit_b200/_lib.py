@@ -39,8 +39,10 @@ class gk_step_view(C.Structure):
     _fields_ = [("K", C.c_int64), ("ld", C.c_int64), ("K_prev", C.c_int64),
                 ("nt", C.c_int32), ("tile", C.c_int32), ("win", C.c_int32), ("lmax", C.c_int32),
                 ("nr_max", C.c_int32), ("desc_words", C.c_int32), ("conf_max", C.c_int32),
-                ("reserved", C.c_int32),
-                ("la", _P), ("pind", _P), ("cls_rank", _P), ("desc", _P)]
+                ("ranked", C.c_int32),
+                ("off_list", C.c_int32), ("off_conf", C.c_int32), ("off_la", C.c_int32),
+                ("off_pind", C.c_int32), ("off_rank", C.c_int32), ("reserved", C.c_int32),
+                ("desc", _P)]
 
 
 def make_opts(device=-1, verbose=False, compress=-1, tile=0, rank=0, world=1, stream=None):

@@ -32,7 +32,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 
 constexpr int64_t kPadDoubles = 256;   // slack after every matrix: window reads may run past the last row
 
-struct StepOffsets { size_t la, pind, rank, desc; };
+struct StepOffsets { size_t desc; };
 
 }  // namespace
 
@@ -55,8 +55,6 @@ struct gk_phi_job {
     size_t off_final_cls = 0, off_final_ind = 0, ints_count = 0;
     int nblocks_expand = 0;
     std::vector<cudaEvent_t> ev;      // G + 2 events around the step launches
-    std::vector<size_t> smem;
-    std::vector<int> pitch;
     int64_t device_bytes = 0;
     int64_t launches = 0;
 };
@@ -206,17 +204,6 @@ int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, c
         delete j;
         return fail(code, msg);
     }
-    // a 64-class tile plan whose staged block would not fit in shared memory falls back to 32
-    if (j->plan.tile == 64) {
-        bool fits = true;
-        for (int g = 1; g < j->plan.G; g++)
-            if (gk::step_smem_bytes(64, j->plan.steps[g].nr_max, j->plan.ranked, nullptr) > 200 * 1024) fits = false;
-        if (!fits && !gk::build_phi_plan(n, sire, dam, m, pro, j->opts.compress, 32, j->plan)) {
-            std::string msg = j->plan.error;
-            delete j;
-            return fail(GK_ERR_ARG, msg);
-        }
-    }
     *job = j;
     return GK_OK;
 }
@@ -229,7 +216,7 @@ int gk_phi_upload(gk_phi_job *j) {
     std::call_once(g_cfg_once, [] { g_cfg_err = gk::configure_kernels(); });
     if (g_cfg_err != cudaSuccess) return cuda_fail(g_cfg_err, "cudaFuncSetAttribute (is this an sm_100 device?)");
     gk::PhiPlan &P = j->plan;
-    const int G = P.G, T = P.tile, W = P.win, LMAX = P.lmax;
+    const int G = P.G;
     if (j->opts.stream) j->stream = (cudaStream_t) j->opts.stream;
     else { GK_CUDA(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking)); j->own_stream = true; }
 
@@ -242,14 +229,10 @@ int gk_phi_upload(gk_phi_job *j) {
         return o;
     };
     j->off.assign(G, StepOffsets{});
-    j->smem.assign(G, 0);
-    j->pitch.assign(G, 0);
     for (int g = 1; g < G; g++) {
         gk::StepPlan &S = P.steps[g];
         StepOffsets &o = j->off[g];
-        o.la = push(S.la); o.pind = push(S.pind); o.rank = push(S.cls_rank); o.desc = push(S.desc);
-        j->smem[g] = gk::step_smem_bytes(T, S.nr_max, P.ranked, &j->pitch[g]);
-        if (j->smem[g] > 227 * 1024) return fail(GK_ERR_ARG, "tile plan needs more than 227 KB of shared memory; use tile=32");
+        o.desc = push(S.desc);
     }
     j->off_final_cls = push(P.final_cls);
     j->off_final_ind = push(P.final_ind);
@@ -258,7 +241,6 @@ int gk_phi_upload(gk_phi_job *j) {
     GK_CUDA(cudaMemcpyAsync(j->ints, arena.data(), arena.size() * sizeof(int32_t), cudaMemcpyHostToDevice, j->stream));
     GK_CUDA(cudaStreamSynchronize(j->stream));
     j->device_bytes += (int64_t) arena.size() * 4;
-    (void) W; (void) LMAX;
 
     // ---- matrices: two ping-pong buffers; the m x m result aliases the one the last step read --
     int64_t need[2] = { 0, 0 };
@@ -323,11 +305,10 @@ int gk_phi_run(gk_phi_job *j) {
             d.Gnew = j->buf[g & 1]; d.dnew = j->dvec[g & 1];
             d.ld_prev = P.steps[g - 1].ld; d.ld_new = S.ld;
             d.K_prev = S.K_prev; d.K = S.K;
-            d.la = j->ints + o.la; d.pind = j->ints + o.pind; d.cls_rank = j->ints + o.rank;
             d.desc = j->ints + o.desc;
-            d.nt = S.nt; d.pitch = j->pitch[g];
+            d.nt = S.nt; d.npairs = (int64_t) S.nt * (S.nt + 1) / 2;
             GK_CUDA(cudaEventRecord(j->ev[g], st));
-            GK_CUDA(gk::launch_step(d, P.tile, P.ranked, j->smem[g], st));
+            GK_CUDA(gk::launch_step(d, P.ranked, st));
             launches++;
         }
         GK_CUDA(cudaEventRecord(j->ev[G], st));
@@ -412,7 +393,7 @@ int gk_phi_get_stats(gk_phi_job *j, gk_phi_stats *s) {
     int64_t ints = (int64_t) P.final_cls.size() + (int64_t) P.final_ind.size();
     for (int g = 1; g < P.G; g++) {
         const gk::StepPlan &S = P.steps[g];
-        ints += (int64_t) (S.la.size() + S.pind.size() + S.cls_rank.size() + S.desc.size());
+        ints += (int64_t) S.desc.size();
     }
     s->plan_bytes = ints * 4;
     return GK_OK;
@@ -458,8 +439,9 @@ int gk_phi_step_view(gk_phi_job *j, int32_t step, gk_step_view *v) {
     const gk::StepPlan &S = P.steps[step];
     v->K = S.K; v->ld = S.ld; v->K_prev = S.K_prev; v->nt = S.nt; v->tile = P.tile; v->win = P.win;
     v->lmax = P.lmax; v->nr_max = S.nr_max;
-    v->la = S.la.data(); v->pind = S.pind.data(); v->cls_rank = P.ranked ? S.cls_rank.data() : nullptr;
-    v->desc = S.desc.data(); v->desc_words = gk::desc_words(P.tile); v->conf_max = gk::kConfMax;
+    v->desc = S.desc.data(); v->desc_words = gk::kDescWords; v->conf_max = gk::kConfMax;
+    v->off_list = gk::kDescList; v->off_conf = gk::kDescConf; v->off_la = gk::kDescLa;
+    v->off_pind = gk::kDescPind; v->off_rank = gk::kDescRank; v->ranked = P.ranked ? 1 : 0;
     return GK_OK;
 }
 int gk_phi_final_view(gk_phi_job *j, const int32_t **cls, const int32_t **ind, int64_t *K_last) {

@@ -7,19 +7,24 @@
 // for one pair of adjacent vertex cuts.  It is an HBM-bound FP64 gather-average: per output
 // cell 4 gathered reads, 3 DADD + 1 DMUL, one 8-byte store.  Tensor cores are not used.
 //
-// One CTA = one unordered pair (I >= J) of T-class tiles of the NEW matrix:
-//   1. stage  E[rows(I)][cols(J)]  of the PREVIOUS matrix in shared memory with cp.async
-//      (LDGSTS): rows(I)/cols(J) = the tile's contiguous parent WINDOW (16-byte coalesced row
-//      segments) + its LIST of scattered parent rows.  The window-rows x list-cols block is
-//      fetched through the symmetric entry (list row, window column) so it is coalesced too;
-//      only list x list is an 8-byte gather.
-//   2. patch "same individual" entries with the self kinship (rule :522-528),
-//   3. out[a][b] = 1/4 * ((p + q) + (r + s)) from shared memory (RANKED: grouping chosen per
-//      pair by rank, reproducing the reference's rounding on pedigrees deeper than 26),
-//   4. store tile (I,J) and, transposed through shared memory, its mirror (J,I): both coalesced.
-// Tile pairs are enumerated I-major so CTAs resident together share rows(I): the scattered
+// PERSISTENT kernel, 2 CTAs per SM, each walking the unordered tile pairs (I >= J) of the new
+// matrix with a grid stride, software-pipelined with cp.async (LDGSTS) groups:
+//   while pair k is being computed from shared-memory buffer k&1, the gathers of pair k+1 are
+//   landing in the other buffer and the descriptors of pair k+2 in a third descriptor slot.
+// Per pair:
+//   1. stage  E[rows(I)][cols(J)]  of the PREVIOUS matrix: rows(I)/cols(J) = the tile's
+//      contiguous parent WINDOW (16-byte coalesced row segments) + its LIST of scattered parent
+//      rows.  The window-rows x list-cols block is fetched through the symmetric entry
+//      (list row, window column) so it is coalesced too; only list x list is an 8-byte gather.
+//   2. out[a][b] = 1/4 * ((p + q) + (r + s)) from shared memory (RANKED: grouping chosen per pair
+//      by rank, reproducing the reference's rounding on pedigrees deeper than 26); tile pairs
+//      that share a parent individual apply "same individual -> self kinship" (:522-528),
+//   3. store tile (I,J) from registers and, transposed through shared memory, its mirror (J,I):
+//      both coalesced.
+// Pairs are enumerated I-major, so the CTAs resident at any time share rows(I): the scattered
 // list rows are then served from the 126 MB L2 instead of HBM.
 #include "gk_kernels.cuh"
+#include "gk_plan.hpp"
 
 namespace gk {
 
@@ -27,6 +32,11 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMiss = 0xFFFF;
+constexpr int T = kTile, W = kWin, CAP = kListCap, DW = kDescWords;
+constexpr int NR = W + CAP;          // 72 staged rows / columns at most
+constexpr int PITCH = NR + 2;        // 74 doubles: 16-byte aligned rows, 2 mod 4 (transposed stores 2-way at worst)
+constexpr int kStageDoubles = NR * PITCH;
+constexpr size_t kStepSmem = (size_t) (2 * kStageDoubles + T * (T + 1)) * sizeof(double) + (size_t) 3 * 2 * DW * sizeof(int32_t);
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
@@ -36,175 +46,172 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
     unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-constexpr int kConf = 12;      // == gk::kConfMax (gk_plan.hpp)
+__device__ __forceinline__ void pair_to_tiles(long long k, int &I, int &J) {
+    int i = (int) ((sqrt(8.0 * (double) k + 1.0) - 1.0) * 0.5);
+    while ((long long) i * (i + 1) / 2 > k) --i;
+    while ((long long) (i + 1) * (i + 2) / 2 <= k) ++i;
+    I = i;
+    J = (int) (k - (long long) i * (i + 1) / 2);
+}
+
+// descriptors of tiles I and J of pair k -> slot (2*DW int32), 16-byte cp.async
+__device__ __forceinline__ void load_desc(int32_t *slot, const int32_t *desc, long long k, int tid) {
+    int I, J;
+    pair_to_tiles(k, I, J);
+    constexpr int CH = DW / 4;
+    if (tid < 2 * CH) {
+        const int t = tid < CH ? I : J, c = tid < CH ? tid : tid - CH;
+        cp_async16(slot + (tid < CH ? 0 : DW) + 4 * c, desc + (size_t) t * DW + 4 * c);
+    }
+}
+
+// stage E[rows(I)][cols(J)] of the previous matrix into S (all asynchronous)
+__device__ __forceinline__ void issue_gathers(double *S, const int32_t *dI, const int32_t *dJ,
+                                              const double *__restrict__ Gp, long long ldp, int lastrow, int tid) {
+    const int c0I = dI[0], nlI = dI[1] & 0xFFFF, c0J = dJ[0], nlJ = dJ[1] & 0xFFFF;
+    const int32_t *listI = dI + kDescList, *listJ = dJ + kDescList;
+    const int nrI = W + nlI;
+    {   // (a) all rows x window columns of J: 16-byte chunks, half a warp per 256-byte row segment
+        constexpr int CH = W / 2;
+        const int ch = tid % CH;
+        const double *colbase = Gp + c0J + 2 * ch;
+        for (int r = tid / CH; r < nrI; r += kThreads / CH) {
+            int row = r < W ? c0I + r : listI[r - W];
+            row = row > lastrow ? lastrow : row;
+            cp_async16(S + r * PITCH + 2 * ch, colbase + (long long) row * ldp);
+        }
+    }
+    {   // (b) window rows of I x list columns of J through the symmetric entry (list row, window col)
+        const int r = tid % W;
+        for (int j = tid / W; j < nlJ; j += kThreads / W)
+            cp_async8(S + r * PITCH + W + j, Gp + (long long) listJ[j] * ldp + c0I + r);
+    }
+    {   // (c) list rows of I x list columns of J: 8-byte gathers (L2-resident across the I sweep)
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int j = lane; j < nlJ; j += 32) {
+            const double *colp = Gp + listJ[j];
+            for (int r = warp; r < nlI; r += kThreads / 32)
+                cp_async8(S + (W + r) * PITCH + W + j, colp + (long long) listI[r] * ldp);
+        }
+    }
+}
 
 // E(x, y) of the previous cut for one (row parent, column parent) pair, applying
 // "same individual -> self kinship" (lib/compute.cpp:522-528) when the CTA is on the slow path.
 template <bool CHECK>
-__device__ __forceinline__ double fetch_e(const double *S, int pitch, int ra, int cb, int ia, int ib,
+__device__ __forceinline__ double fetch_e(const double *S, int ra, int cb, int ia, int ib,
                                           const double *dprev, int cls_a) {
     if (ra == kMiss || cb == kMiss) return 0.0;
     if (CHECK && ia == ib) return dprev[cls_a];
-    return S[(size_t) ra * pitch + cb];
+    return S[ra * PITCH + cb];
 }
 
-template <int T, bool RANKED>
-__global__ void __launch_bounds__(kThreads) phi_step_kernel(const StepDev s) {
-    constexpr int W = T, LMAX = 2 * T, DW = 4 + LMAX + kConf;
+template <bool RANKED>
+__global__ void __launch_bounds__(kThreads, 2) phi_step_kernel(const StepDev s) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *Sbuf = reinterpret_cast<double *>(smem_raw);                  // 2 x NR x PITCH
+    double *O = Sbuf + 2 * kStageDoubles;                                 // T x (T+1) transpose buffer
+    int32_t *Dbuf = reinterpret_cast<int32_t *>(O + T * (T + 1));          // 3 slots x (desc I, desc J)
 
-    // ---- which tile pair (I-major: CTAs resident together share rows(I) -> L2 reuse) ----------
-    const long long bid = blockIdx.x;
-    int I = (int) ((sqrt(8.0 * (double) bid + 1.0) - 1.0) * 0.5);
-    while ((long long) I * (I + 1) / 2 > bid) --I;
-    while ((long long) (I + 1) * (I + 2) / 2 <= bid) ++I;
-    const int J = (int) (bid - (long long) I * (I + 1) / 2);
     const int tid = threadIdx.x;
-    const int pitch = s.pitch;
-
-    // ---- shared memory carve-up ----------------------------------------------------------------
-    double *S = reinterpret_cast<double *>(smem_raw);                    // nr_max x pitch; reused as O (T x (T+1))
-    int32_t *dI = reinterpret_cast<int32_t *>(S + (size_t) pitch * pitch); // DW: descriptor of tile I
-    int32_t *dJ = dI + DW;                                                // DW
-    int32_t *laI = dJ + DW;                                               // T
-    int32_t *laJ = laI + T;                                               // T
-    int32_t *piI = laJ + T;                                               // 2T parent individuals
-    int32_t *piJ = piI + 2 * T;                                           // 2T
-    int32_t *rkI = piJ + 2 * T;                                           // T (RANKED)
-    int32_t *rkJ = rkI + T;                                               // T (RANKED)
-
-    // ---- phase 0: ONE round trip for every index the CTA needs (fixed-size descriptors) --------
-    for (int i = tid; i < 2 * DW; i += kThreads) {
-        const int t = i < DW ? I : J, w = i < DW ? i : i - DW;
-        dI[i] = s.desc[(size_t) t * DW + w];
-    }
-    for (int i = tid; i < 2 * T; i += kThreads) {
-        const int t = i < T ? I : J, k = i < T ? i : i - T;
-        const long long c = (long long) t * T + k;
-        const bool ok = c < s.K;
-        laI[i] = ok ? s.la[c] : (kMiss | (kMiss << 16));
-        piI[2 * i] = ok ? s.pind[2 * c] : -1;
-        piI[2 * i + 1] = ok ? s.pind[2 * c + 1] : -1;
-        if (RANKED) rkI[i] = ok ? s.cls_rank[c] : 0;
-    }
-    __syncthreads();
-    const int c0I = dI[0], nlI = dI[1], c0J = dJ[0], nlJ = dJ[1];
-    const int32_t *listI = dI + 4, *listJ = dJ + 4;
-    const int nrI = W + nlI;
-    // slow path <=> the two tiles share a parent individual (or it is a diagonal tile)
-    bool slow = (I == J) || dI[2] < 0 || dJ[2] < 0;
-    if (!slow)
-        for (int k = 0; k < dI[2]; k++) slow |= (dI[4 + LMAX + k] == J);
-
-    // ---- phase 1: stage E[rows(I)][cols(J)] with cp.async (second and last global round trip) --
+    const long long np = s.npairs, stride = gridDim.x;
     const double *__restrict__ Gp = s.Gprev;
-    const long long ldp = s.ld_prev;
+    const long long ldp = s.ld_prev, ldn = s.ld_new;
     const int lastrow = (int) (s.K_prev - 1);
-    {   // (a) all rows x window columns of J: 16-byte chunks, half a warp (T=32) per 256-byte segment
-        constexpr int CH = W / 2;
-        for (int r = tid / CH; r < nrI; r += kThreads / CH) {
-            const int ch = tid % CH;
-            int row = r < W ? c0I + r : listI[r - W];
-            row = row > lastrow ? lastrow : row;
-            cp_async16(S + (size_t) r * pitch + 2 * ch, Gp + (long long) row * ldp + c0J + 2 * ch);
-        }
-    }
-    {   // (b) window rows of I x list columns of J through the symmetric entry (list row, window col)
-        for (int j = tid / W; j < nlJ; j += kThreads / W) {
-            const int r = tid % W;
-            cp_async8(S + (size_t) r * pitch + W + j, Gp + (long long) listJ[j] * ldp + c0I + r);
-        }
-    }
-    {   // (c) list rows of I x list columns of J: 8-byte gathers (L2-resident across the I sweep)
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int j0 = 0; j0 < nlJ; j0 += 32) {
-            const int j = j0 + lane;
-            if (j < nlJ) {
-                const long long col = listJ[j];
-                for (int r = warp; r < nlI; r += kThreads / 32)
-                    cp_async8(S + (size_t) (W + r) * pitch + W + j, Gp + (long long) listI[r] * ldp + col);
-            }
-        }
-    }
+    long long k = blockIdx.x;
+    if (k >= np) return;
+
+    // ---- prologue: descriptors of the first pair, then its gathers + the second pair's descriptors
+    load_desc(Dbuf, s.desc, k, tid);
+    cp_async_commit();
     cp_async_wait_all();
     __syncthreads();
+    issue_gathers(Sbuf, Dbuf, Dbuf + DW, Gp, ldp, lastrow, tid);
+    if (k + stride < np) load_desc(Dbuf + 2 * DW, s.desc, k + stride, tid);
+    cp_async_commit();
 
-    // ---- phase 2: gather-average from shared memory -----------------------------------------
-    constexpr int CPT = T * T / kThreads;      // cells per thread
-    double v[CPT];
+    for (int it = 0; k < np; k += stride, ++it) {
+        const int32_t *dI = Dbuf + (it % 3) * 2 * DW, *dJ = dI + DW;
+        const double *S = Sbuf + (it & 1) * kStageDoubles;
+        cp_async_wait_all();
+        __syncthreads();       // pair k staged, next descriptors landed, everyone done with pair k-1
+        // ---- keep the memory system busy: gathers of pair k+1, descriptors of pair k+2 ----------
+        if (k + stride < np) {
+            const int32_t *nI = Dbuf + ((it + 1) % 3) * 2 * DW;
+            issue_gathers(Sbuf + ((it + 1) & 1) * kStageDoubles, nI, nI + DW, Gp, ldp, lastrow, tid);
+            if (k + 2 * stride < np) load_desc(Dbuf + ((it + 2) % 3) * 2 * DW, s.desc, k + 2 * stride, tid);
+        }
+        cp_async_commit();
+
+        // ---- pair k -----------------------------------------------------------------------------
+        int I, J;
+        pair_to_tiles(k, I, J);
+        const int c0I = dI[0], cntI = dI[1] >> 16, cntJ = dJ[1] >> 16;
+        const long long startI = dI[3], startJ = dJ[3];
+        const int32_t *listI = dI + kDescList;
+        bool slow = (I == J) || dI[2] < 0 || dJ[2] < 0;      // do the two tiles share a parent individual?
+        if (!slow)
+            for (int c = 0; c < dI[2]; c++) slow |= (dI[kDescConf + c] == J);
+
+        constexpr int CPT = T * T / kThreads;                 // 4 cells per thread
+        double v[CPT];
 #pragma unroll
-    for (int k = 0; k < CPT; k++) {
-        const int cell = tid + k * kThreads;
-        const int a = cell / T, b = cell % T;
-        const int la = laI[a], lb = laJ[b];
-        const int a0 = la & 0xFFFF, a1 = (la >> 16) & 0xFFFF;
-        const int b0 = lb & 0xFFFF, b1 = (lb >> 16) & 0xFFFF;
-        double p, q, r, t;
-        if (!slow) {
-            p = fetch_e<false>(S, pitch, a0, b0, 0, 0, nullptr, 0);
-            q = fetch_e<false>(S, pitch, a1, b0, 0, 0, nullptr, 0);
-            r = fetch_e<false>(S, pitch, a0, b1, 0, 0, nullptr, 0);
-            t = fetch_e<false>(S, pitch, a1, b1, 0, 0, nullptr, 0);
-        } else {
-            const int ia0 = piI[2 * a], ia1 = piI[2 * a + 1], ib0 = piJ[2 * b], ib1 = piJ[2 * b + 1];
-            const int ca0 = a0 == kMiss ? 0 : (a0 < W ? c0I + a0 : listI[a0 - W]);
-            const int ca1 = a1 == kMiss ? 0 : (a1 < W ? c0I + a1 : listI[a1 - W]);
-            p = fetch_e<true>(S, pitch, a0, b0, ia0, ib0, s.dprev, ca0);
-            q = fetch_e<true>(S, pitch, a1, b0, ia1, ib0, s.dprev, ca1);
-            r = fetch_e<true>(S, pitch, a0, b1, ia0, ib1, s.dprev, ca0);
-            t = fetch_e<true>(S, pitch, a1, b1, ia1, ib1, s.dprev, ca1);
+        for (int c = 0; c < CPT; c++) {
+            const int cell = tid + c * kThreads;
+            const int a = cell / T, b = cell % T;
+            const int la = dI[kDescLa + a], lb = dJ[kDescLa + b];
+            const int a0 = la & 0xFFFF, a1 = (la >> 16) & 0xFFFF;
+            const int b0 = lb & 0xFFFF, b1 = (lb >> 16) & 0xFFFF;
+            double p, q, r, t;
+            if (!slow) {
+                p = fetch_e<false>(S, a0, b0, 0, 0, nullptr, 0);
+                q = fetch_e<false>(S, a1, b0, 0, 0, nullptr, 0);
+                r = fetch_e<false>(S, a0, b1, 0, 0, nullptr, 0);
+                t = fetch_e<false>(S, a1, b1, 0, 0, nullptr, 0);
+            } else {
+                const int ia0 = dI[kDescPind + 2 * a], ia1 = dI[kDescPind + 2 * a + 1];
+                const int ib0 = dJ[kDescPind + 2 * b], ib1 = dJ[kDescPind + 2 * b + 1];
+                const int ca0 = a0 == kMiss ? 0 : (a0 < W ? c0I + a0 : listI[a0 - W]);
+                const int ca1 = a1 == kMiss ? 0 : (a1 < W ? c0I + a1 : listI[a1 - W]);
+                p = fetch_e<true>(S, a0, b0, ia0, ib0, s.dprev, ca0);
+                q = fetch_e<true>(S, a1, b0, ia1, ib0, s.dprev, ca1);
+                r = fetch_e<true>(S, a0, b1, ia0, ib1, s.dprev, ca0);
+                t = fetch_e<true>(S, a1, b1, ia1, ib1, s.dprev, ca1);
+            }
+            if (RANKED) {
+                // lib/compute.cpp:529-548: the higher-ranked individual is expanded first, so the
+                // inner sums run over the LOWER-ranked one's parents.
+                v[c] = (dI[kDescRank + a] < dJ[kDescRank + b]) ? 0.25 * (__dadd_rn(p, q) + __dadd_rn(r, t))
+                                                              : 0.25 * (__dadd_rn(p, r) + __dadd_rn(q, t));
+            } else {
+                v[c] = 0.25 * ((p + q) + (r + t));
+            }
+            if (a < cntI && b < cntJ) s.Gnew[(startI + a) * ldn + startJ + b] = v[c];
+            O[a * (T + 1) + b] = v[c];
         }
-        if (RANKED) {
-            // lib/compute.cpp:529-548: the higher-ranked individual is expanded first, so the
-            // inner sums run over the LOWER-ranked one's parents.
-            v[k] = (rkI[a] < rkJ[b]) ? 0.25 * (__dadd_rn(p, q) + __dadd_rn(r, t))
-                                     : 0.25 * (__dadd_rn(p, r) + __dadd_rn(q, t));
-        } else {
-            v[k] = 0.25 * ((p + q) + (r + t));
-        }
-    }
-    if (I == J) {
-        // self kinship of the new classes (lib/compute.cpp:553-568): a kept individual copies its
-        // value (bitwise what the reference recomputes); a new one gets 1/2 + 1/2 phi(father, mother)
-        for (int a = tid; a < T; a += kThreads) {
-            const long long ga = (long long) I * T + a;
-            if (ga < s.K) {
-                const int la = laI[a];
+        if (I == J) {
+            // self kinship of the new classes (lib/compute.cpp:553-568): a kept individual copies its
+            // value (bitwise what the reference recomputes); a new one gets 1/2 + 1/2 phi(father, mother)
+            if (tid < cntI) {
+                const int la = dI[kDescLa + tid];
                 const int a0 = la & 0xFFFF, a1 = (la >> 16) & 0xFFFF;
-                const int i0 = piI[2 * a], i1 = piI[2 * a + 1];
+                const int i0 = dI[kDescPind + 2 * tid], i1 = dI[kDescPind + 2 * tid + 1];
                 double d = 0.5;
                 if (a0 != kMiss && i0 == i1) d = s.dprev[a0 < W ? c0I + a0 : listI[a0 - W]];
-                else if (a0 != kMiss && a1 != kMiss) d = 0.5 + 0.5 * S[(size_t) a0 * pitch + a1];
-                s.dnew[ga] = d;
+                else if (a0 != kMiss && a1 != kMiss) d = 0.5 + 0.5 * S[a0 * PITCH + a1];
+                s.dnew[startI + tid] = d;
             }
-        }
-    }
-    // ---- phase 3: store tile (I,J) from registers; mirror (J,I) transposed through smem --------
-    const long long ldn = s.ld_new;
+        } else {
+            __syncthreads();
 #pragma unroll
-    for (int k = 0; k < CPT; k++) {
-        const int cell = tid + k * kThreads;
-        const int a = cell / T, b = cell % T;
-        const long long ga = (long long) I * T + a, gb = (long long) J * T + b;
-        if (ga < s.K && gb < s.K) s.Gnew[ga * ldn + gb] = v[k];
-    }
-    if (I != J) {
-        __syncthreads();                       // everyone is done reading S
-        double *O = S;
-#pragma unroll
-        for (int k = 0; k < CPT; k++) {
-            const int cell = tid + k * kThreads;
-            O[(cell / T) * (T + 1) + cell % T] = v[k];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < CPT; k++) {
-            const int cell = tid + k * kThreads;
-            const int b = cell / T, a = cell % T;          // lanes run along a -> coalesced mirror rows
-            const long long ga = (long long) I * T + a, gb = (long long) J * T + b;
-            if (ga < s.K && gb < s.K) s.Gnew[gb * ldn + ga] = O[a * (T + 1) + b];
+            for (int c = 0; c < CPT; c++) {
+                const int cell = tid + c * kThreads;
+                const int b = cell / T, a = cell % T;          // lanes run along a -> coalesced mirror rows
+                if (a < cntI && b < cntJ) s.Gnew[(startJ + b) * ldn + startI + a] = O[a * (T + 1) + b];
+            }
         }
     }
 }
@@ -310,41 +317,34 @@ __global__ void __launch_bounds__(256) gc_gather_kernel(const double *V, long lo
     for (long long c = threadIdx.x; c < a; c += 256) out[i * a + c] = r >= 0 ? V[(long long) r * ld + c] : 0.0;
 }
 
-template <int T, bool RANKED>
-cudaError_t launch_step_t(const StepDev &s, size_t smem, cudaStream_t st) {
-    const long long pairs = (long long) s.nt * (s.nt + 1) / 2;
-    phi_step_kernel<T, RANKED><<<(unsigned) pairs, kThreads, smem, st>>>(s);
-    return cudaGetLastError();
-}
-
 }  // namespace
 
-size_t step_smem_bytes(int tile, int nr_max, bool ranked, int *pitch_out) {
-    (void) ranked;
-    const int W = tile, LMAX = 2 * tile, DW = 4 + LMAX + kConf;
-    int pitch = (nr_max + 1) & ~1;
-    if (pitch < W + 2) pitch = W + 2;          // also large enough for the T x (T+1) transpose buffer
-    while (pitch % 4 != 2) pitch += 2;         // even (16-byte rows) and 2 mod 4 (transposed stores: 2-way at worst)
-    if (pitch_out) *pitch_out = pitch;
-    size_t bytes = (size_t) pitch * pitch * sizeof(double);
-    bytes += (size_t) (2 * DW + 2 * tile + 4 * tile + 2 * tile) * sizeof(int32_t);
-    return bytes;
-}
+size_t step_smem_bytes() { return kStepSmem; }
+
+static int g_step_grid[2] = { 0, 0 };
 
 cudaError_t configure_kernels() {
-    const int maxsmem = 227 * 1024;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(phi_step_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem))) return e;
-    if ((e = cudaFuncSetAttribute(phi_step_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem))) return e;
-    if ((e = cudaFuncSetAttribute(phi_step_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem))) return e;
-    if ((e = cudaFuncSetAttribute(phi_step_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem))) return e;
+    if ((e = cudaFuncSetAttribute(phi_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kStepSmem))) return e;
+    if ((e = cudaFuncSetAttribute(phi_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kStepSmem))) return e;
+    int dev = 0, sms = 0, occ = 0;
+    if ((e = cudaGetDevice(&dev))) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev))) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phi_step_kernel<false>, kThreads, kStepSmem))) return e;
+    g_step_grid[0] = sms * (occ > 0 ? occ : 1);            // persistent: one wave, every CTA resident
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phi_step_kernel<true>, kThreads, kStepSmem))) return e;
+    g_step_grid[1] = sms * (occ > 0 ? occ : 1);
     return cudaSuccess;
 }
 
-cudaError_t launch_step(const StepDev &s, int tile, bool ranked, size_t smem, cudaStream_t st) {
+cudaError_t launch_step(const StepDev &s, bool ranked, cudaStream_t st) {
     if (s.nt <= 0) return cudaSuccess;
-    if (tile == 64) return ranked ? launch_step_t<64, true>(s, smem, st) : launch_step_t<64, false>(s, smem, st);
-    return ranked ? launch_step_t<32, true>(s, smem, st) : launch_step_t<32, false>(s, smem, st);
+    long long grid = g_step_grid[ranked ? 1 : 0];
+    if (grid <= 0) grid = 296;
+    if (grid > s.npairs) grid = s.npairs;
+    if (ranked) phi_step_kernel<true><<<(unsigned) grid, kThreads, kStepSmem, st>>>(s);
+    else phi_step_kernel<false><<<(unsigned) grid, kThreads, kStepSmem, st>>>(s);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_init(double *G0, double *d0, int64_t K0, int64_t ld0, cudaStream_t st) {

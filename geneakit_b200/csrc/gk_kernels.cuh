@@ -5,7 +5,7 @@
 
 namespace gk {
 
-// Everything one recurrence step needs, by value (fits the 4 KB kernel-parameter space).
+// Everything one recurrence step needs, by value.
 struct StepDev {
     const double *Gprev;     // K_prev x ld_prev class matrix of cut g-1 (row-major, symmetric)
     const double *dprev;     // self kinship of each class of cut g-1
@@ -13,12 +13,9 @@ struct StepDev {
     double *dnew;            // self kinship of each class of cut g
     int64_t ld_prev, ld_new;
     int64_t K_prev, K;
-    const int32_t *la;       // K: local parent rows la0 | la1 << 16 (0xFFFF = unknown parent)
-    const int32_t *pind;     // 2K: parent individuals (identity rule), -1 unknown
-    const int32_t *cls_rank; // K: rank of the class's individual (RANKED only)
-    const int32_t *desc;     // nt * (4 + LMAX + kConf): c0, nl, nconf, 0, list[LMAX], conf[kConf]
+    const int32_t *desc;     // nt tile descriptors of kDescWords int32 (layout: gk_plan.hpp)
+    int64_t npairs;          // nt*(nt+1)/2 unordered tile pairs
     int32_t nt;
-    int32_t pitch;           // shared-memory pitch (doubles) of the staged block
 };
 
 struct ExpandDev {
@@ -33,8 +30,8 @@ struct ExpandDev {
     int32_t single_cut;      // 1: every proband is a top founder -> 0.5*I (lib/compute.cpp:655-661)
 };
 
-size_t step_smem_bytes(int tile, int nr_max, bool ranked, int *pitch_out);
-cudaError_t launch_step(const StepDev &s, int tile, bool ranked, size_t smem, cudaStream_t st);
+size_t step_smem_bytes();
+cudaError_t launch_step(const StepDev &s, bool ranked, cudaStream_t st);
 cudaError_t launch_init(double *G0, double *d0, int64_t K0, int64_t ld0, cudaStream_t st);
 cudaError_t launch_expand(const ExpandDev &e, int *nblocks_out, cudaStream_t st);
 cudaError_t launch_mean_finish(const double *partials, int nblocks, double *sums /*2*/, cudaStream_t st);

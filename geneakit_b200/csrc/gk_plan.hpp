@@ -35,7 +35,19 @@ namespace gk {
 
 constexpr int kMissing = 0xFFFF;   // la half-word for "parent unknown"
 constexpr int kConfMax = 12;       // conflicting tiles stored inline per descriptor
-inline int desc_words(int tile) { return 4 + 2 * tile + kConfMax; }
+constexpr int kTile = 32;          // classes per tile (at most)
+constexpr int kWin = 32;           // window width (columns of the previous matrix)
+constexpr int kListCap = 40;       // scattered parent rows per tile (a tile is closed early rather than exceed it)
+// Tile descriptor, int32 words (16-byte aligned blocks, fetched with cp.async):
+//   [0] c0  [1] nl | count << 16  [2] nconf (-1: always apply the identity rule)  [3] first class
+//   [4, 4+cap)  list   [.., +kConfMax) conflicting tiles   [.., +T) la   [.., +2T) pind   [.., +T) rank
+constexpr int kDescList = 4;
+constexpr int kDescConf = kDescList + kListCap;
+constexpr int kDescLa = kDescConf + kConfMax;
+constexpr int kDescPind = kDescLa + kTile;
+constexpr int kDescRank = kDescPind + 2 * kTile;
+constexpr int kDescWords = kDescRank + kTile;      // 184 words = 736 bytes
+static_assert(kDescWords % 4 == 0, "descriptor must be a multiple of 16 bytes");
 
 struct StepPlan {
     int64_t K = 0, ld = 0, K_prev = 0;
@@ -45,15 +57,13 @@ struct StepPlan {
     int64_t P_ref = 0;        // distinct individuals of cut g-1 that are a parent of a NEW member
     int64_t P_cls = 0;        // distinct rows of matrix g-1 read by this step
     int64_t kept_cls = 0;     // singleton classes of kept individuals
-    std::vector<int32_t> la;        // K : la0 | la1 << 16 (local row of each parent's class, 0xFFFF unknown)
-    std::vector<int32_t> pind;      // 2K : parent individuals (pi0, pi1), -1 unknown; kept: both = the individual
-    std::vector<int32_t> cls_rank;  // K (ranked mode only)
-    std::vector<int32_t> desc;      // nt * desc_words : [c0, nl, nconf(-1 = always check), 0, list[lmax], conf[kConfMax]]
+    std::vector<int32_t> cls_rank;  // K (ranked mode only; host copy, the device reads the descriptors)
+    std::vector<int32_t> desc;      // nt * kDescWords
 };
 
 struct PhiPlan {
     int32_t n = 0, m = 0, G = 0;
-    int tile = 32, win = 32, lmax = 64;
+    int tile = kTile, win = kWin, lmax = kListCap;
     bool compressed = true, ranked = false, single_cut = false;
     std::vector<StepPlan> steps;            // steps[g], g = 0 .. G-1 (steps[0]: K only)
     std::vector<int32_t> final_cls, final_ind;   // m entries, caller order
@@ -145,10 +155,8 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
     P.single_cut = (G == 1);
     P.ranked = (G - 1 > 26);
     P.compressed = P.ranked ? false : (compress_opt != 0);
-    P.tile = (tile_opt == 64) ? 64 : 32;
-    P.win = P.tile;
-    P.lmax = 2 * P.tile;
-    const int T = P.tile, W = P.win, LMAX = P.lmax;
+    (void) tile_opt;                   // one tile shape: 32 classes, 32-column window, <= 40 list rows
+    const int T = kTile, W = kWin;
     P.steps.resize(G);
 
     // members entering each cut: enter(x) = G-1-maxp, last cut containing x = G-1-minp
@@ -253,7 +261,6 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
         });
         S.K = K;
         S.ld = round_up(std::max<int64_t>(K, 1), 16);
-        S.nt = (int) ((K + T - 1) / T);
         for (int64_t pos = 0; pos < K; pos++) {
             const ClassRec &c = cls[order[pos]];
             for (int32_t q = c.member_begin; q < c.member_end; q++) cls_cur[mem[q].ind] = (int32_t) pos;
@@ -265,51 +272,77 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
 
         // ---- tiles (only steps that read a previous matrix) -------------------------------
         if (g > 0) {
-            const int DW = desc_words(T);
-            S.la.assign(K, 0);
-            S.pind.assign((size_t) 2 * K, -1);
-            S.desc.assign((size_t) S.nt * DW, 0);
+            const int DW = kDescWords;
+            S.desc.clear();
             prow_stamp.assign((size_t) S.K_prev, -1);
             row_tile_stamp.assign((size_t) S.K_prev, -1);
             row_loc.assign((size_t) S.K_prev, 0);
             use_pairs.clear();
             int64_t pcls = 0, keptc = 0;
-            for (int t = 0; t < S.nt; t++) {
-                const int64_t lo = (int64_t) t * T, hi = std::min<int64_t>(K, lo + T);
+            int t = -1, nl = 0, cnt = 0;
+            int32_t c0 = 0;
+            uint8_t tile_section = 0;
+            auto open_tile = [&](int64_t pos) {
+                t++;
+                S.desc.resize((size_t) (t + 1) * DW, 0);
+                int32_t *d = &S.desc[(size_t) t * DW];
+                for (int k = 0; k < T; k++) { d[kDescLa + k] = kMissing | (kMissing << 16); d[kDescPind + 2 * k] = d[kDescPind + 2 * k + 1] = -1; }
+                // window start: first known father class from here on inside this section (sorted => the minimum)
                 int32_t cmin = -1;
-                for (int64_t pos = lo; pos < hi; pos++) {
-                    const ClassRec &c = cls[order[pos]];
-                    if (c.pc0 >= 0 && (cmin < 0 || c.pc0 < cmin)) cmin = c.pc0;
+                for (int64_t q = pos; q < K && q < pos + T; q++) {
+                    const ClassRec &c = cls[order[q]];
+                    if (c.section != cls[order[pos]].section) break;
+                    if (c.pc0 >= 0) { cmin = c.pc0; break; }
                 }
-                const int32_t c0 = cmin < 0 ? 0 : (cmin & ~1);      // even: 16-byte aligned row segments
-                int32_t *desc = &S.desc[(size_t) t * DW];
-                int32_t *list = desc + 4;
-                int nl = 0;
-                for (int64_t pos = lo; pos < hi; pos++) {
-                    const ClassRec &c = cls[order[pos]];
-                    if (c.kept) keptc++;
-                    int la[2] = { kMissing, kMissing };
+                c0 = cmin < 0 ? 0 : (cmin & ~1);                 // even: 16-byte aligned row segments
+                nl = 0; cnt = 0; tile_section = cls[order[pos]].section;
+                d[0] = c0; d[3] = (int32_t) pos;
+            };
+            auto close_tile = [&]() {
+                int32_t *d = &S.desc[(size_t) t * DW];
+                d[1] = nl | (cnt << 16);
+                S.nr_max = std::max(S.nr_max, W + nl);
+            };
+            for (int64_t pos = 0; pos < K; pos++) {
+                const ClassRec &c = cls[order[pos]];
+                // how many new list rows would this class add to the open tile?
+                auto extra = [&]() {
+                    int e = 0;
+                    int32_t seen = -1;
                     for (int q = 0; q < 2; q++) {
                         const int32_t pi = q ? c.pi1 : c.pi0, pc = q ? c.pc1 : c.pc0;
-                        S.pind[2 * pos + q] = pi;
-                        if (pi < 0) continue;
-                        if (prow_stamp[pc] != g) { prow_stamp[pc] = g; pcls++; }
-                        if (use_stamp[pi] != ((int64_t) g << 32 | (uint32_t) t)) {
-                            use_stamp[pi] = ((int64_t) g << 32 | (uint32_t) t);
-                            use_pairs.emplace_back(pi, t);
-                        }
-                        if (pc >= c0 && pc < c0 + W) { la[q] = pc - c0; continue; }
-                        if (row_tile_stamp[pc] != t) {
-                            row_tile_stamp[pc] = t; row_loc[pc] = W + nl;
-                            list[nl++] = pc;
-                        }
-                        la[q] = row_loc[pc];
+                        if (pi < 0 || (pc >= c0 && pc < c0 + W) || row_tile_stamp[pc] == t || pc == seen) continue;
+                        seen = pc; e++;
                     }
-                    S.la[pos] = la[0] | (la[1] << 16);
+                    return e;
+                };
+                if (t < 0 || cnt == T || c.section != tile_section || nl + extra() > kListCap) {
+                    if (t >= 0) close_tile();
+                    open_tile(pos);
                 }
-                desc[0] = c0; desc[1] = nl; desc[2] = 0; desc[3] = 0;
-                S.nr_max = std::max(S.nr_max, W + nl);
+                int32_t *d = &S.desc[(size_t) t * DW];
+                if (c.kept) keptc++;
+                int la[2] = { kMissing, kMissing };
+                for (int q = 0; q < 2; q++) {
+                    const int32_t pi = q ? c.pi1 : c.pi0, pc = q ? c.pc1 : c.pc0;
+                    d[kDescPind + 2 * cnt + q] = pi;
+                    if (pi < 0) continue;
+                    if (prow_stamp[pc] != g) { prow_stamp[pc] = g; pcls++; }
+                    const int64_t us = ((int64_t) g << 32) | (uint32_t) t;
+                    if (use_stamp[pi] != us) { use_stamp[pi] = us; use_pairs.emplace_back(pi, t); }
+                    if (pc >= c0 && pc < c0 + W) { la[q] = pc - c0; continue; }
+                    if (row_tile_stamp[pc] != t) {
+                        row_tile_stamp[pc] = t; row_loc[pc] = W + nl;
+                        d[kDescList + nl++] = pc;
+                    }
+                    la[q] = row_loc[pc];
+                }
+                d[kDescLa + cnt] = la[0] | (la[1] << 16);
+                d[kDescRank + cnt] = P.ranked ? c.first_member : 0;
+                cnt++;
             }
+            if (t >= 0) close_tile();
+            S.nt = t + 1;
             S.P_cls = pcls; S.kept_cls = keptc;
             // tiles that share a parent individual: only those pairs apply the identity rule
             std::sort(use_pairs.begin(), use_pairs.end());
@@ -326,13 +359,13 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
             conf_pairs.erase(std::unique(conf_pairs.begin(), conf_pairs.end()), conf_pairs.end());
             for (size_t i = 0; i < conf_pairs.size();) {
                 size_t j = i;
-                const int t = conf_pairs[i].first;
-                while (j < conf_pairs.size() && conf_pairs[j].first == t) j++;
-                int32_t *desc = &S.desc[(size_t) t * DW];
-                if ((int) (j - i) > kConfMax) desc[2] = -1;
+                const int tt = conf_pairs[i].first;
+                while (j < conf_pairs.size() && conf_pairs[j].first == tt) j++;
+                int32_t *d = &S.desc[(size_t) tt * DW];
+                if ((int) (j - i) > kConfMax) d[2] = -1;
                 else {
-                    desc[2] = (int32_t) (j - i);
-                    for (size_t q = i; q < j; q++) desc[4 + LMAX + (q - i)] = conf_pairs[q].second;
+                    d[2] = (int32_t) (j - i);
+                    for (size_t q = i; q < j; q++) d[kDescConf + (q - i)] = conf_pairs[q].second;
                 }
                 i = j;
             }

@@ -142,11 +142,17 @@ void gk_phi_free(gk_phi_job *job);
  * plan that the kernels consume.  See DESIGN.md "Plan layout". */
 typedef struct gk_step_view {
     int64_t K, ld, K_prev;
-    int32_t nt, tile, win, lmax, nr_max, desc_words, conf_max, reserved;
-    const int32_t *la;        /* K entries: local parent rows la0 | (la1 << 16), 0xFFFF = missing parent */
-    const int32_t *pind;      /* 2K entries: parent individuals (ranks), -1 = missing; kept member: both = itself */
-    const int32_t *cls_rank;  /* K entries (ranked mode) or NULL */
-    const int32_t *desc;      /* nt * desc_words: [c0, nl, nconf (-1: always check), 0, list[lmax], conf[conf_max]] */
+    int32_t nt, tile, win, lmax, nr_max, desc_words, conf_max, ranked;
+    int32_t off_list, off_conf, off_la, off_pind, off_rank, reserved;
+    /* nt descriptors of desc_words int32:
+     *   [0] c0 (window start column in the previous matrix, even)   [1] nl | count << 16
+     *   [2] nconf (-1: always apply the identity rule)              [3] first class (row of the new matrix)
+     *   [off_list, +lmax)  scattered parent rows of the previous matrix
+     *   [off_conf, +conf_max) tiles sharing a parent individual with this one
+     *   [off_la, +tile)   per class: local parent rows la0 | la1 << 16 (0xFFFF = unknown parent)
+     *   [off_pind, +2*tile) per class: parent individuals (ranks), -1 unknown; kept member: both = itself
+     *   [off_rank, +tile) per class: rank of its individual (ranked mode) */
+    const int32_t *desc;
 } gk_step_view;
 int gk_phi_step_view(gk_phi_job *job, int32_t step, gk_step_view *view);  /* step = 1 .. G-1 */
 /* Final expansion map: for caller entry i the class row in the last matrix and the individual. */

@@ -24,16 +24,17 @@ def _arr(ptr, n):
 def step_view(job, g):
     v = _lib.gk_step_view()
     check(lib.gk_phi_step_view(job._h, g, C.byref(v)))
-    nt, W, LMAX, DW = v.nt, v.win, v.lmax, v.desc_words
-    d = dict(K=v.K, ld=v.ld, K_prev=v.K_prev, nt=nt, T=v.tile, W=W, LMAX=LMAX, nr_max=v.nr_max,
-             conf_max=v.conf_max)
-    d["la"] = _arr(v.la, v.K)
-    d["pind"] = _arr(v.pind, 2 * v.K).reshape(-1, 2)
-    d["cls_rank"] = _arr(v.cls_rank, v.K) if v.cls_rank else None
+    nt, W, LMAX, DW, T = v.nt, v.win, v.lmax, v.desc_words, v.tile
+    d = dict(K=v.K, ld=v.ld, K_prev=v.K_prev, nt=nt, T=T, W=W, LMAX=LMAX, nr_max=v.nr_max,
+             conf_max=v.conf_max, ranked=bool(v.ranked))
     desc = _arr(v.desc, nt * DW).reshape(nt, DW)
-    d["c0"], d["nl"], d["nconf"] = desc[:, 0], desc[:, 1], desc[:, 2]
-    d["list"] = desc[:, 4:4 + LMAX]
-    d["conf"] = desc[:, 4 + LMAX:]
+    d["c0"], d["nl"], d["cnt"] = desc[:, 0], desc[:, 1] & 0xFFFF, desc[:, 1] >> 16
+    d["nconf"], d["start"] = desc[:, 2], desc[:, 3]
+    d["list"] = desc[:, v.off_list:v.off_list + LMAX]
+    d["conf"] = desc[:, v.off_conf:v.off_conf + v.conf_max]
+    d["la"] = desc[:, v.off_la:v.off_la + T]
+    d["pind"] = desc[:, v.off_pind:v.off_pind + 2 * T].reshape(nt, T, 2)
+    d["rank"] = desc[:, v.off_rank:v.off_rank + T]
     return d
 
 
@@ -53,10 +54,10 @@ def emulate(job):
         v = step_view(job, g)
         K, T, W, nt = v["K"], v["T"], v["W"], v["nt"]
         assert v["K_prev"] == Gp.shape[0]
+        assert int(v["cnt"].sum()) == K and np.array_equal(v["start"], np.concatenate([[0], np.cumsum(v["cnt"])[:-1]]))
+        assert v["nl"].max(initial=0) <= v["LMAX"] and v["cnt"].max(initial=0) <= T
         Gn = np.full((K, K), np.nan)
         dn = np.full(K, np.nan)
-        la0, la1 = v["la"] & 0xFFFF, (v["la"] >> 16) & 0xFFFF
-        pind = v["pind"]
         last = Gp.shape[0] - 1
 
         def local_classes(t):
@@ -66,20 +67,21 @@ def emulate(job):
 
         for I in range(nt):
             rI, nlI = local_classes(I)
+            nI, sI = v["cnt"][I], v["start"][I]
             for J in range(I + 1):
                 cJ, nlJ = local_classes(J)
+                nJ, sJ = v["cnt"][J], v["start"][J]
                 S = np.empty((W + nlI, W + nlJ))
                 S[:, :W] = Gp[np.ix_(rI, cJ[:W])]                      # rows x window columns
                 S[:W, W:] = Gp[np.ix_(cJ[W:], rI[:W])].T               # window rows x list cols via symmetry
                 S[W:, W:] = Gp[np.ix_(rI[W:], cJ[W:])]                 # list x list
                 slow = I == J or v["nconf"][I] < 0 or v["nconf"][J] < 0 or \
                     J in [int(x) for x in v["conf"][I, :max(v["nconf"][I], 0)]]
-                a_lo, a_hi = I * T, min(K, I * T + T)
-                b_lo, b_hi = J * T, min(K, J * T + T)
-                A = [la0[a_lo:a_hi], la1[a_lo:a_hi]]
-                B = [la0[b_lo:b_hi], la1[b_lo:b_hi]]
-                IA = [pind[a_lo:a_hi, 0], pind[a_lo:a_hi, 1]]
-                IB = [pind[b_lo:b_hi, 0], pind[b_lo:b_hi, 1]]
+                laI, laJ = v["la"][I, :nI], v["la"][J, :nJ]
+                A = [laI & 0xFFFF, (laI >> 16) & 0xFFFF]
+                B = [laJ & 0xFFFF, (laJ >> 16) & 0xFFFF]
+                IA = [v["pind"][I, :nI, 0], v["pind"][I, :nI, 1]]
+                IB = [v["pind"][J, :nJ, 0], v["pind"][J, :nJ, 1]]
 
                 def take(qa, qb):
                     ra, cb = A[qa], B[qb]
@@ -96,23 +98,23 @@ def emulate(job):
                     return np.where(ok, val, 0.0)
 
                 p, q, r, s = take(0, 0), take(1, 0), take(0, 1), take(1, 1)
-                if v["cls_rank"] is not None:
-                    lower = v["cls_rank"][a_lo:a_hi][:, None] < v["cls_rank"][b_lo:b_hi][None, :]
+                if v["ranked"]:
+                    lower = v["rank"][I, :nI][:, None] < v["rank"][J, :nJ][None, :]
                     out = np.where(lower, 0.25 * ((p + q) + (r + s)), 0.25 * ((p + r) + (q + s)))
                 else:
                     out = 0.25 * ((p + q) + (r + s))
-                Gn[a_lo:a_hi, b_lo:b_hi] = out
+                Gn[sI:sI + nI, sJ:sJ + nJ] = out
                 if I != J:
-                    Gn[b_lo:b_hi, a_lo:a_hi] = out.T
+                    Gn[sJ:sJ + nJ, sI:sI + nI] = out.T
                 else:
-                    for k in range(a_hi - a_lo):
+                    for k in range(nI):
                         x0, x1 = A[0][k], A[1][k]
                         if x0 != MISS and IA[0][k] == IA[1][k]:
-                            dn[a_lo + k] = dp[rI[x0]]
+                            dn[sI + k] = dp[rI[x0]]
                         elif x0 != MISS and x1 != MISS:
-                            dn[a_lo + k] = 0.5 + 0.5 * S[x0, x1]
+                            dn[sI + k] = 0.5 + 0.5 * S[x0, x1]
                         else:
-                            dn[a_lo + k] = 0.5
+                            dn[sI + k] = 0.5
         assert not np.isnan(Gn).any() and not np.isnan(dn).any()
         Gp, dp = Gn, dn
     out = Gp[np.ix_(fcls, fcls)]

@@ -47,12 +47,11 @@ def test_loader_and_cuts_match_reference(name):
 
 
 @pytest.mark.parametrize("compress", [0, 1])
-@pytest.mark.parametrize("tile", [32, 64])
 @pytest.mark.parametrize("name", golden_names(small_only=True))
-def test_tile_plan_reproduces_reference_phi(name, compress, tile):
+def test_tile_plan_reproduces_reference_phi(name, compress):
     g = load_golden(name)
     ped = _ped(g)
-    job = gk.cgeneakit.DevicePhi(ped, [int(x) for x in g["pro"]], compress=compress, tile=tile)
+    job = gk.cgeneakit.DevicePhi(ped, [int(x) for x in g["pro"]], compress=compress)
     st = job.stats()
     assert job.cut_sizes() == [int(x) for x in g["cut_sizes"]]
     if st["n_cuts"] - 1 > 26:
