@@ -8,17 +8,20 @@
 // cell 4 gathered reads, 3 DADD + 1 DMUL, one 8-byte store.  Tensor cores are not used.
 //
 // PERSISTENT kernel, 2 CTAs per SM, each walking the unordered tile pairs (I >= J) of the new
-// matrix with a grid stride, software-pipelined with cp.async (LDGSTS) groups:
-//   while pair k is being computed from shared-memory buffer k&1, the gathers of pair k+1 are
-//   landing in the other buffer and the descriptors of pair k+2 in a third descriptor slot.
-// Per pair:
-//   1. stage  E[rows(I)][cols(J)]  of the PREVIOUS matrix: rows(I)/cols(J) = the tile's
-//      contiguous parent WINDOW (16-byte coalesced row segments) + its LIST of scattered parent
-//      rows.  The window-rows x list-cols block is fetched through the symmetric entry
-//      (list row, window column) so it is coalesced too; only list x list is an 8-byte gather.
+// matrix with a grid stride, software-pipelined: while pair k is computed from stage buffer
+// k&1, the parent rows of pair k+1 are landing in the other buffer and the descriptors of pair
+// k+2 in a third descriptor slot.  Per pair:
+//   1. stage E[rows(I)][cols(J)] of the PREVIOUS matrix.  rows(I)/cols(J) = the tile's
+//      contiguous parent WINDOW + its LIST of scattered parent rows:
+//        L[r][0..W)   = G[row r of I][window of J]      one 256-byte BULK async copy per row
+//        R[j][0..W)   = G[list row j of J][window of I] (the window x list block through the
+//                       symmetric entry)                one 256-byte BULK async copy per row
+//        R[j][W + r]  = G[list row r of I][list col j of J]   8-byte cp.async gathers (L2 hits)
+//      Bulk copies (cp.async.bulk -> UBLKCP, the TMA engine) complete on an mbarrier.
 //   2. out[a][b] = 1/4 * ((p + q) + (r + s)) from shared memory (RANKED: grouping chosen per pair
-//      by rank, reproducing the reference's rounding on pedigrees deeper than 26); tile pairs
-//      that share a parent individual apply "same individual -> self kinship" (:522-528),
+//      by rank, reproducing the reference's rounding on pedigrees deeper than 26); unknown
+//      parents index an all-zero row; tile pairs that share a parent individual apply
+//      "same individual -> self kinship" (:522-528),
 //   3. store tile (I,J) from registers and, transposed through shared memory, its mirror (J,I):
 //      both coalesced.
 // Pairs are enumerated I-major, so the CTAs resident at any time share rows(I): the scattered
@@ -31,23 +34,48 @@ namespace gk {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kMiss = 0xFFFF;
 constexpr int T = kTile, W = kWin, CAP = kListCap, DW = kDescWords;
-constexpr int NR = W + CAP;          // 72 staged rows / columns at most
-constexpr int PITCH = NR + 2;        // 74 doubles: 16-byte aligned rows, 2 mod 4 (transposed stores 2-way at worst)
-constexpr int kStageDoubles = NR * PITCH;
-constexpr size_t kStepSmem = (size_t) (2 * kStageDoubles + T * (T + 1)) * sizeof(double) + (size_t) 3 * 2 * DW * sizeof(int32_t);
+constexpr int ZIDX = W + CAP;            // local index of the all-zero row / column (unknown parent)
+constexpr int PL = W;                    // L pitch: (W + CAP + 1) rows x W doubles
+constexpr int PR = W + CAP + 2;          // R pitch: (CAP + 1) rows x 74 doubles (16-byte aligned rows)
+constexpr int OFFR = (W + CAP + 1) * PL; // R starts after L inside one stage buffer
+constexpr int kStageDoubles = OFFR + (CAP + 1) * PR;
+constexpr size_t kStepSmem = (size_t) (2 * kStageDoubles + T * (T + 1)) * sizeof(double) +
+                             (size_t) 3 * 2 * DW * sizeof(int32_t) + 2 * sizeof(unsigned long long);
+static_assert(kStageDoubles % 2 == 0 && OFFR % 2 == 0 && PR % 2 == 0, "16-byte alignment of staged rows");
 
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
-    unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// ---- mbarrier + bulk async copy (TMA engine, 1-D) ---------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "GK_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra GK_DONE;\n"
+        "bra GK_WAIT;\n"
+        "GK_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_256(void *smem, const void *gmem, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(W * 8), "r"(smem_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ void pair_to_tiles(long long k, int &I, int &J) {
     int i = (int) ((sqrt(8.0 * (double) k + 1.0) - 1.0) * 0.5);
@@ -56,11 +84,13 @@ __device__ __forceinline__ void pair_to_tiles(long long k, int &I, int &J) {
     I = i;
     J = (int) (k - (long long) i * (i + 1) / 2);
 }
+__device__ __forceinline__ void advance_pair(int &I, int &J, int step) {   // pair index += step (row-major triangle)
+    J += step;
+    while (J > I) { J -= I + 1; ++I; }
+}
 
-// descriptors of tiles I and J of pair k -> slot (2*DW int32), 16-byte cp.async
-__device__ __forceinline__ void load_desc(int32_t *slot, const int32_t *desc, long long k, int tid) {
-    int I, J;
-    pair_to_tiles(k, I, J);
+// descriptors of tiles I and J -> slot (2*DW int32), 16-byte cp.async
+__device__ __forceinline__ void load_desc(int32_t *slot, const int32_t *desc, int I, int J, int tid) {
     constexpr int CH = DW / 4;
     if (tid < 2 * CH) {
         const int t = tid < CH ? I : J, c = tid < CH ? tid : tid - CH;
@@ -68,87 +98,97 @@ __device__ __forceinline__ void load_desc(int32_t *slot, const int32_t *desc, lo
     }
 }
 
-// stage E[rows(I)][cols(J)] of the previous matrix into S (all asynchronous)
-__device__ __forceinline__ void issue_gathers(double *S, const int32_t *dI, const int32_t *dJ,
-                                              const double *__restrict__ Gp, long long ldp, int lastrow, int tid) {
+// stage E[rows(I)][cols(J)] of the previous matrix into one stage buffer (all asynchronous)
+__device__ __forceinline__ void issue_stage(double *S, unsigned long long *bar, const int32_t *dI, const int32_t *dJ,
+                                            const double *__restrict__ Gp, long long ldp, int lastrow, int tid) {
     const int c0I = dI[0], nlI = dI[1] & 0xFFFF, c0J = dJ[0], nlJ = dJ[1] & 0xFFFF;
     const int32_t *listI = dI + kDescList, *listJ = dJ + kDescList;
     const int nrI = W + nlI;
-    {   // (a) all rows x window columns of J: 16-byte chunks, half a warp per 256-byte row segment
-        constexpr int CH = W / 2;
-        const int ch = tid % CH;
-        const double *colbase = Gp + c0J + 2 * ch;
-        for (int r = tid / CH; r < nrI; r += kThreads / CH) {
-            int row = r < W ? c0I + r : listI[r - W];
-            row = row > lastrow ? lastrow : row;
-            cp_async16(S + r * PITCH + 2 * ch, colbase + (long long) row * ldp);
-        }
+    if (tid == 0) mbar_expect_tx(bar, (unsigned) ((nrI + nlJ) * W * 8));
+    if (tid < nrI) {                       // L[r][:] = G[row r of I][window of J]
+        int row = tid < W ? c0I + tid : listI[tid - W];
+        row = row > lastrow ? lastrow : row;
+        bulk_copy_256(S + tid * PL, Gp + (long long) row * ldp + c0J, bar);
+    } else if (tid >= 128 && tid < 128 + nlJ) {   // R[j][0..W) = G[list row j of J][window of I]
+        const int j = tid - 128;
+        bulk_copy_256(S + OFFR + j * PR, Gp + (long long) listJ[j] * ldp + c0I, bar);
     }
-    {   // (b) window rows of I x list columns of J through the symmetric entry (list row, window col)
-        const int r = tid % W;
-        for (int j = tid / W; j < nlJ; j += kThreads / W)
-            cp_async8(S + r * PITCH + W + j, Gp + (long long) listJ[j] * ldp + c0I + r);
-    }
-    {   // (c) list rows of I x list columns of J: 8-byte gathers (L2-resident across the I sweep)
+    {   // R[j][W + r] = G[list row r of I][list col j of J]: 8-byte gathers (L2-resident across the I sweep)
         const int lane = tid & 31, warp = tid >> 5;
+        long long roff[CAP / 8];
+#pragma unroll
+        for (int u = 0; u < CAP / 8; u++) {
+            const int r = warp + 8 * u;
+            roff[u] = r < nlI ? (long long) listI[r] * ldp : -1;
+        }
         for (int j = lane; j < nlJ; j += 32) {
             const double *colp = Gp + listJ[j];
-            for (int r = warp; r < nlI; r += kThreads / 32)
-                cp_async8(S + (W + r) * PITCH + W + j, colp + (long long) listI[r] * ldp);
+            double *dst = S + OFFR + j * PR + W + warp;
+#pragma unroll
+            for (int u = 0; u < CAP / 8; u++)
+                if (roff[u] >= 0) cp_async8(dst + 8 * u, colp + roff[u]);
         }
     }
-}
-
-// E(x, y) of the previous cut for one (row parent, column parent) pair, applying
-// "same individual -> self kinship" (lib/compute.cpp:522-528) when the CTA is on the slow path.
-template <bool CHECK>
-__device__ __forceinline__ double fetch_e(const double *S, int ra, int cb, int ia, int ib,
-                                          const double *dprev, int cls_a) {
-    if (ra == kMiss || cb == kMiss) return 0.0;
-    if (CHECK && ia == ib) return dprev[cls_a];
-    return S[ra * PITCH + cb];
 }
 
 template <bool RANKED>
 __global__ void __launch_bounds__(kThreads, 2) phi_step_kernel(const StepDev s) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *Sbuf = reinterpret_cast<double *>(smem_raw);                  // 2 x NR x PITCH
+    double *Sbuf = reinterpret_cast<double *>(smem_raw);                  // 2 stage buffers
     double *O = Sbuf + 2 * kStageDoubles;                                 // T x (T+1) transpose buffer
     int32_t *Dbuf = reinterpret_cast<int32_t *>(O + T * (T + 1));          // 3 slots x (desc I, desc J)
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(Dbuf + 3 * 2 * DW);   // one mbarrier per stage
 
     const int tid = threadIdx.x;
-    const long long np = s.npairs, stride = gridDim.x;
+    const long long np = s.npairs;
+    const int stride = (int) gridDim.x;
     const double *__restrict__ Gp = s.Gprev;
     const long long ldp = s.ld_prev, ldn = s.ld_new;
     const int lastrow = (int) (s.K_prev - 1);
     long long k = blockIdx.x;
     if (k >= np) return;
 
-    // ---- prologue: descriptors of the first pair, then its gathers + the second pair's descriptors
-    load_desc(Dbuf, s.desc, k, tid);
+    // ---- one-time setup: zero rows / columns for unknown parents, mbarriers ---------------------
+    for (int b = 0; b < 2; b++) {
+        double *S = Sbuf + b * kStageDoubles;
+        for (int i = tid; i < PL; i += kThreads) S[ZIDX * PL + i] = 0.0;            // L zero row
+        for (int i = tid; i < PR; i += kThreads) S[OFFR + CAP * PR + i] = 0.0;       // R zero row
+        for (int i = tid; i < CAP; i += kThreads) S[OFFR + i * PR + ZIDX] = 0.0;     // R zero column
+    }
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    int I, J, In, Jn, Inn, Jnn;              // tiles of pair k, k+stride, k+2*stride
+    pair_to_tiles(k, I, J);
+    In = I; Jn = J; advance_pair(In, Jn, stride);
+    Inn = In; Jnn = Jn; advance_pair(Inn, Jnn, stride);
+
+    // ---- prologue: descriptors of the first pair, then its rows + the second pair's descriptors
+    load_desc(Dbuf, s.desc, I, J, tid);
     cp_async_commit();
     cp_async_wait_all();
     __syncthreads();
-    issue_gathers(Sbuf, Dbuf, Dbuf + DW, Gp, ldp, lastrow, tid);
-    if (k + stride < np) load_desc(Dbuf + 2 * DW, s.desc, k + stride, tid);
+    issue_stage(Sbuf, &bars[0], Dbuf, Dbuf + DW, Gp, ldp, lastrow, tid);
+    if (k + stride < np) load_desc(Dbuf + 2 * DW, s.desc, In, Jn, tid);
     cp_async_commit();
 
     for (int it = 0; k < np; k += stride, ++it) {
         const int32_t *dI = Dbuf + (it % 3) * 2 * DW, *dJ = dI + DW;
         const double *S = Sbuf + (it & 1) * kStageDoubles;
         cp_async_wait_all();
+        mbar_wait(&bars[it & 1], (unsigned) ((it >> 1) & 1));
         __syncthreads();       // pair k staged, next descriptors landed, everyone done with pair k-1
-        // ---- keep the memory system busy: gathers of pair k+1, descriptors of pair k+2 ----------
+        // ---- keep the memory system busy: rows of pair k+1, descriptors of pair k+2 ---------------
         if (k + stride < np) {
             const int32_t *nI = Dbuf + ((it + 1) % 3) * 2 * DW;
-            issue_gathers(Sbuf + ((it + 1) & 1) * kStageDoubles, nI, nI + DW, Gp, ldp, lastrow, tid);
-            if (k + 2 * stride < np) load_desc(Dbuf + ((it + 2) % 3) * 2 * DW, s.desc, k + 2 * stride, tid);
+            issue_stage(Sbuf + ((it + 1) & 1) * kStageDoubles, &bars[(it + 1) & 1], nI, nI + DW, Gp, ldp, lastrow, tid);
+            if (k + 2 * (long long) stride < np) load_desc(Dbuf + ((it + 2) % 3) * 2 * DW, s.desc, Inn, Jnn, tid);
         }
         cp_async_commit();
 
         // ---- pair k -----------------------------------------------------------------------------
-        int I, J;
-        pair_to_tiles(k, I, J);
         const int c0I = dI[0], cntI = dI[1] >> 16, cntJ = dJ[1] >> 16;
         const long long startI = dI[3], startJ = dJ[3];
         const int32_t *listI = dI + kDescList;
@@ -156,39 +196,63 @@ __global__ void __launch_bounds__(kThreads, 2) phi_step_kernel(const StepDev s) 
         if (!slow)
             for (int c = 0; c < dI[2]; c++) slow |= (dI[kDescConf + c] == J);
 
-        constexpr int CPT = T * T / kThreads;                 // 4 cells per thread
+        constexpr int CPT = T * T / kThreads;                 // 4 cells per thread: rows a = tid/32 + 8c, column b = tid%32
+        const int b = tid & 31, a_base = tid >> 5;
+        const int lb = dJ[kDescLa + b];
+        const int b0 = min(lb & 0xFFFF, ZIDX), b1 = min((lb >> 16) & 0xFFFF, ZIDX);
+        // E(ra, cb) = cb < W ? L[ra][cb] : R[cb - W][ra]  ==  S[base(cb) + ra * stride(cb)]
+        const int base0 = b0 < W ? b0 : OFFR + (b0 - W) * PR, str0 = b0 < W ? PL : 1;
+        const int base1 = b1 < W ? b1 : OFFR + (b1 - W) * PR, str1 = b1 < W ? PL : 1;
         double v[CPT];
+        if (!slow) {
+#pragma unroll
+            for (int c = 0; c < CPT; c++) {
+                const int a = a_base + 8 * c;
+                const int la = dI[kDescLa + a];
+                const int a0 = min(la & 0xFFFF, ZIDX), a1 = min((la >> 16) & 0xFFFF, ZIDX);
+                const double p = S[base0 + a0 * str0], q = S[base0 + a1 * str0];
+                const double r = S[base1 + a0 * str1], t = S[base1 + a1 * str1];
+                if (RANKED) {
+                    // lib/compute.cpp:529-548: the higher-ranked individual is expanded first, so the
+                    // inner sums run over the LOWER-ranked one's parents.
+                    v[c] = (dI[kDescRank + a] < dJ[kDescRank + b]) ? 0.25 * (__dadd_rn(p, q) + __dadd_rn(r, t))
+                                                                  : 0.25 * (__dadd_rn(p, r) + __dadd_rn(q, t));
+                } else {
+                    v[c] = 0.25 * ((p + q) + (r + t));
+                }
+            }
+        } else {
+            const int ib0 = dJ[kDescPind + 2 * b], ib1 = dJ[kDescPind + 2 * b + 1];
+#pragma unroll
+            for (int c = 0; c < CPT; c++) {
+                const int a = a_base + 8 * c;
+                const int la = dI[kDescLa + a];
+                const int a0 = min(la & 0xFFFF, ZIDX), a1 = min((la >> 16) & 0xFFFF, ZIDX);
+                const int ia0 = dI[kDescPind + 2 * a], ia1 = dI[kDescPind + 2 * a + 1];
+                double p = S[base0 + a0 * str0], q = S[base0 + a1 * str0];
+                double r = S[base1 + a0 * str1], t = S[base1 + a1 * str1];
+                // same individual on both sides -> its self kinship (lib/compute.cpp:522-528)
+                if (ia0 >= 0 && (ia0 == ib0 || ia0 == ib1)) {
+                    const double d = s.dprev[a0 < W ? c0I + a0 : listI[a0 - W]];
+                    if (ia0 == ib0) p = d;
+                    if (ia0 == ib1) r = d;
+                }
+                if (ia1 >= 0 && (ia1 == ib0 || ia1 == ib1)) {
+                    const double d = s.dprev[a1 < W ? c0I + a1 : listI[a1 - W]];
+                    if (ia1 == ib0) q = d;
+                    if (ia1 == ib1) t = d;
+                }
+                if (RANKED) {
+                    v[c] = (dI[kDescRank + a] < dJ[kDescRank + b]) ? 0.25 * (__dadd_rn(p, q) + __dadd_rn(r, t))
+                                                                  : 0.25 * (__dadd_rn(p, r) + __dadd_rn(q, t));
+                } else {
+                    v[c] = 0.25 * ((p + q) + (r + t));
+                }
+            }
+        }
 #pragma unroll
         for (int c = 0; c < CPT; c++) {
-            const int cell = tid + c * kThreads;
-            const int a = cell / T, b = cell % T;
-            const int la = dI[kDescLa + a], lb = dJ[kDescLa + b];
-            const int a0 = la & 0xFFFF, a1 = (la >> 16) & 0xFFFF;
-            const int b0 = lb & 0xFFFF, b1 = (lb >> 16) & 0xFFFF;
-            double p, q, r, t;
-            if (!slow) {
-                p = fetch_e<false>(S, a0, b0, 0, 0, nullptr, 0);
-                q = fetch_e<false>(S, a1, b0, 0, 0, nullptr, 0);
-                r = fetch_e<false>(S, a0, b1, 0, 0, nullptr, 0);
-                t = fetch_e<false>(S, a1, b1, 0, 0, nullptr, 0);
-            } else {
-                const int ia0 = dI[kDescPind + 2 * a], ia1 = dI[kDescPind + 2 * a + 1];
-                const int ib0 = dJ[kDescPind + 2 * b], ib1 = dJ[kDescPind + 2 * b + 1];
-                const int ca0 = a0 == kMiss ? 0 : (a0 < W ? c0I + a0 : listI[a0 - W]);
-                const int ca1 = a1 == kMiss ? 0 : (a1 < W ? c0I + a1 : listI[a1 - W]);
-                p = fetch_e<true>(S, a0, b0, ia0, ib0, s.dprev, ca0);
-                q = fetch_e<true>(S, a1, b0, ia1, ib0, s.dprev, ca1);
-                r = fetch_e<true>(S, a0, b1, ia0, ib1, s.dprev, ca0);
-                t = fetch_e<true>(S, a1, b1, ia1, ib1, s.dprev, ca1);
-            }
-            if (RANKED) {
-                // lib/compute.cpp:529-548: the higher-ranked individual is expanded first, so the
-                // inner sums run over the LOWER-ranked one's parents.
-                v[c] = (dI[kDescRank + a] < dJ[kDescRank + b]) ? 0.25 * (__dadd_rn(p, q) + __dadd_rn(r, t))
-                                                              : 0.25 * (__dadd_rn(p, r) + __dadd_rn(q, t));
-            } else {
-                v[c] = 0.25 * ((p + q) + (r + t));
-            }
+            const int a = a_base + 8 * c;
             if (a < cntI && b < cntJ) s.Gnew[(startI + a) * ldn + startJ + b] = v[c];
             O[a * (T + 1) + b] = v[c];
         }
@@ -200,19 +264,20 @@ __global__ void __launch_bounds__(kThreads, 2) phi_step_kernel(const StepDev s) 
                 const int a0 = la & 0xFFFF, a1 = (la >> 16) & 0xFFFF;
                 const int i0 = dI[kDescPind + 2 * tid], i1 = dI[kDescPind + 2 * tid + 1];
                 double d = 0.5;
-                if (a0 != kMiss && i0 == i1) d = s.dprev[a0 < W ? c0I + a0 : listI[a0 - W]];
-                else if (a0 != kMiss && a1 != kMiss) d = 0.5 + 0.5 * S[a0 * PITCH + a1];
+                if (a0 != 0xFFFF && i0 == i1) d = s.dprev[a0 < W ? c0I + a0 : listI[a0 - W]];
+                else if (a0 != 0xFFFF && a1 != 0xFFFF) d = 0.5 + 0.5 * (a1 < W ? S[a0 * PL + a1] : S[OFFR + (a1 - W) * PR + a0]);
                 s.dnew[startI + tid] = d;
             }
         } else {
             __syncthreads();
 #pragma unroll
             for (int c = 0; c < CPT; c++) {
-                const int cell = tid + c * kThreads;
-                const int b = cell / T, a = cell % T;          // lanes run along a -> coalesced mirror rows
-                if (a < cntI && b < cntJ) s.Gnew[(startJ + b) * ldn + startI + a] = O[a * (T + 1) + b];
+                const int bb = a_base + 8 * c, aa = tid & 31;      // lanes run along a -> coalesced mirror rows
+                if (aa < cntI && bb < cntJ) s.Gnew[(startJ + bb) * ldn + startI + aa] = O[aa * (T + 1) + bb];
             }
         }
+        I = In; J = Jn; In = Inn; Jn = Jnn;
+        advance_pair(Inn, Jnn, stride);
     }
 }
 
