@@ -73,6 +73,7 @@ def _load():
     L.gk_parentless.argtypes = [i32, _I, _I, vp]; L.gk_parentless.restype = i32
     L.gk_dfs_order.argtypes = [i32, _I, _I, _I]
     L.gk_cut_sizes.argtypes = [i32, _I, _I, i32, _I, _I, i32]; L.gk_cut_sizes.restype = i32
+    L.gk_shard_rows.argtypes = [i32, i32, i32, C.POINTER(i64), C.POINTER(i64)]; L.gk_shard_rows.restype = None
     L.gk_phi_plan.argtypes = [i32, _I, _I, i32, _I, OP, C.POINTER(vp)]
     for name in ("gk_phi_upload", "gk_phi_run", "gk_phi_sync"):
         getattr(L, name).argtypes = [vp]
@@ -96,7 +97,7 @@ lib = _load()
 
 EXPORTS = [
     "gk_phi_f64", "gk_gc_f64", "gk_phi_required_gb", "gk_childless", "gk_parentless", "gk_dfs_order",
-    "gk_cut_sizes", "gk_last_error", "gk_abi_version", "gk_host_alloc", "gk_host_free",
+    "gk_cut_sizes", "gk_shard_rows", "gk_last_error", "gk_abi_version", "gk_host_alloc", "gk_host_free",
     "gk_phi_plan", "gk_phi_upload", "gk_phi_run", "gk_phi_sync", "gk_phi_mean", "gk_phi_copy_out",
     "gk_phi_device_result", "gk_phi_get_stats", "gk_phi_cut_sizes", "gk_phi_class_sizes",
     "gk_phi_step_times", "gk_phi_step_bytes", "gk_phi_free", "gk_phi_step_view", "gk_phi_final_view", "gk_phi_initial_classes",

@@ -198,6 +198,9 @@ class DevicePhi:
         r = _pro_ranks(pedigree, proband_ids)
         self.m = len(r)
         self._opts = make_opts(verbose=verbose, **gk)
+        r0, r1 = C.c_int64(), C.c_int64()
+        lib.gk_shard_rows(self.m, self._opts.rank, max(self._opts.world, 1), C.byref(r0), C.byref(r1))
+        self.row0, self.row1 = r0.value, r1.value          # result rows held by this job (multi-GPU shard)
         check(lib.gk_phi_plan(len(pedigree), pedigree.sire, pedigree.dam, self.m, r,
                               C.byref(self._opts), C.byref(self._h)))
 
@@ -222,7 +225,7 @@ class DevicePhi:
 
     def to_host(self, out=None):
         if out is None:
-            out, ptr = _pinned_matrix(self.m, self.m)
+            out, ptr = _pinned_matrix(self.row1 - self.row0, self.m)
         else:
             ptr = out.ctypes.data
         check(lib.gk_phi_copy_out(self._h, ptr))

@@ -52,8 +52,11 @@ struct gk_phi_job {
     double *sums_host = nullptr;      // pinned
     int32_t *ints = nullptr;          // all plan arrays, one allocation
     std::vector<StepOffsets> off;
-    size_t off_final_cls = 0, off_final_ind = 0, ints_count = 0;
-    int nblocks_expand = 0;
+    size_t off_final_cls = 0, off_final_ind = 0, off_cact = 0, off_coff = 0, off_cmem = 0, ints_count = 0;
+    int64_t row0 = 0, row1 = 0;       // result rows owned by this shard (caller order)
+    int32_t nact = 0, nchunks = 0;
+    int64_t nblocks_expand = 0;
+    double *scratch = nullptr;
     std::vector<cudaEvent_t> ev;      // G + 2 events around the step launches
     int64_t device_bytes = 0;
     int64_t launches = 0;
@@ -66,6 +69,7 @@ void destroy(gk_phi_job *j) {
     cudaSetDevice(j->device);
     for (int p = 0; p < 2; p++) { if (j->buf[p]) cudaFree(j->buf[p]); if (j->dvec[p]) cudaFree(j->dvec[p]); }
     if (j->partials) cudaFree(j->partials);
+    if (j->scratch) cudaFree(j->scratch);
     if (j->sums_dev) cudaFree(j->sums_dev);
     if (j->sums_host) cudaFreeHost(j->sums_host);
     if (j->ints) cudaFree(j->ints);
@@ -166,6 +170,15 @@ int gk_dfs_order(int32_t n, const int32_t *fidx, const int32_t *midx, int32_t *o
     return GK_OK;
 }
 
+void gk_shard_rows(int32_t m, int32_t rank, int32_t world, int64_t *row0, int64_t *row1) {
+    if (world < 1) world = 1;
+    if (rank < 0) rank = 0;
+    if (rank >= world) rank = world - 1;
+    // contiguous blocks of result rows, sizes differing by at most one
+    if (row0) *row0 = (int64_t) m * rank / world;
+    if (row1) *row1 = (int64_t) m * (rank + 1) / world;
+}
+
 int32_t gk_cut_sizes(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, const int32_t *pro,
                      int32_t *sizes, int32_t cap) {
     std::vector<int64_t> s;
@@ -196,7 +209,8 @@ int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, c
     gk_phi_job *j = new gk_phi_job();
     if (opts) std::memcpy(&j->opts, opts, std::min<size_t>(sizeof(gk_opts), (size_t) std::max(0, opts->struct_size)));
     else { j->opts.device = -1; j->opts.compress = -1; }
-    if (j->opts.world > 1) { delete j; return fail(GK_ERR_ARG, "column sharding (world > 1) goes through gk_phi_plan_shard"); }
+    if (j->opts.world < 1) j->opts.world = 1;
+    if (j->opts.rank < 0 || j->opts.rank >= j->opts.world) { delete j; return fail(GK_ERR_ARG, "rank outside [0, world)"); }
     int tile = j->opts.tile;
     if (!gk::build_phi_plan(n, sire, dam, m, pro, j->opts.compress, tile, j->plan)) {
         int code = j->plan.error_code == 2 ? GK_ERR_INDEX : GK_ERR_ARG;
@@ -236,6 +250,24 @@ int gk_phi_upload(gk_phi_job *j) {
     }
     j->off_final_cls = push(P.final_cls);
     j->off_final_ind = push(P.final_ind);
+    // result rows of this shard and, for the expansion kernel, its caller entries grouped by class
+    gk_shard_rows(P.m, j->opts.rank, j->opts.world, &j->row0, &j->row1);
+    {
+        const int64_t Kl = P.steps[G - 1].K;
+        std::vector<int32_t> cnt((size_t) Kl + 1, 0), cact, coff(1, 0), cmem;
+        if (!P.single_cut) {
+            for (int64_t i = j->row0; i < j->row1; i++) cnt[P.final_cls[i] + 1]++;
+            for (int64_t c = 0; c < Kl; c++) if (cnt[c + 1] > 0) { cact.push_back((int32_t) c); coff.push_back(coff.back() + cnt[c + 1]); }
+            std::vector<int32_t> slot((size_t) Kl, -1), w(coff.begin(), coff.end() - 1);
+            for (size_t a = 0; a < cact.size(); a++) slot[cact[a]] = (int32_t) a;
+            cmem.assign((size_t) (j->row1 - j->row0), 0);
+            for (int64_t i = j->row0; i < j->row1; i++) cmem[w[slot[P.final_cls[i]]]++] = (int32_t) i;
+        }
+        j->nact = (int32_t) cact.size();
+        j->nchunks = (int32_t) ((P.m + gk::kExpandCols - 1) / gk::kExpandCols);
+        j->off_cact = push(cact); j->off_coff = push(coff); j->off_cmem = push(cmem);
+        j->nblocks_expand = P.single_cut ? 1 : (int64_t) j->nact * j->nchunks;
+    }
     j->ints_count = arena.size();
     GK_CUDA(cudaMalloc(&j->ints, std::max<size_t>(arena.size(), 4) * sizeof(int32_t)));
     GK_CUDA(cudaMemcpyAsync(j->ints, arena.data(), arena.size() * sizeof(int32_t), cudaMemcpyHostToDevice, j->stream));
@@ -250,7 +282,7 @@ int gk_phi_upload(gk_phi_job *j) {
         need[g & 1] = std::max(need[g & 1], S.K * S.ld + kPadDoubles);
         maxK = std::max(maxK, S.K);
     }
-    const int64_t mm = (int64_t) P.m * P.m;
+    const int64_t mm = (j->row1 - j->row0) * (int64_t) P.m;
     const int out_buf = P.single_cut ? 0 : 1 - ((G - 1) & 1);
     need[out_buf] = std::max(need[out_buf], mm + kPadDoubles);
     for (int p = 0; p < 2; p++) {
@@ -268,9 +300,9 @@ int gk_phi_upload(gk_phi_job *j) {
     }
     j->out = j->buf[out_buf];
     for (int p = 0; p < 2; p++) { GK_CUDA(cudaMalloc(&j->dvec[p], (size_t) maxK * sizeof(double))); j->device_bytes += maxK * 8; }
-    const int64_t gx = (P.m + 255) / 256, gy = (P.m + 15) / 16;
-    GK_CUDA(cudaMalloc(&j->partials, (size_t) (gx * gy * 2) * sizeof(double)));
-    j->device_bytes += gx * gy * 16;
+    GK_CUDA(cudaMalloc(&j->partials, (size_t) std::max<int64_t>(j->nblocks_expand, 1) * 2 * sizeof(double)));
+    GK_CUDA(cudaMalloc(&j->scratch, 2 * 256 * sizeof(double)));
+    j->device_bytes += j->nblocks_expand * 16;
     GK_CUDA(cudaMalloc(&j->sums_dev, 2 * sizeof(double)));
     GK_CUDA(cudaHostAlloc(&j->sums_host, 2 * sizeof(double), cudaHostAllocDefault));
     j->ev.resize(G + 2);
@@ -313,17 +345,21 @@ int gk_phi_run(gk_phi_job *j) {
         }
         GK_CUDA(cudaEventRecord(j->ev[G], st));
     }
-    gk::ExpandDev e{};
     const int last = G - 1;
-    e.G = P.single_cut ? nullptr : j->buf[last & 1];
-    e.d = P.single_cut ? nullptr : j->dvec[last & 1];
-    e.ld = P.steps[last].ld;
-    e.cls = j->ints + j->off_final_cls; e.ind = j->ints + j->off_final_ind;
-    e.out = j->out; e.m = P.m; e.partials = j->partials; e.single_cut = P.single_cut ? 1 : 0;
-    GK_CUDA(gk::launch_expand(e, &j->nblocks_expand, st));
-    GK_CUDA(gk::launch_mean_finish(j->partials, j->nblocks_expand, j->sums_dev, st));
+    if (P.single_cut) {
+        GK_CUDA(gk::launch_eye(j->out, P.m, j->row0, j->row1, j->partials, st));
+    } else {
+        gk::ExpandDev e{};
+        e.G = j->buf[last & 1]; e.d = j->dvec[last & 1]; e.ld = P.steps[last].ld;
+        e.cls = j->ints + j->off_final_cls; e.ind = j->ints + j->off_final_ind;
+        e.cact = j->ints + j->off_cact; e.coff = j->ints + j->off_coff; e.cmem = j->ints + j->off_cmem;
+        e.out = j->out; e.m = P.m; e.row0 = j->row0; e.row1 = j->row1;
+        e.nact = j->nact; e.nchunks = j->nchunks; e.partials = j->partials;
+        GK_CUDA(gk::launch_expand(e, st));
+    }
+    GK_CUDA(gk::launch_mean_finish(j->partials, j->nblocks_expand, j->scratch, j->sums_dev, st));
     GK_CUDA(cudaEventRecord(j->ev[G + 1], st));
-    launches += 2;
+    launches += 3;
     GK_CUDA(cudaMemcpyAsync(j->sums_host, j->sums_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     j->launches = launches;
     j->ran = true;
@@ -345,7 +381,9 @@ int gk_phi_mean(gk_phi_job *j, double *sum_all, double *sum_diag, double *mean) 
     if (sum_all) *sum_all = total;
     if (sum_diag) *sum_diag = diag;
     const double n = (double) j->plan.m;
-    if (mean) *mean = (total - diag) / (n * n - n);      // geneakit/compute.py:131-132
+    // geneakit/compute.py:131-132 (with world > 1 these are this shard's partial sums: the driver
+    // all-reduces sum_all / sum_diag across ranks and applies the same formula)
+    if (mean) *mean = (total - diag) / (n * n - n);
     return GK_OK;
 }
 
@@ -353,7 +391,7 @@ int gk_phi_copy_out(gk_phi_job *j, double *host_out) {
     if (!j || !j->ran) return fail(GK_ERR_STATE, "gk_phi_copy_out before gk_phi_run");
     if (!host_out) return fail(GK_ERR_ARG, "null output");
     GK_CUDA(cudaSetDevice(j->device));
-    const size_t bytes = (size_t) j->plan.m * j->plan.m * sizeof(double);
+    const size_t bytes = (size_t) (j->row1 - j->row0) * j->plan.m * sizeof(double);
     GK_CUDA(cudaMemcpyAsync(host_out, j->out, bytes, cudaMemcpyDeviceToHost, j->stream));
     GK_CUDA(cudaStreamSynchronize(j->stream));
     return GK_OK;
@@ -388,7 +426,7 @@ int gk_phi_get_stats(gk_phi_job *j, gk_phi_stats *s) {
     s->cells_device += mm;
     s->algorithmic_bytes_device += 8 * (mm + std::min(mm, Kl * Kl));
     s->device_bytes = j->device_bytes;
-    s->kernel_launches = j->launches ? j->launches : (P.single_cut ? 2 : P.G + 2);
+    s->kernel_launches = j->launches ? j->launches : (P.single_cut ? 3 : P.G + 3);
     s->plan_seconds = P.plan_seconds;
     int64_t ints = (int64_t) P.final_cls.size() + (int64_t) P.final_ind.size();
     for (int g = 1; g < P.G; g++) {

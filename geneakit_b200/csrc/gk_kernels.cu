@@ -98,35 +98,59 @@ __device__ __forceinline__ void load_desc(int32_t *slot, const int32_t *desc, in
     }
 }
 
+// Ask the L2 to stream in the scattered parent rows of a tile that the sweep reaches two waves
+// from now: turns the first touch of those rows (otherwise random 32-byte sector misses of the
+// list x list gathers) into sequential DRAM reads.
+__device__ __forceinline__ void prefetch_list_rows(const int32_t *desc, int tile, const double *Gp, long long ldp, int lane) {
+    const int32_t *d = desc + (size_t) tile * DW;
+    const int nl = d[1] & 0xFFFF;
+    if (lane < nl || lane + 32 < nl) {
+        const unsigned row_bytes = (unsigned) (ldp * 8);
+        for (int r = lane; r < nl; r += 32) {
+            const char *p = reinterpret_cast<const char *>(Gp + (long long) d[kDescList + r] * ldp);
+            for (unsigned off = 0; off < row_bytes; off += 65536u) {
+                const unsigned n = row_bytes - off < 65536u ? row_bytes - off : 65536u;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p + off), "r"(n) : "memory");
+            }
+        }
+    }
+}
+
 // stage E[rows(I)][cols(J)] of the previous matrix into one stage buffer (all asynchronous)
 __device__ __forceinline__ void issue_stage(double *S, unsigned long long *bar, const int32_t *dI, const int32_t *dJ,
                                             const double *__restrict__ Gp, long long ldp, int lastrow, int tid) {
     const int c0I = dI[0], nlI = dI[1] & 0xFFFF, c0J = dJ[0], nlJ = dJ[1] & 0xFFFF;
     const int32_t *listI = dI + kDescList, *listJ = dJ + kDescList;
     const int nrI = W + nlI;
+    const int lane = tid & 31, warp = tid >> 5;
     if (tid == 0) mbar_expect_tx(bar, (unsigned) ((nrI + nlJ) * W * 8));
-    if (tid < nrI) {                       // L[r][:] = G[row r of I][window of J]
-        int row = tid < W ? c0I + tid : listI[tid - W];
-        row = row > lastrow ? lastrow : row;
-        bulk_copy_256(S + tid * PL, Gp + (long long) row * ldp + c0J, bar);
-    } else if (tid >= 128 && tid < 128 + nlJ) {   // R[j][0..W) = G[list row j of J][window of I]
-        const int j = tid - 128;
-        bulk_copy_256(S + OFFR + j * PR, Gp + (long long) listJ[j] * ldp + c0I, bar);
+    // bulk copies, interleaved over the 8 warps (the issue loop is serial inside a warp):
+    // copy c < nrI        : L[c][:]        = G[row c of I][window of J]
+    // copy nrI <= c       : R[c - nrI][:W] = G[list row of J][window of I]
+    {
+        const int c = lane * 8 + warp;
+        if (c < nrI) {
+            int row = c < W ? c0I + c : listI[c - W];
+            row = row > lastrow ? lastrow : row;
+            bulk_copy_256(S + c * PL, Gp + (long long) row * ldp + c0J, bar);
+        } else if (c < nrI + nlJ) {
+            const int j = c - nrI;
+            bulk_copy_256(S + OFFR + j * PR, Gp + (long long) listJ[j] * ldp + c0I, bar);
+        }
     }
     {   // R[j][W + r] = G[list row r of I][list col j of J]: 8-byte gathers (L2-resident across the I sweep)
-        const int lane = tid & 31, warp = tid >> 5;
-        long long roff[CAP / 8];
+        const char *rowp[CAP / 8];
 #pragma unroll
         for (int u = 0; u < CAP / 8; u++) {
             const int r = warp + 8 * u;
-            roff[u] = r < nlI ? (long long) listI[r] * ldp : -1;
+            rowp[u] = r < nlI ? reinterpret_cast<const char *>(Gp + (long long) listI[r] * ldp) : nullptr;
         }
         for (int j = lane; j < nlJ; j += 32) {
-            const double *colp = Gp + listJ[j];
+            const unsigned col8 = (unsigned) listJ[j] * 8u;
             double *dst = S + OFFR + j * PR + W + warp;
 #pragma unroll
             for (int u = 0; u < CAP / 8; u++)
-                if (roff[u] >= 0) cp_async8(dst + 8 * u, colp + roff[u]);
+                if (rowp[u]) cp_async8(dst + 8 * u, rowp[u] + col8);
         }
     }
 }
@@ -250,11 +274,15 @@ __global__ void __launch_bounds__(kThreads, 2) phi_step_kernel(const StepDev s) 
                 }
             }
         }
+        {
+            double *g = s.Gnew + (startI + a_base) * ldn + startJ + b;
+            const bool colok = b < cntJ;
 #pragma unroll
-        for (int c = 0; c < CPT; c++) {
-            const int a = a_base + 8 * c;
-            if (a < cntI && b < cntJ) s.Gnew[(startI + a) * ldn + startJ + b] = v[c];
-            O[a * (T + 1) + b] = v[c];
+            for (int c = 0; c < CPT; c++) {
+                if (colok && a_base + 8 * c < cntI) *g = v[c];
+                g += 8 * ldn;
+                O[(a_base + 8 * c) * (T + 1) + b] = v[c];
+            }
         }
         if (I == J) {
             // self kinship of the new classes (lib/compute.cpp:553-568): a kept individual copies its
@@ -270,12 +298,18 @@ __global__ void __launch_bounds__(kThreads, 2) phi_step_kernel(const StepDev s) 
             }
         } else {
             __syncthreads();
+            // mirror tile (J,I): thread (row bb = a_base + 8c of tile J, column aa = b of tile I); lanes along aa -> coalesced
+            double *g = s.Gnew + (startJ + a_base) * ldn + startI + b;
+            const bool colok = b < cntI;
+            const double *o = O + b * (T + 1) + a_base;
 #pragma unroll
             for (int c = 0; c < CPT; c++) {
-                const int bb = a_base + 8 * c, aa = tid & 31;      // lanes run along a -> coalesced mirror rows
-                if (aa < cntI && bb < cntJ) s.Gnew[(startJ + bb) * ldn + startI + aa] = O[aa * (T + 1) + bb];
+                if (colok && a_base + 8 * c < cntJ) *g = o[8 * c];
+                g += 8 * ldn;
             }
         }
+        // L2 prefetch duty: the CTA that will open tile row Inn (two strides ahead) streams its list rows in
+        if (Jnn == 0 && (tid >> 5) == 7 && k + 2 * (long long) stride < np) prefetch_list_rows(s.desc, Inn, Gp, ldp, tid & 31);
         I = In; J = Jn; In = Inn; Jn = Jnn;
         advance_pair(Inn, Jnn, stride);
     }
@@ -293,30 +327,40 @@ __global__ void init_kernel(double *G0, double *d0, long long K0, long long ld0)
 }
 
 // Final expansion to the caller's proband order (duplicates, ancestors-as-probands) fused with
-// the gen.phiMean reduction (geneakit/compute.py:124-132): every CTA writes a 16 x 256 block
-// of the m x m result and one (sum, diagonal sum) partial.
-constexpr int kExpRows = 16;
+// the gen.phiMean reduction (geneakit/compute.py:124-132).  Probands of one class (sibship) have
+// identical rows, so one CTA gathers a 1024-column slice of the class row ONCE (8-byte gathers,
+// the row stays in L2) and then streams it, coalesced, to every local result row of that class,
+// patching the "same individual" entries with the self kinship.  Each CTA also emits one
+// (sum, diagonal sum) partial for the mean.
 __global__ void __launch_bounds__(256) expand_kernel(const ExpandDev e) {
-    const long long j = (long long) blockIdx.x * 256 + threadIdx.x;
-    const long long i0 = (long long) blockIdx.y * kExpRows;
+    const int a = blockIdx.x / e.nchunks, chunk = blockIdx.x - a * e.nchunks;
+    const int c = e.cact[a];
+    const long long j0 = (long long) chunk * kExpandCols + threadIdx.x;
+    double v[4];
+    int uj[4];
+    const double *row = e.G + (long long) c * e.ld;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const long long j = j0 + 256 * k;
+        const bool ok = j < e.m;
+        uj[k] = ok ? e.ind[j] : -2;
+        v[k] = ok ? row[e.cls[j]] : 0.0;
+    }
+    const double dc = e.d[c];
     double sum = 0.0, dsum = 0.0;
-    if (j < e.m) {
-        const int cj = e.single_cut ? 0 : e.cls[j];
-        const int uj = e.ind[j];
-#pragma unroll 4
-        for (int k = 0; k < kExpRows; k++) {
-            const long long i = i0 + k;
-            if (i >= e.m) break;
-            double v;
-            if (e.single_cut) {
-                v = (i == j) ? 0.5 : 0.0;
-            } else {
-                const int ci = e.cls[i];
-                v = (e.ind[i] == uj) ? e.d[ci] : e.G[(long long) ci * e.ld + cj];
+    for (int q = e.coff[a]; q < e.coff[a + 1]; q++) {
+        const long long i = e.cmem[q];
+        const int ui = e.ind[i];
+        double *orow = e.out + (i - e.row0) * e.m;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const long long j = j0 + 256 * k;
+            if (j < e.m) {
+                const double val = (uj[k] == ui) ? dc : v[k];
+                orow[j] = val;
+                sum += val;
+                if (i == j) dsum += val;
             }
-            e.out[i * e.m + j] = v;
-            sum += v;
-            if (i == j) dsum += v;
         }
     }
     // warp shuffle -> shared -> one partial per CTA (fixed order: deterministic)
@@ -329,12 +373,35 @@ __global__ void __launch_bounds__(256) expand_kernel(const ExpandDev e) {
     if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = sum; wd[threadIdx.x >> 5] = dsum; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double a = 0.0, b = 0.0;
-        for (int w = 0; w < 8; w++) { a += ws[w]; b += wd[w]; }
-        const long long blk = (long long) blockIdx.y * gridDim.x + blockIdx.x;
-        e.partials[2 * blk] = a;
-        e.partials[2 * blk + 1] = b;
+        double x = 0.0, y = 0.0;
+        for (int w = 0; w < 8; w++) { x += ws[w]; y += wd[w]; }
+        e.partials[2 * (long long) blockIdx.x] = x;
+        e.partials[2 * (long long) blockIdx.x + 1] = y;
     }
+}
+
+// All probands are top founders (single cut): 0.5*I, even for duplicated probands
+// (lib/compute.cpp:655-661).  partials[0..1] = (sum, diagonal sum) of the local rows.
+__global__ void eye_kernel(double *out, long long m, long long row0, long long row1, double *partials) {
+    const long long total = (row1 - row0) * m;
+    for (long long x = blockIdx.x * (long long) blockDim.x + threadIdx.x; x < total; x += (long long) gridDim.x * blockDim.x) {
+        const long long i = row0 + x / m, j = x % m;
+        out[x] = (i == j) ? 0.5 : 0.0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { partials[0] = 0.5 * (double) (row1 - row0); partials[1] = partials[0]; }
+}
+
+__global__ void __launch_bounds__(256) mean_stage1_kernel(const double *partials, long long nblocks, double *scratch) {
+    __shared__ double sa[256], sb[256];
+    double a = 0.0, b = 0.0;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < nblocks; i += 256LL * gridDim.x) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+    sa[threadIdx.x] = a; sb[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sb[threadIdx.x] += sb[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { scratch[2 * blockIdx.x] = sa[0]; scratch[2 * blockIdx.x + 1] = sb[0]; }
 }
 
 __global__ void __launch_bounds__(256) mean_finish_kernel(const double *partials, int nblocks, double *sums) {
@@ -421,15 +488,22 @@ cudaError_t launch_init(double *G0, double *d0, int64_t K0, int64_t ld0, cudaStr
     return cudaGetLastError();
 }
 
-cudaError_t launch_expand(const ExpandDev &e, int *nblocks_out, cudaStream_t st) {
-    dim3 grid((unsigned) ((e.m + 255) / 256), (unsigned) ((e.m + kExpRows - 1) / kExpRows));
-    if (nblocks_out) *nblocks_out = (int) (grid.x * grid.y);
-    expand_kernel<<<grid, 256, 0, st>>>(e);
+cudaError_t launch_expand(const ExpandDev &e, cudaStream_t st) {
+    if (e.nact <= 0) return cudaSuccess;
+    expand_kernel<<<(unsigned) ((long long) e.nact * e.nchunks), 256, 0, st>>>(e);
     return cudaGetLastError();
 }
 
-cudaError_t launch_mean_finish(const double *partials, int nblocks, double *sums, cudaStream_t st) {
-    mean_finish_kernel<<<1, 256, 0, st>>>(partials, nblocks, sums);
+cudaError_t launch_eye(double *out, int64_t m, int64_t row0, int64_t row1, double *partials, cudaStream_t st) {
+    eye_kernel<<<148 * 4, 256, 0, st>>>(out, m, row0, row1, partials);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mean_finish(const double *partials, int64_t nblocks, double *scratch, double *sums, cudaStream_t st) {
+    mean_stage1_kernel<<<256, 256, 0, st>>>(partials, nblocks, scratch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    mean_finish_kernel<<<1, 256, 0, st>>>(scratch, 256, sums);
     return cudaGetLastError();
 }
 

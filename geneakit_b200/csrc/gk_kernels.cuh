@@ -22,19 +22,25 @@ struct ExpandDev {
     const double *G;         // K_last x ld last class matrix
     const double *d;         // self kinship per class
     int64_t ld;
-    const int32_t *cls;      // m: class row of caller entry i
-    const int32_t *ind;      // m: individual of caller entry i
-    double *out;             // m x m, row-major, caller order
-    int64_t m;
-    double *partials;        // gridDim.x*gridDim.y*2 : per-CTA (sum all, sum diag)
-    int32_t single_cut;      // 1: every proband is a top founder -> 0.5*I (lib/compute.cpp:655-661)
+    const int32_t *cls;      // m: class row of caller entry j
+    const int32_t *ind;      // m: individual of caller entry j
+    const int32_t *cact;     // nact: classes that have at least one caller entry among the local rows
+    const int32_t *coff;     // nact + 1: CSR into cmem
+    const int32_t *cmem;     // local caller entries (row indices i, row0 <= i < row1) grouped by class
+    double *out;             // (row1 - row0) x m, row-major, caller order
+    int64_t m, row0, row1;
+    int32_t nact, nchunks;
+    double *partials;        // nact*nchunks*2 : per-CTA (sum all, sum diag)
 };
 
 size_t step_smem_bytes();
 cudaError_t launch_step(const StepDev &s, bool ranked, cudaStream_t st);
 cudaError_t launch_init(double *G0, double *d0, int64_t K0, int64_t ld0, cudaStream_t st);
-cudaError_t launch_expand(const ExpandDev &e, int *nblocks_out, cudaStream_t st);
-cudaError_t launch_mean_finish(const double *partials, int nblocks, double *sums /*2*/, cudaStream_t st);
+constexpr int kExpandCols = 1024;     // result columns per CTA of the expansion kernel
+cudaError_t launch_expand(const ExpandDev &e, cudaStream_t st);
+cudaError_t launch_eye(double *out, int64_t m, int64_t row0, int64_t row1, double *partials, cudaStream_t st);
+// two-stage deterministic reduction of the per-CTA partials: scratch holds 2*256 doubles
+cudaError_t launch_mean_finish(const double *partials, int64_t nblocks, double *scratch, double *sums /*2*/, cudaStream_t st);
 cudaError_t configure_kernels();   // cudaFuncSetAttribute for large dynamic shared memory
 
 // gen.gc propagation: out row = 0.5*w0*row(p0) + 0.5*w1*row(p1), then seed own ancestor columns.

@@ -84,6 +84,11 @@ int gk_dfs_order(int32_t n, const int32_t *fidx, const int32_t *midx, int32_t *o
 int32_t gk_cut_sizes(int32_t n, const int32_t *sire, const int32_t *dam,
                      int32_t m, const int32_t *pro, int32_t *sizes, int32_t cap);
 
+/* Multi-GPU: the final m x m matrix is sharded by contiguous blocks of result ROWS (== columns,
+ * the matrix is symmetric), one block per rank; opts->rank / opts->world select the block a job
+ * produces.  Host only. */
+void gk_shard_rows(int32_t m, int32_t rank, int32_t world, int64_t *row0, int64_t *row1);
+
 const char *gk_last_error(void);
 int32_t gk_abi_version(void);
 
@@ -123,8 +128,8 @@ int gk_phi_upload(gk_phi_job *job);                 /* allocate HBM, copy the pl
 int gk_phi_run(gk_phi_job *job);                    /* enqueue init + all steps + expansion; async */
 int gk_phi_sync(gk_phi_job *job);                   /* wait for the job's stream */
 int gk_phi_mean(gk_phi_job *job, double *sum_all, double *sum_diag, double *mean);
-int gk_phi_copy_out(gk_phi_job *job, double *host_out);            /* m*m doubles */
-int gk_phi_device_result(gk_phi_job *job, double **dev, int64_t *ld); /* final m x m matrix in HBM */
+int gk_phi_copy_out(gk_phi_job *job, double *host_out);            /* (row1-row0)*m doubles: this shard's rows */
+int gk_phi_device_result(gk_phi_job *job, double **dev, int64_t *ld); /* this shard's rows of the m x m matrix, in HBM */
 int gk_phi_get_stats(gk_phi_job *job, gk_phi_stats *stats);
 int gk_phi_cut_sizes(gk_phi_job *job, int32_t *sizes, int32_t cap);   /* |cut_g| as the reference counts them */
 int gk_phi_class_sizes(gk_phi_job *job, int32_t *sizes, int32_t cap); /* K_g actually stored */
