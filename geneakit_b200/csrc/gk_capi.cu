@@ -338,7 +338,7 @@ int gk_phi_run(gk_phi_job *j) {
             d.ld_prev = P.steps[g - 1].ld; d.ld_new = S.ld;
             d.K_prev = S.K_prev; d.K = S.K;
             d.desc = j->ints + o.desc;
-            d.nt = S.nt; d.npairs = (int64_t) S.nt * (S.nt + 1) / 2;
+            d.nt = S.nt; d.npairs = (int64_t) S.nt * (S.nt + 1) / 2; d.prefetch = gk::step_prefetch_default();
             GK_CUDA(cudaEventRecord(j->ev[g], st));
             GK_CUDA(gk::launch_step(d, P.ranked, st));
             launches++;

@@ -26,6 +26,7 @@
 //      both coalesced.
 // Pairs are enumerated I-major, so the CTAs resident at any time share rows(I): the scattered
 // list rows are then served from the 126 MB L2 instead of HBM.
+#include <cstdlib>
 #include "gk_kernels.cuh"
 #include "gk_plan.hpp"
 
@@ -40,8 +41,12 @@ constexpr int PL = W;                    // L pitch: (W + CAP + 1) rows x W doub
 constexpr int PR = W + CAP + 2;          // R pitch: (CAP + 1) rows x 74 doubles (16-byte aligned rows)
 constexpr int OFFR = (W + CAP + 1) * PL; // R starts after L inside one stage buffer
 constexpr int kStageDoubles = OFFR + (CAP + 1) * PR;
-constexpr size_t kStepSmem = (size_t) (2 * kStageDoubles + T * (T + 1)) * sizeof(double) +
-                             (size_t) 3 * 2 * DW * sizeof(int32_t) + 2 * sizeof(unsigned long long);
+// NSTAGE = 2: double-buffered pipeline, 2 CTAs / SM.  NSTAGE = 1: one buffer (the transpose
+// buffer aliases it), 4 CTAs / SM: the other resident CTAs hide the staging latency instead.
+constexpr size_t step_smem(int nstage) {
+    return (size_t) (nstage * kStageDoubles + (nstage > 1 ? T * (T + 1) : 0)) * sizeof(double) +
+           (size_t) 3 * 2 * DW * sizeof(int32_t) + 2 * sizeof(unsigned long long);
+}
 static_assert(kStageDoubles % 2 == 0 && OFFR % 2 == 0 && PR % 2 == 0, "16-byte alignment of staged rows");
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
@@ -155,12 +160,12 @@ __device__ __forceinline__ void issue_stage(double *S, unsigned long long *bar, 
     }
 }
 
-template <bool RANKED>
-__global__ void __launch_bounds__(kThreads, 2) phi_step_kernel(const StepDev s) {
+template <bool RANKED, int NSTAGE>
+__global__ void __launch_bounds__(kThreads, NSTAGE == 1 ? 4 : 2) phi_step_kernel(const StepDev s) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *Sbuf = reinterpret_cast<double *>(smem_raw);                  // 2 stage buffers
-    double *O = Sbuf + 2 * kStageDoubles;                                 // T x (T+1) transpose buffer
-    int32_t *Dbuf = reinterpret_cast<int32_t *>(O + T * (T + 1));          // 3 slots x (desc I, desc J)
+    double *Sbuf = reinterpret_cast<double *>(smem_raw);                  // NSTAGE stage buffers
+    double *O = NSTAGE > 1 ? Sbuf + NSTAGE * kStageDoubles : Sbuf;         // T x (T+1) transpose buffer (aliased when NSTAGE == 1)
+    int32_t *Dbuf = reinterpret_cast<int32_t *>(Sbuf + NSTAGE * kStageDoubles + (NSTAGE > 1 ? T * (T + 1) : 0));   // 3 slots x (desc I, desc J)
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(Dbuf + 3 * 2 * DW);   // one mbarrier per stage
 
     const int tid = threadIdx.x;
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 2) phi_step_kernel(const StepDev s) 
     if (k >= np) return;
 
     // ---- one-time setup: zero rows / columns for unknown parents, mbarriers ---------------------
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < NSTAGE; b++) {
         double *S = Sbuf + b * kStageDoubles;
         for (int i = tid; i < PL; i += kThreads) S[ZIDX * PL + i] = 0.0;            // L zero row
         for (int i = tid; i < PR; i += kThreads) S[OFFR + CAP * PR + i] = 0.0;       // R zero row
@@ -200,17 +205,20 @@ __global__ void __launch_bounds__(kThreads, 2) phi_step_kernel(const StepDev s) 
 
     for (int it = 0; k < np; k += stride, ++it) {
         const int32_t *dI = Dbuf + (it % 3) * 2 * DW, *dJ = dI + DW;
-        const double *S = Sbuf + (it & 1) * kStageDoubles;
+        double *S = Sbuf + (NSTAGE > 1 ? (it & 1) : 0) * kStageDoubles;
         cp_async_wait_all();
-        mbar_wait(&bars[it & 1], (unsigned) ((it >> 1) & 1));
+        if (NSTAGE > 1) mbar_wait(&bars[it & 1], (unsigned) ((it >> 1) & 1));
+        else mbar_wait(&bars[0], (unsigned) (it & 1));
         __syncthreads();       // pair k staged, next descriptors landed, everyone done with pair k-1
-        // ---- keep the memory system busy: rows of pair k+1, descriptors of pair k+2 ---------------
-        if (k + stride < np) {
-            const int32_t *nI = Dbuf + ((it + 1) % 3) * 2 * DW;
-            issue_stage(Sbuf + ((it + 1) & 1) * kStageDoubles, &bars[(it + 1) & 1], nI, nI + DW, Gp, ldp, lastrow, tid);
-            if (k + 2 * (long long) stride < np) load_desc(Dbuf + ((it + 2) % 3) * 2 * DW, s.desc, Inn, Jnn, tid);
+        if (NSTAGE > 1) {
+            // ---- keep the memory system busy: rows of pair k+1, descriptors of pair k+2 -----------
+            if (k + stride < np) {
+                const int32_t *nI = Dbuf + ((it + 1) % 3) * 2 * DW;
+                issue_stage(Sbuf + ((it + 1) & 1) * kStageDoubles, &bars[(it + 1) & 1], nI, nI + DW, Gp, ldp, lastrow, tid);
+                if (k + 2 * (long long) stride < np) load_desc(Dbuf + ((it + 2) % 3) * 2 * DW, s.desc, Inn, Jnn, tid);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
 
         // ---- pair k -----------------------------------------------------------------------------
         const int c0I = dI[0], cntI = dI[1] >> 16, cntJ = dJ[1] >> 16;
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 2) phi_step_kernel(const StepDev s) 
             for (int c = 0; c < CPT; c++) {
                 if (colok && a_base + 8 * c < cntI) *g = v[c];
                 g += 8 * ldn;
-                O[(a_base + 8 * c) * (T + 1) + b] = v[c];
+                if (NSTAGE > 1) O[(a_base + 8 * c) * (T + 1) + b] = v[c];
             }
         }
         if (I == J) {
@@ -296,8 +304,14 @@ __global__ void __launch_bounds__(kThreads, 2) phi_step_kernel(const StepDev s) 
                 else if (a0 != 0xFFFF && a1 != 0xFFFF) d = 0.5 + 0.5 * (a1 < W ? S[a0 * PL + a1] : S[OFFR + (a1 - W) * PR + a0]);
                 s.dnew[startI + tid] = d;
             }
+            if (NSTAGE == 1) __syncthreads();      // all reads of the single stage buffer are done
         } else {
             __syncthreads();
+            if (NSTAGE == 1) {                     // the transpose buffer aliases the (now dead) stage buffer
+#pragma unroll
+                for (int c = 0; c < CPT; c++) O[(a_base + 8 * c) * (T + 1) + b] = v[c];
+                __syncthreads();
+            }
             // mirror tile (J,I): thread (row bb = a_base + 8c of tile J, column aa = b of tile I); lanes along aa -> coalesced
             double *g = s.Gnew + (startJ + a_base) * ldn + startI + b;
             const bool colok = b < cntI;
@@ -307,9 +321,19 @@ __global__ void __launch_bounds__(kThreads, 2) phi_step_kernel(const StepDev s) 
                 if (colok && a_base + 8 * c < cntJ) *g = o[8 * c];
                 g += 8 * ldn;
             }
+            if (NSTAGE == 1) __syncthreads();      // before the next stage overwrites the aliased buffer
+        }
+        if (NSTAGE == 1) {
+            if (k + stride < np) {
+                const int32_t *nI = Dbuf + ((it + 1) % 3) * 2 * DW;
+                // (the aliased transpose buffer covers L rows 0..32 only: the zero rows / columns survive)
+                issue_stage(S, &bars[0], nI, nI + DW, Gp, ldp, lastrow, tid);
+                if (k + 2 * (long long) stride < np) load_desc(Dbuf + ((it + 2) % 3) * 2 * DW, s.desc, Inn, Jnn, tid);
+            }
+            cp_async_commit();
         }
         // L2 prefetch duty: the CTA that will open tile row Inn (two strides ahead) streams its list rows in
-        if (Jnn == 0 && (tid >> 5) == 7 && k + 2 * (long long) stride < np) prefetch_list_rows(s.desc, Inn, Gp, ldp, tid & 31);
+        if (s.prefetch && Jnn == 0 && (tid >> 5) == 7 && k + 2 * (long long) stride < np) prefetch_list_rows(s.desc, Inn, Gp, ldp, tid & 31);
         I = In; J = Jn; In = Inn; Jn = Jnn;
         advance_pair(Inn, Jnn, stride);
     }
@@ -451,31 +475,52 @@ __global__ void __launch_bounds__(256) gc_gather_kernel(const double *V, long lo
 
 }  // namespace
 
-size_t step_smem_bytes() { return kStepSmem; }
+static int g_stages = 2, g_prefetch = 1;
+int step_prefetch_default() { return g_prefetch; }
+size_t step_smem_bytes() { return step_smem(g_stages); }
 
-static int g_step_grid[2] = { 0, 0 };
+static int g_step_grid[2][2] = { { 0, 0 }, { 0, 0 } };    // [ranked][nstage - 1]
+
+template <bool RANKED, int NSTAGE>
+static cudaError_t configure_one(int sms) {
+    cudaError_t e;
+    const size_t smem = step_smem(NSTAGE);
+    if ((e = cudaFuncSetAttribute(phi_step_kernel<RANKED, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem))) return e;
+    int occ = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phi_step_kernel<RANKED, NSTAGE>, kThreads, smem))) return e;
+    g_step_grid[RANKED ? 1 : 0][NSTAGE - 1] = sms * (occ > 0 ? occ : 1);     // persistent: one wave, every CTA resident
+    return cudaSuccess;
+}
 
 cudaError_t configure_kernels() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(phi_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kStepSmem))) return e;
-    if ((e = cudaFuncSetAttribute(phi_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kStepSmem))) return e;
-    int dev = 0, sms = 0, occ = 0;
+    int dev = 0, sms = 0;
     if ((e = cudaGetDevice(&dev))) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev))) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phi_step_kernel<false>, kThreads, kStepSmem))) return e;
-    g_step_grid[0] = sms * (occ > 0 ? occ : 1);            // persistent: one wave, every CTA resident
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phi_step_kernel<true>, kThreads, kStepSmem))) return e;
-    g_step_grid[1] = sms * (occ > 0 ? occ : 1);
+    if ((e = configure_one<false, 1>(sms))) return e;
+    if ((e = configure_one<false, 2>(sms))) return e;
+    if ((e = configure_one<true, 1>(sms))) return e;
+    if ((e = configure_one<true, 2>(sms))) return e;
+    const char *env = getenv("GK_STAGES");
+    if (env && (env[0] == '1' || env[0] == '2')) g_stages = env[0] - '0';
+    env = getenv("GK_PREFETCH");
+    if (env && (env[0] == '0' || env[0] == '1')) g_prefetch = env[0] - '0';
     return cudaSuccess;
 }
 
 cudaError_t launch_step(const StepDev &s, bool ranked, cudaStream_t st) {
     if (s.nt <= 0) return cudaSuccess;
-    long long grid = g_step_grid[ranked ? 1 : 0];
+    long long grid = g_step_grid[ranked ? 1 : 0][g_stages - 1];
     if (grid <= 0) grid = 296;
     if (grid > s.npairs) grid = s.npairs;
-    if (ranked) phi_step_kernel<true><<<(unsigned) grid, kThreads, kStepSmem, st>>>(s);
-    else phi_step_kernel<false><<<(unsigned) grid, kThreads, kStepSmem, st>>>(s);
+    const size_t smem = step_smem(g_stages);
+    if (g_stages == 1) {
+        if (ranked) phi_step_kernel<true, 1><<<(unsigned) grid, kThreads, smem, st>>>(s);
+        else phi_step_kernel<false, 1><<<(unsigned) grid, kThreads, smem, st>>>(s);
+    } else {
+        if (ranked) phi_step_kernel<true, 2><<<(unsigned) grid, kThreads, smem, st>>>(s);
+        else phi_step_kernel<false, 2><<<(unsigned) grid, kThreads, smem, st>>>(s);
+    }
     return cudaGetLastError();
 }
 

@@ -16,6 +16,7 @@ struct StepDev {
     const int32_t *desc;     // nt tile descriptors of kDescWords int32 (layout: gk_plan.hpp)
     int64_t npairs;          // nt*(nt+1)/2 unordered tile pairs
     int32_t nt;
+    int32_t prefetch;        // 1: stream the list rows of upcoming tile rows into L2
 };
 
 struct ExpandDev {
@@ -34,6 +35,7 @@ struct ExpandDev {
 };
 
 size_t step_smem_bytes();
+int step_prefetch_default();
 cudaError_t launch_step(const StepDev &s, bool ranked, cudaStream_t st);
 cudaError_t launch_init(double *G0, double *d0, int64_t K0, int64_t ld0, cudaStream_t st);
 constexpr int kExpandCols = 1024;     // result columns per CTA of the expansion kernel
