@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--compress", type=int, default=-1)
-    ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--order", type=int, default=-1)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -182,7 +182,7 @@ def main():
     m = len(pro)
     stream = torch.cuda.Stream()          # a real stream: the default stream's handle is NULL
     torch.cuda.set_stream(stream)
-    job = gk.cgeneakit.DevicePhi(ped, pro, compress=args.compress, tile=args.tile, device=local,
+    job = gk.cgeneakit.DevicePhi(ped, pro, compress=args.compress, order=args.order, device=local,
                                  stream=stream.cuda_stream)
     job.upload()                                   # plan + buffers resident in HBM before timing
     st = job.stats()
@@ -236,7 +236,7 @@ def main():
             host = np.empty((m, m), dtype=np.float64)
             ptr = host.ctypes.data
         r = ped.ranks(pro)
-        opts = _lib.make_opts(device=local, compress=args.compress, tile=args.tile)
+        opts = _lib.make_opts(device=local, compress=args.compress, order=args.order)
         mu = C.c_double()
         check(lib.gk_phi_f64(len(ped), ped.sire, ped.dam, m, r, ptr, C.byref(mu), C.byref(opts)))   # warm
         t0 = time.time()

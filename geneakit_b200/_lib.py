@@ -20,7 +20,7 @@ _F = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 
 class gk_opts(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("verbose", C.c_int32),
-                ("compress", C.c_int32), ("tile", C.c_int32), ("rank", C.c_int32),
+                ("compress", C.c_int32), ("order", C.c_int32), ("rank", C.c_int32),
                 ("world", C.c_int32), ("reserved0", C.c_int32), ("stream", C.c_void_p)]
 
 
@@ -31,24 +31,24 @@ class gk_phi_stats(C.Structure):
                 ("cells_reference", C.c_int64), ("cells_device", C.c_int64),
                 ("algorithmic_bytes_reference", C.c_int64), ("algorithmic_bytes_device", C.c_int64),
                 ("device_bytes", C.c_int64), ("kernel_launches", C.c_int64),
-                ("plan_seconds", C.c_double), ("plan_bytes", C.c_int64)]
+                ("plan_seconds", C.c_double), ("plan_bytes", C.c_int64),
+                ("panel_row_bytes", C.c_int64), ("corrections", C.c_int64)]
 
 
 class gk_step_view(C.Structure):
     _P = C.POINTER(C.c_int32)
-    _fields_ = [("K", C.c_int64), ("ld", C.c_int64), ("K_prev", C.c_int64),
-                ("nt", C.c_int32), ("tile", C.c_int32), ("win", C.c_int32), ("lmax", C.c_int32),
-                ("nr_max", C.c_int32), ("desc_words", C.c_int32), ("conf_max", C.c_int32),
-                ("ranked", C.c_int32),
-                ("off_list", C.c_int32), ("off_conf", C.c_int32), ("off_la", C.c_int32),
-                ("off_pind", C.c_int32), ("off_rank", C.c_int32), ("reserved", C.c_int32),
-                ("desc", _P)]
+    _fields_ = [("K", C.c_int64), ("Kpad", C.c_int64), ("K_prev", C.c_int64), ("Kpad_prev", C.c_int64),
+                ("panel_rows", C.c_int64),
+                ("np", C.c_int32), ("panel", C.c_int32), ("ranked", C.c_int32), ("ngroups", C.c_int32),
+                ("panel_begin", C.c_int32), ("panel_end", C.c_int32),
+                ("pF", _P), ("pM", _P), ("flags", _P), ("cls_ind", _P), ("cls_size", _P),
+                ("pg_i", _P), ("pg_j", _P), ("pg_off", _P), ("pt_cls", _P), ("pt_mult", _P)]
 
 
-def make_opts(device=-1, verbose=False, compress=-1, tile=0, rank=0, world=1, stream=None):
+def make_opts(device=-1, verbose=False, compress=-1, order=-1, rank=0, world=1, stream=None):
     o = gk_opts()
     o.struct_size = C.sizeof(gk_opts)
-    o.device, o.verbose, o.compress, o.tile = int(device), int(bool(verbose)), int(compress), int(tile)
+    o.device, o.verbose, o.compress, o.order = int(device), int(bool(verbose)), int(compress), int(order)
     o.rank, o.world, o.reserved0 = int(rank), int(world), 0
     o.stream = stream
     return o
@@ -88,7 +88,14 @@ def _load():
     L.gk_phi_step_view.argtypes = [vp, i32, C.POINTER(gk_step_view)]
     L.gk_phi_final_view.argtypes = [vp, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32)),
                                     C.POINTER(i64)]
-    L.gk_phi_initial_classes.argtypes = [vp, C.POINTER(i64)]
+    L.gk_phi_ipc_export.argtypes = [vp, vp]
+    L.gk_phi_ipc_open.argtypes = [vp, i32, vp]
+    L.gk_phi_local_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.gk_phi_set_peer.argtypes = [vp, i32, vp, vp]
+    L.gk_phi_peers_ready.argtypes = [vp]
+    L.gk_phi_run_step.argtypes = [vp, i32]
+    L.gk_phi_finish.argtypes = [vp]
+    L.gk_phi_dvec.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
     L.gk_phi_free.argtypes = [vp]; L.gk_phi_free.restype = None
     return L
 
@@ -100,7 +107,9 @@ EXPORTS = [
     "gk_cut_sizes", "gk_shard_rows", "gk_last_error", "gk_abi_version", "gk_host_alloc", "gk_host_free",
     "gk_phi_plan", "gk_phi_upload", "gk_phi_run", "gk_phi_sync", "gk_phi_mean", "gk_phi_copy_out",
     "gk_phi_device_result", "gk_phi_get_stats", "gk_phi_cut_sizes", "gk_phi_class_sizes",
-    "gk_phi_step_times", "gk_phi_step_bytes", "gk_phi_free", "gk_phi_step_view", "gk_phi_final_view", "gk_phi_initial_classes",
+    "gk_phi_step_times", "gk_phi_step_bytes", "gk_phi_free", "gk_phi_step_view", "gk_phi_final_view",
+    "gk_phi_ipc_export", "gk_phi_ipc_open", "gk_phi_local_buffers", "gk_phi_set_peer", "gk_phi_peers_ready",
+    "gk_phi_run_step", "gk_phi_finish", "gk_phi_dvec",
 ]
 
 

@@ -59,7 +59,7 @@ def phi_device(gen, **kwargs):
     if pro is None:
         pro = cgeneakit.get_proband_ids(gen)
     job = cgeneakit.DevicePhi(gen, pro, kwargs.get('verbose', False),
-                              **{k: v for k, v in kwargs.items() if k in ('compress', 'tile', 'device')})
+                              **{k: v for k, v in kwargs.items() if k in ('compress', 'order', 'device')})
     return job.upload().run()
 
 

@@ -30,9 +30,13 @@ int cuda_fail(cudaError_t e, const char *what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #call);      \
     } while (0)
 
-constexpr int64_t kPadDoubles = 256;   // slack after every matrix: window reads may run past the last row
-
-struct StepOffsets { size_t desc; };
+struct StepOffsets {
+    size_t pF = 0, pM = 0, flags = 0, pg_i = 0, pg_j = 0, pg_off = 0, pt_cls = 0, pt_mult = 0, grp_off = 0, grp_info = 0;
+    size_t done = 0;              // offset into the counter arena: done1 at +0, done2 at +np
+    int32_t ngroups = 0, npatch = 0;
+    int64_t total_items = 0;
+    int32_t pb = 0, pe = 0, cpp = 0;      // own panels [pb, pe), panels per rank
+};
 
 }  // namespace
 
@@ -40,19 +44,30 @@ struct gk_phi_job {
     gk::PhiPlan plan;
     gk_opts opts{};
     int device = 0;
+    int rank = 0, world = 1;
     bool uploaded = false, ran = false;
+    int steps_done = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    double *buf[2] = { nullptr, nullptr };
-    int64_t buf_doubles[2] = { 0, 0 };
-    double *dvec[2] = { nullptr, nullptr };
-    double *out = nullptr;            // aliases buf[1 - parity(last)] (or buf[0] when single cut)
+    double *buf[2] = { nullptr, nullptr };            // own rows of the class matrices, ping-pong by step parity
+    double *peer[gk::kMaxShards][2] = {};             // every rank's buffers (own entry = buf); IPC mappings for the others
+    bool peer_ipc[gk::kMaxShards][2] = {};
+    bool peers_set = false;
+    double *dvec[2] = { nullptr, nullptr };           // self kinship per class (full length, replicated)
+    int64_t dvec_len = 0;
+    double *ring = nullptr;
+    int64_t ring_stride = 0;
+    double *out = nullptr;            // result rows; single GPU: aliases the buffer the last step does not use
+    double *out_own = nullptr;        // separately allocated result (world > 1)
+    double *gloc = nullptr;           // world > 1: class rows needed by the expansion, fetched from their owners
     double *partials = nullptr;
     double *sums_dev = nullptr;
     double *sums_host = nullptr;      // pinned
     int32_t *ints = nullptr;          // all plan arrays, one allocation
+    int32_t *counters = nullptr;
+    size_t counters_count = 0;
     std::vector<StepOffsets> off;
-    size_t off_final_cls = 0, off_final_ind = 0, off_cact = 0, off_coff = 0, off_cmem = 0, ints_count = 0;
+    size_t off_final_cls = 0, off_final_ind = 0, off_cact = 0, off_coff = 0, off_cmem = 0, off_flags0 = 0, ints_count = 0;
     int64_t row0 = 0, row1 = 0;       // result rows owned by this shard (caller order)
     int32_t nact = 0, nchunks = 0;
     int64_t nblocks_expand = 0;
@@ -67,12 +82,19 @@ namespace {
 void destroy(gk_phi_job *j) {
     if (!j) return;
     cudaSetDevice(j->device);
+    for (int q = 0; q < gk::kMaxShards; q++)
+        for (int p = 0; p < 2; p++)
+            if (j->peer_ipc[q][p] && j->peer[q][p]) cudaIpcCloseMemHandle(j->peer[q][p]);
     for (int p = 0; p < 2; p++) { if (j->buf[p]) cudaFree(j->buf[p]); if (j->dvec[p]) cudaFree(j->dvec[p]); }
+    if (j->ring) cudaFree(j->ring);
+    if (j->out_own) cudaFree(j->out_own);
+    if (j->gloc) cudaFree(j->gloc);
     if (j->partials) cudaFree(j->partials);
     if (j->scratch) cudaFree(j->scratch);
     if (j->sums_dev) cudaFree(j->sums_dev);
     if (j->sums_host) cudaFreeHost(j->sums_host);
     if (j->ints) cudaFree(j->ints);
+    if (j->counters) cudaFree(j->counters);
     for (cudaEvent_t e : j->ev) cudaEventDestroy(e);
     if (j->own_stream && j->stream) cudaStreamDestroy(j->stream);
     delete j;
@@ -97,6 +119,28 @@ int select_device(const gk_opts *o, int *dev_out) {
 
 std::once_flag g_cfg_once;
 cudaError_t g_cfg_err = cudaSuccess;
+
+// panels of step g owned by each rank: equal blocks of cpp = ceil(np / world) panels
+void panel_range(int np, int rank, int world, int32_t *pb, int32_t *pe, int32_t *cpp) {
+    const int c = (np + world - 1) / world;
+    *cpp = c;
+    *pb = std::min(np, rank * c);
+    *pe = std::min(np, (rank + 1) * c);
+}
+
+gk::RowTable row_table(const gk_phi_job *j, int g) {
+    gk::RowTable t{};
+    const gk::StepPlan &S = j->plan.steps[g];
+    const int cpp = j->off[g].cpp;
+    t.n = j->world;
+    for (int q = 0; q < gk::kMaxShards; q++) {
+        t.base[q] = q < j->world ? j->peer[q][g & 1] : nullptr;
+        t.row0[q] = (int32_t) std::min<int64_t>(S.Kpad, (int64_t) q * cpp * gk::kPanel);
+    }
+    t.row0[gk::kMaxShards] = (int32_t) S.Kpad;
+    for (int q = j->world; q <= gk::kMaxShards; q++) t.row0[q] = (int32_t) S.Kpad;
+    return t;
+}
 
 }  // namespace
 
@@ -208,16 +252,26 @@ int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, c
     *job = nullptr;
     gk_phi_job *j = new gk_phi_job();
     if (opts) std::memcpy(&j->opts, opts, std::min<size_t>(sizeof(gk_opts), (size_t) std::max(0, opts->struct_size)));
-    else { j->opts.device = -1; j->opts.compress = -1; }
+    else { j->opts.device = -1; j->opts.compress = -1; j->opts.order = -1; }
     if (j->opts.world < 1) j->opts.world = 1;
+    if (j->opts.world > gk::kMaxShards) { delete j; return fail(GK_ERR_ARG, "world > 8 shards"); }
     if (j->opts.rank < 0 || j->opts.rank >= j->opts.world) { delete j; return fail(GK_ERR_ARG, "rank outside [0, world)"); }
-    int tile = j->opts.tile;
-    if (!gk::build_phi_plan(n, sire, dam, m, pro, j->opts.compress, tile, j->plan)) {
+    j->rank = j->opts.rank; j->world = j->opts.world;
+    if (!gk::build_phi_plan(n, sire, dam, m, pro, j->opts.compress, j->opts.order, j->plan)) {
         int code = j->plan.error_code == 2 ? GK_ERR_INDEX : GK_ERR_ARG;
         std::string msg = j->plan.error;
         delete j;
         return fail(code, msg);
     }
+    if (j->world > 1 && j->plan.ranked) {
+        delete j;
+        return fail(GK_ERR_ARG, "pedigrees deeper than 26 generations (ranked rounding) run on one GPU per job");
+    }
+    const int G = j->plan.G;
+    j->off.assign(G, StepOffsets{});
+    for (int g = 0; g < G; g++)
+        panel_range(j->plan.steps[g].np, j->rank, j->world, &j->off[g].pb, &j->off[g].pe, &j->off[g].cpp);
+    gk_shard_rows(j->plan.m, j->rank, j->world, &j->row0, &j->row1);
     *job = j;
     return GK_OK;
 }
@@ -228,30 +282,53 @@ int gk_phi_upload(gk_phi_job *j) {
     int rc = select_device(&j->opts, &j->device);
     if (rc) return rc;
     std::call_once(g_cfg_once, [] { g_cfg_err = gk::configure_kernels(); });
-    if (g_cfg_err != cudaSuccess) return cuda_fail(g_cfg_err, "cudaFuncSetAttribute (is this an sm_100 device?)");
+    if (g_cfg_err != cudaSuccess) return cuda_fail(g_cfg_err, "kernel configuration (is this an sm_100 device?)");
     gk::PhiPlan &P = j->plan;
     const int G = P.G;
     if (j->opts.stream) j->stream = (cudaStream_t) j->opts.stream;
     else { GK_CUDA(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking)); j->own_stream = true; }
 
-    // ---- plan arrays: one int32 arena -------------------------------------------------------
+    // ---- plan arrays: one int32 arena (every array 16-byte aligned) -------------------------
     std::vector<int32_t> arena;
     auto push = [&](const std::vector<int32_t> &v) {
         size_t o = arena.size();
         arena.insert(arena.end(), v.begin(), v.end());
-        while (arena.size() % 4) arena.push_back(0);     // keep every array 16-byte aligned
+        while (arena.size() % 4) arena.push_back(0);
         return o;
     };
-    j->off.assign(G, StepOffsets{});
+    size_t ncount = 0;
+    j->off_flags0 = push(P.steps[0].flags);
     for (int g = 1; g < G; g++) {
         gk::StepPlan &S = P.steps[g];
         StepOffsets &o = j->off[g];
-        o.desc = push(S.desc);
+        o.pF = push(S.pF); o.pM = push(S.pM); o.flags = push(S.flags);
+        o.pg_i = push(S.pg_i); o.pg_j = push(S.pg_j); o.pg_off = push(S.pg_off);
+        o.pt_cls = push(S.pt_cls); o.pt_mult = push(S.pt_mult);
+        o.npatch = (int32_t) S.pg_i.size();
+        // work queue of the own panels: P1(pb), then P1(s), P2(s-1) ..., then P2(pe-1)
+        const int ncb = (int) ((S.Kpad_prev + gk::kCB - 1) / gk::kCB);
+        std::vector<int64_t> goff(1, 0);
+        std::vector<int32_t> ginfo;
+        auto add = [&](int phase, int panel) {
+            const int64_t items = phase == 1 ? ncb : (j->world > 1 ? S.np : panel + 1);
+            ginfo.push_back(panel | ((phase - 1) << 30));
+            goff.push_back(goff.back() + items);
+        };
+        for (int s = o.pb; s < o.pe; s++) {
+            add(1, s);
+            if (s > o.pb) add(2, s - 1);
+        }
+        if (o.pe > o.pb) add(2, o.pe - 1);
+        o.ngroups = (int32_t) ginfo.size();
+        o.total_items = goff.back();
+        std::vector<int32_t> g32(goff.size() * 2);
+        std::memcpy(g32.data(), goff.data(), goff.size() * 8);
+        o.grp_off = push(g32); o.grp_info = push(ginfo);
+        o.done = ncount; ncount += 2 * (size_t) S.np;
     }
     j->off_final_cls = push(P.final_cls);
     j->off_final_ind = push(P.final_ind);
     // result rows of this shard and, for the expansion kernel, its caller entries grouped by class
-    gk_shard_rows(P.m, j->opts.rank, j->opts.world, &j->row0, &j->row1);
     {
         const int64_t Kl = P.steps[G - 1].K;
         std::vector<int32_t> cnt((size_t) Kl + 1, 0), cact, coff(1, 0), cmem;
@@ -273,20 +350,24 @@ int gk_phi_upload(gk_phi_job *j) {
     GK_CUDA(cudaMemcpyAsync(j->ints, arena.data(), arena.size() * sizeof(int32_t), cudaMemcpyHostToDevice, j->stream));
     GK_CUDA(cudaStreamSynchronize(j->stream));
     j->device_bytes += (int64_t) arena.size() * 4;
+    j->counters_count = std::max<size_t>(ncount, 1);
+    GK_CUDA(cudaMalloc(&j->counters, j->counters_count * sizeof(int32_t)));
 
-    // ---- matrices: two ping-pong buffers; the m x m result aliases the one the last step read --
+    // ---- matrices: two ping-pong buffers holding the own rows of each cut's class matrix --------
     int64_t need[2] = { 0, 0 };
-    int64_t maxK = 1;
+    int64_t max_prev = 1, dlen = 1;
     for (int g = 0; g < G; g++) {
         const gk::StepPlan &S = P.steps[g];
-        need[g & 1] = std::max(need[g & 1], S.K * S.ld + kPadDoubles);
-        maxK = std::max(maxK, S.K);
+        const int64_t rows = (int64_t) (j->off[g].pe - j->off[g].pb) * gk::kPanel;
+        need[g & 1] = std::max(need[g & 1], rows * S.Kpad);
+        if (g + 1 < G) max_prev = std::max(max_prev, S.Kpad);
+        dlen = std::max(dlen, (int64_t) j->off[g].cpp * gk::kPanel * j->world);
     }
     const int64_t mm = (j->row1 - j->row0) * (int64_t) P.m;
     const int out_buf = P.single_cut ? 0 : 1 - ((G - 1) & 1);
-    need[out_buf] = std::max(need[out_buf], mm + kPadDoubles);
+    if (j->world == 1) need[out_buf] = std::max(need[out_buf], mm);
     for (int p = 0; p < 2; p++) {
-        if (need[p] == 0) continue;
+        need[p] = std::max<int64_t>(need[p], 32);
         cudaError_t e = cudaMalloc(&j->buf[p], (size_t) need[p] * sizeof(double));
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -295,11 +376,22 @@ int gk_phi_upload(gk_phi_job *j) {
                           need[0] * 8 / 1e9, need[1] * 8 / 1e9);
             return fail(GK_ERR_OOM, msg);
         }
-        j->buf_doubles[p] = need[p];
         j->device_bytes += need[p] * 8;
+        j->peer[j->rank][p] = j->buf[p];
     }
-    j->out = j->buf[out_buf];
-    for (int p = 0; p < 2; p++) { GK_CUDA(cudaMalloc(&j->dvec[p], (size_t) maxK * sizeof(double))); j->device_bytes += maxK * 8; }
+    if (j->world == 1) { j->out = j->buf[out_buf]; j->peers_set = true; }
+    else {
+        GK_CUDA(cudaMalloc(&j->out_own, (size_t) std::max<int64_t>(mm, 1) * sizeof(double)));
+        j->out = j->out_own;
+        const int64_t gl = (int64_t) std::max(j->nact, 1) * P.steps[G - 1].Kpad;
+        GK_CUDA(cudaMalloc(&j->gloc, (size_t) gl * sizeof(double)));
+        j->device_bytes += (mm + gl) * 8;
+    }
+    j->dvec_len = dlen;
+    for (int p = 0; p < 2; p++) { GK_CUDA(cudaMalloc(&j->dvec[p], (size_t) dlen * sizeof(double))); j->device_bytes += dlen * 8; }
+    j->ring_stride = max_prev * gk::kPanel;
+    GK_CUDA(cudaMalloc(&j->ring, (size_t) gk::kRing * j->ring_stride * sizeof(double)));
+    j->device_bytes += gk::kRing * j->ring_stride * 8;
     GK_CUDA(cudaMalloc(&j->partials, (size_t) std::max<int64_t>(j->nblocks_expand, 1) * 2 * sizeof(double)));
     GK_CUDA(cudaMalloc(&j->scratch, 2 * 256 * sizeof(double)));
     j->device_bytes += j->nblocks_expand * 16;
@@ -311,59 +403,167 @@ int gk_phi_upload(gk_phi_job *j) {
     return GK_OK;
 }
 
-int gk_phi_run(gk_phi_job *j) {
-    if (!j) return fail(GK_ERR_ARG, "null job");
-    if (!j->uploaded) return fail(GK_ERR_STATE, "gk_phi_run before gk_phi_upload");
+// ---- multi-GPU plumbing: every rank's ping-pong buffers become addressable by every rank -------
+int gk_phi_ipc_export(gk_phi_job *j, void *handles /* 2 * 64 bytes */) {
+    if (!j || !j->uploaded || !handles) return fail(GK_ERR_STATE, "job not uploaded");
     GK_CUDA(cudaSetDevice(j->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    for (int p = 0; p < 2; p++)
+        GK_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handles) + p, j->buf[p]));
+    return GK_OK;
+}
+int gk_phi_ipc_open(gk_phi_job *j, int32_t q, const void *handles) {
+    if (!j || !j->uploaded || !handles) return fail(GK_ERR_STATE, "job not uploaded");
+    if (q < 0 || q >= j->world || q == j->rank) return fail(GK_ERR_ARG, "bad peer rank");
+    GK_CUDA(cudaSetDevice(j->device));
+    for (int p = 0; p < 2; p++) {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, reinterpret_cast<const cudaIpcMemHandle_t *>(handles) + p, sizeof h);
+        void *ptr = nullptr;
+        GK_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        j->peer[q][p] = static_cast<double *>(ptr);
+        j->peer_ipc[q][p] = true;
+    }
+    return GK_OK;
+}
+int gk_phi_local_buffers(gk_phi_job *j, void **buf0, void **buf1) {
+    if (!j || !j->uploaded) return fail(GK_ERR_STATE, "job not uploaded");
+    if (buf0) *buf0 = j->buf[0];
+    if (buf1) *buf1 = j->buf[1];
+    return GK_OK;
+}
+int gk_phi_set_peer(gk_phi_job *j, int32_t q, void *buf0, void *buf1) {
+    if (!j || !j->uploaded) return fail(GK_ERR_STATE, "job not uploaded");
+    if (q < 0 || q >= j->world || q == j->rank) return fail(GK_ERR_ARG, "bad peer rank");
+    j->peer[q][0] = static_cast<double *>(buf0); j->peer[q][1] = static_cast<double *>(buf1);
+    return GK_OK;
+}
+int gk_phi_peers_ready(gk_phi_job *j) {
+    if (!j || !j->uploaded) return fail(GK_ERR_STATE, "job not uploaded");
+    for (int q = 0; q < j->world; q++)
+        for (int p = 0; p < 2; p++)
+            if (!j->peer[q][p]) return fail(GK_ERR_STATE, "a peer buffer has not been set");
+    j->peers_set = true;
+    return GK_OK;
+}
+int gk_phi_dvec(gk_phi_job *j, int32_t step, void **dev, int64_t *chunk_doubles, int64_t *total_doubles) {
+    if (!j || !j->uploaded || step < 0 || step >= j->plan.G) return fail(GK_ERR_ARG, "bad step");
+    if (dev) *dev = j->dvec[step & 1];
+    if (chunk_doubles) *chunk_doubles = (int64_t) j->off[step].cpp * gk::kPanel;
+    if (total_doubles) *total_doubles = (int64_t) j->off[step].cpp * gk::kPanel * j->world;
+    return GK_OK;
+}
+
+// One cut: step 0 initialises the founders' matrix, step g >= 1 runs the recurrence kernel and the
+// diagonal kernel.  With world > 1 the driver all-gathers the self-kinship vector (gk_phi_dvec) after
+// every step -- that collective is also the barrier that makes the rows written here readable by
+// the peers' next step.
+int gk_phi_run_step(gk_phi_job *j, int32_t g) {
+    if (!j) return fail(GK_ERR_ARG, "null job");
+    if (!j->uploaded) return fail(GK_ERR_STATE, "gk_phi_run_step before gk_phi_upload");
+    if (!j->peers_set) return fail(GK_ERR_STATE, "peer buffers are not set (gk_phi_ipc_open / gk_phi_set_peer, gk_phi_peers_ready)");
+    gk::PhiPlan &P = j->plan;
+    if (g < 0 || g >= P.G) return fail(GK_ERR_ARG, "bad step");
+    GK_CUDA(cudaSetDevice(j->device));
+    cudaStream_t st = j->stream;
+    const gk::StepPlan &S = P.steps[g];
+    const StepOffsets &o = j->off[g];
+    if (g == 0) {
+        GK_CUDA(cudaMemsetAsync(j->counters, 0, j->counters_count * sizeof(int32_t), st));
+        j->launches = 0;
+        if (P.single_cut) { j->steps_done = 1; return GK_OK; }
+        // own rows of the founders' matrix
+        const int64_t rows = (int64_t) (o.pe - o.pb) * gk::kPanel;
+        if (j->world == 1) {
+            GK_CUDA(gk::launch_init(j->buf[0], j->dvec[0], j->ints + j->off_flags0, S.K, S.Kpad, st));
+        } else {
+            // (rare) uncompressed multi-GPU start: every rank zeroes its rows, the diagonal comes from the flags
+            GK_CUDA(cudaMemsetAsync(j->buf[0], 0, (size_t) std::max<int64_t>(rows * S.Kpad, 1) * sizeof(double), st));
+            GK_CUDA(gk::launch_init_rows(j->buf[0], j->dvec[0], j->ints + j->off_flags0, S.K, S.Kpad,
+                                         (int64_t) o.pb * gk::kPanel, rows, j->dvec_len, st));
+        }
+        j->launches++;
+        j->steps_done = 1;
+        return GK_OK;
+    }
+    if (j->opts.verbose && j->rank == 0) std::printf("Cut %d out of %d\n", g, P.G);
+    gk::StepDev d{};
+    d.prev = row_table(j, g - 1); d.out = row_table(j, g);
+    d.ld_prev = S.Kpad_prev; d.ld_new = S.Kpad;
+    d.Kpad_prev = (int32_t) S.Kpad_prev; d.np = S.np;
+    d.pF = j->ints + o.pF; d.pM = j->ints + o.pM;
+    d.ring = j->ring; d.ring_stride = j->ring_stride;
+    d.done1 = j->counters + o.done; d.done2 = d.done1 + S.np;
+    d.grp_off = reinterpret_cast<const int64_t *>(j->ints + o.grp_off); d.grp_info = j->ints + o.grp_info;
+    d.total_items = o.total_items; d.ngroups = o.ngroups;
+    d.ncb = (int32_t) ((S.Kpad_prev + gk::kCB - 1) / gk::kCB);
+    d.panel_begin = o.pb; d.panel_end = o.pe;
+    d.full_rows = j->world > 1 ? 1 : 0;
+    GK_CUDA(cudaEventRecord(j->ev[g], st));
+    GK_CUDA(gk::launch_step(d, st));
+    gk::DiagDev q{};
+    q.prev = d.prev; q.out = d.out; q.ld_prev = d.ld_prev; q.ld_new = d.ld_new;
+    q.dprev = j->dvec[(g - 1) & 1]; q.dnew = j->dvec[g & 1];
+    q.pF = d.pF; q.pM = d.pM; q.flags = j->ints + o.flags;
+    q.c_begin = (int32_t) std::min<int64_t>(S.K, (int64_t) o.pb * gk::kPanel);
+    q.c_end = (int32_t) std::min<int64_t>(S.K, (int64_t) o.pe * gk::kPanel);
+    q.pg_i = j->ints + o.pg_i; q.pg_j = j->ints + o.pg_j; q.pg_off = j->ints + o.pg_off;
+    q.pt_cls = j->ints + o.pt_cls; q.pt_mult = j->ints + o.pt_mult; q.ngroups = o.npatch;
+    GK_CUDA(gk::launch_diag(q, st));
+    GK_CUDA(cudaEventRecord(j->ev[g + 1], st));        // (overwritten by the next step's start record: same instant)
+    j->launches += 2;
+    j->steps_done = g + 1;
+    return GK_OK;
+}
+
+// Final expansion to the caller's proband order + the fused phiMean partial sums of the own rows.
+int gk_phi_finish(gk_phi_job *j) {
+    if (!j || !j->uploaded) return fail(GK_ERR_STATE, "job not uploaded");
     gk::PhiPlan &P = j->plan;
     const int G = P.G;
+    if (j->steps_done < G) return fail(GK_ERR_STATE, "gk_phi_finish before the last gk_phi_run_step");
+    GK_CUDA(cudaSetDevice(j->device));
     cudaStream_t st = j->stream;
-    int64_t launches = 0;
-    if (j->opts.verbose) {
-        // same text as lib/compute.cpp:662-676
-        for (int g = 0; g < G; g++) std::printf("Cut size %d/%d: %d\n", g + 1, G, (int) P.steps[g].cut_size);
-        std::printf("Computing the kinship matrix:\n");
-    }
-    if (!P.single_cut) {
-        const gk::StepPlan &S0 = P.steps[0];
-        GK_CUDA(gk::launch_init(j->buf[0], j->dvec[0], S0.K, S0.ld, st));
-        launches++;
-        for (int g = 1; g < G; g++) {
-            if (j->opts.verbose) std::printf("Cut %d out of %d\n", g, G);
-            const gk::StepPlan &S = P.steps[g];
-            const StepOffsets &o = j->off[g];
-            gk::StepDev d{};
-            d.Gprev = j->buf[(g - 1) & 1]; d.dprev = j->dvec[(g - 1) & 1];
-            d.Gnew = j->buf[g & 1]; d.dnew = j->dvec[g & 1];
-            d.ld_prev = P.steps[g - 1].ld; d.ld_new = S.ld;
-            d.K_prev = S.K_prev; d.K = S.K;
-            d.desc = j->ints + o.desc;
-            d.nt = S.nt; d.npairs = (int64_t) S.nt * (S.nt + 1) / 2; d.prefetch = gk::step_prefetch_default();
-            GK_CUDA(cudaEventRecord(j->ev[g], st));
-            GK_CUDA(gk::launch_step(d, P.ranked, st));
-            launches++;
-        }
-        GK_CUDA(cudaEventRecord(j->ev[G], st));
-    }
     const int last = G - 1;
+    GK_CUDA(cudaEventRecord(j->ev[G], st));
     if (P.single_cut) {
         GK_CUDA(gk::launch_eye(j->out, P.m, j->row0, j->row1, j->partials, st));
     } else {
         gk::ExpandDev e{};
-        e.G = j->buf[last & 1]; e.d = j->dvec[last & 1]; e.ld = P.steps[last].ld;
+        e.d = j->dvec[last & 1]; e.ld = P.steps[last].Kpad;
         e.cls = j->ints + j->off_final_cls; e.ind = j->ints + j->off_final_ind;
         e.cact = j->ints + j->off_cact; e.coff = j->ints + j->off_coff; e.cmem = j->ints + j->off_cmem;
         e.out = j->out; e.m = P.m; e.row0 = j->row0; e.row1 = j->row1;
         e.nact = j->nact; e.nchunks = j->nchunks; e.partials = j->partials;
+        if (j->world == 1) { e.G = j->buf[last & 1]; e.compact = 0; }
+        else {
+            // the class rows of the own probands live on their owners: fetch them (coalesced peer reads)
+            GK_CUDA(gk::launch_fetch_rows(row_table(j, last), e.ld, e.cact, j->nact, j->gloc, st));
+            j->launches++;
+            e.G = j->gloc; e.compact = 1;
+        }
         GK_CUDA(gk::launch_expand(e, st));
     }
     GK_CUDA(gk::launch_mean_finish(j->partials, j->nblocks_expand, j->scratch, j->sums_dev, st));
     GK_CUDA(cudaEventRecord(j->ev[G + 1], st));
-    launches += 3;
+    j->launches += 3;
     GK_CUDA(cudaMemcpyAsync(j->sums_host, j->sums_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    j->launches = launches;
     j->ran = true;
     return GK_OK;
+}
+
+int gk_phi_run(gk_phi_job *j) {
+    if (!j) return fail(GK_ERR_ARG, "null job");
+    if (!j->uploaded) return fail(GK_ERR_STATE, "gk_phi_run before gk_phi_upload");
+    if (j->world > 1) return fail(GK_ERR_STATE, "a sharded job is driven step by step (gk_phi_run_step + the all-gather of gk_phi_dvec)");
+    gk::PhiPlan &P = j->plan;
+    if (j->opts.verbose) {
+        // same text as lib/compute.cpp:662-676
+        for (int g = 0; g < P.G; g++) std::printf("Cut size %d/%d: %d\n", g + 1, P.G, (int) P.steps[g].cut_size);
+        std::printf("Computing the kinship matrix:\n");
+    }
+    for (int g = 0; g < P.G; g++) { int rc = gk_phi_run_step(j, g); if (rc) return rc; }
+    return gk_phi_finish(j);
 }
 
 int gk_phi_sync(gk_phi_job *j) {
@@ -409,7 +609,7 @@ int gk_phi_get_stats(gk_phi_job *j, gk_phi_stats *s) {
     const gk::PhiPlan &P = j->plan;
     std::memset(s, 0, sizeof *s);
     s->n_cuts = P.G; s->n_steps = P.G - 1; s->compressed = P.compressed; s->ranked = P.ranked;
-    s->tile = P.tile; s->m = P.m;
+    s->tile = gk::kPanel; s->m = P.m;
     for (int g = 0; g < P.G; g++) {
         const gk::StepPlan &S = P.steps[g];
         s->max_cut = std::max(s->max_cut, S.cut_size);
@@ -420,20 +620,17 @@ int gk_phi_get_stats(gk_phi_job *j, gk_phi_stats *s) {
             s->cells_device += S.K * S.K;
             s->algorithmic_bytes_reference += 8 * (S.P_ref * Sp.cut_size + S.cut_size * S.cut_size - S.n_kept * S.n_kept);
             s->algorithmic_bytes_device += 8 * (S.P_cls * Sp.K + S.K * S.K - S.kept_cls * S.kept_cls);
+            s->panel_row_bytes += 8 * S.panel_rows * Sp.Kpad;
+            s->corrections += (int64_t) S.pg_i.size();
         }
     }
     const int64_t mm = (int64_t) P.m * P.m, Kl = P.steps[P.G - 1].K;
     s->cells_device += mm;
     s->algorithmic_bytes_device += 8 * (mm + std::min(mm, Kl * Kl));
     s->device_bytes = j->device_bytes;
-    s->kernel_launches = j->launches ? j->launches : (P.single_cut ? 3 : P.G + 3);
+    s->kernel_launches = j->launches ? j->launches : (P.single_cut ? 3 : 2 * (P.G - 1) + 4);
     s->plan_seconds = P.plan_seconds;
-    int64_t ints = (int64_t) P.final_cls.size() + (int64_t) P.final_ind.size();
-    for (int g = 1; g < P.G; g++) {
-        const gk::StepPlan &S = P.steps[g];
-        ints += (int64_t) S.desc.size();
-    }
-    s->plan_bytes = ints * 4;
+    s->plan_bytes = (int64_t) j->ints_count * 4;
     return GK_OK;
 }
 
@@ -472,14 +669,18 @@ int gk_phi_step_bytes(gk_phi_job *j, int64_t *bytes, int32_t cap) {
 }
 
 int gk_phi_step_view(gk_phi_job *j, int32_t step, gk_step_view *v) {
-    if (!j || !v || step < 1 || step >= j->plan.G) return fail(GK_ERR_ARG, "bad step");
+    if (!j || !v || step < 0 || step >= j->plan.G) return fail(GK_ERR_ARG, "bad step");
     const gk::PhiPlan &P = j->plan;
     const gk::StepPlan &S = P.steps[step];
-    v->K = S.K; v->ld = S.ld; v->K_prev = S.K_prev; v->nt = S.nt; v->tile = P.tile; v->win = P.win;
-    v->lmax = P.lmax; v->nr_max = S.nr_max;
-    v->desc = S.desc.data(); v->desc_words = gk::kDescWords; v->conf_max = gk::kConfMax;
-    v->off_list = gk::kDescList; v->off_conf = gk::kDescConf; v->off_la = gk::kDescLa;
-    v->off_pind = gk::kDescPind; v->off_rank = gk::kDescRank; v->ranked = P.ranked ? 1 : 0;
+    std::memset(v, 0, sizeof *v);
+    v->K = S.K; v->Kpad = S.Kpad; v->K_prev = S.K_prev; v->Kpad_prev = S.Kpad_prev;
+    v->np = S.np; v->panel = gk::kPanel; v->ranked = P.ranked ? 1 : 0; v->ngroups = (int32_t) S.pg_i.size();
+    v->panel_begin = j->off[step].pb; v->panel_end = j->off[step].pe;
+    v->pF = S.pF.data(); v->pM = S.pM.data(); v->flags = S.flags.data();
+    v->cls_ind = S.cls_ind.data(); v->cls_size = S.cls_size.data();
+    v->pg_i = S.pg_i.data(); v->pg_j = S.pg_j.data(); v->pg_off = S.pg_off.data();
+    v->pt_cls = S.pt_cls.data(); v->pt_mult = S.pt_mult.data();
+    v->panel_rows = S.panel_rows;
     return GK_OK;
 }
 int gk_phi_final_view(gk_phi_job *j, const int32_t **cls, const int32_t **ind, int64_t *K_last) {
@@ -487,11 +688,6 @@ int gk_phi_final_view(gk_phi_job *j, const int32_t **cls, const int32_t **ind, i
     if (cls) *cls = j->plan.final_cls.data();
     if (ind) *ind = j->plan.final_ind.data();
     if (K_last) *K_last = j->plan.steps[j->plan.G - 1].K;
-    return GK_OK;
-}
-int gk_phi_initial_classes(gk_phi_job *j, int64_t *K0) {
-    if (!j || !K0) return fail(GK_ERR_ARG, "null argument");
-    *K0 = j->plan.steps[0].K;
     return GK_OK;
 }
 

@@ -3,29 +3,30 @@
 // The step kernel replaces the reference's hot loop nest
 //   compute_kinship_between_probands (lib/compute.cpp:571-588)  [n'(n'-1)/2 calls of]
 //   compute_kinship                  (lib/compute.cpp:491-550)
+// for one pair of adjacent vertex cuts; the diagonal kernel replaces
 //   compute_kinship_with_oneself     (lib/compute.cpp:553-568)
-// for one pair of adjacent vertex cuts.  It is an HBM-bound FP64 gather-average: per output
-// cell 4 gathered reads, 3 DADD + 1 DMUL, one 8-byte store.  Tensor cores are not used.
+// and applies the "same individual" rule (:522-528).  The step is an HBM-bound FP64
+// gather-average, B = P A P^T with two 1/2 entries per row of P.  Tensor cores are not used.
 //
-// PERSISTENT kernel, 2 CTAs per SM, each walking the unordered tile pairs (I >= J) of the new
-// matrix with a grid stride, software-pipelined: while pair k is computed from stage buffer
-// k&1, the parent rows of pair k+1 are landing in the other buffer and the descriptors of pair
-// k+2 in a third descriptor slot.  Per pair:
-//   1. stage E[rows(I)][cols(J)] of the PREVIOUS matrix.  rows(I)/cols(J) = the tile's
-//      contiguous parent WINDOW + its LIST of scattered parent rows:
-//        L[r][0..W)   = G[row r of I][window of J]      one 256-byte BULK async copy per row
-//        R[j][0..W)   = G[list row j of J][window of I] (the window x list block through the
-//                       symmetric entry)                one 256-byte BULK async copy per row
-//        R[j][W + r]  = G[list row r of I][list col j of J]   8-byte cp.async gathers (L2 hits)
-//      Bulk copies (cp.async.bulk -> UBLKCP, the TMA engine) complete on an mbarrier.
-//   2. out[a][b] = 1/4 * ((p + q) + (r + s)) from shared memory (RANKED: grouping chosen per pair
-//      by rank, reproducing the reference's rounding on pedigrees deeper than 26); unknown
-//      parents index an all-zero row; tile pairs that share a parent individual apply
-//      "same individual -> self kinship" (:522-528),
-//   3. store tile (I,J) from registers and, transposed through shared memory, its mirror (J,I):
-//      both coalesced.
-// Pairs are enumerated I-major, so the CTAs resident at any time share rows(I): the scattered
-// list rows are then served from the 126 MB L2 instead of HBM.
+// FACTORISED, two phases per PANEL I of 32 new classes, inside ONE persistent launch:
+//   phase 1 (I, cb):  N[i][c] = 1/2 (A[F_i][c] + A[M_i][c]),  i in I, c in a block of 64 columns.
+//            Reads 64-column segments of whole rows of A (512 B, coalesced; rows may live on a peer
+//            GPU: the row table holds CUDA-IPC mappings, the loads cross NVLink), transposes the
+//            32 x 64 tile through shared memory and stores N^T[c][0..32) (16 KB contiguous) into
+//            one of kRing panel buffers that stay resident in the 126 MB L2.
+//   phase 2 (I, J):   B[j][i] = 1/2 (N^T[F_j][i] + N^T[M_j][i]),  j in tile J, i in I.
+//            Reads two 256-byte rows of the L2-resident panel per class j, stores the 32 x 32 tile
+//            (J,I) directly and its mirror (I,J) transposed through shared memory: both coalesced.
+//            Only tiles J <= I are evaluated (full_rows = 0); a rank that owns a row block of a
+//            sharded matrix evaluates every J and stores only its own rows (full_rows = 1).
+// Work items are dealt round-robin to the resident CTAs in QUEUE ORDER
+//   P1(0), P1(1), P2(0), P1(2), P2(1), ...
+// and an item waits only on items that precede it in the queue (phase 2 of panel I on the ncb
+// phase-1 items of I; phase 1 of panel I on phase 2 of panel I - kRing, whose ring slot it
+// overwrites), so the wait can never deadlock: the lowest unfinished item never waits.
+// No 8-byte gathers, no index arithmetic per element: every global access is a 256/512-byte
+// segment.  In RANKED mode (pedigrees deeper than 26 generations) the planner orders the classes
+// by descending rank, which makes "J <= I" the reference's rounding order (gk_plan.hpp).
 #include <cstdlib>
 #include "gk_kernels.cuh"
 #include "gk_plan.hpp"
@@ -35,319 +36,187 @@ namespace gk {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int T = kTile, W = kWin, CAP = kListCap, DW = kDescWords;
-constexpr int ZIDX = W + CAP;            // local index of the all-zero row / column (unknown parent)
-constexpr int PL = W;                    // L pitch: (W + CAP + 1) rows x W doubles
-constexpr int PR = W + CAP + 2;          // R pitch: (CAP + 1) rows x 74 doubles (16-byte aligned rows)
-constexpr int OFFR = (W + CAP + 1) * PL; // R starts after L inside one stage buffer
-constexpr int kStageDoubles = OFFR + (CAP + 1) * PR;
-// NSTAGE = 2: double-buffered pipeline, 2 CTAs / SM.  NSTAGE = 1: one buffer (the transpose
-// buffer aliases it), 4 CTAs / SM: the other resident CTAs hide the staging latency instead.
-constexpr size_t step_smem(int nstage) {
-    return (size_t) (nstage * kStageDoubles + (nstage > 1 ? T * (T + 1) : 0)) * sizeof(double) +
-           (size_t) 3 * 2 * DW * sizeof(int32_t) + 2 * sizeof(unsigned long long);
-}
-static_assert(kStageDoubles % 2 == 0 && OFFR % 2 == 0 && PR % 2 == 0, "16-byte alignment of staged rows");
+constexpr int T = kPanel;                 // 32
+constexpr int PS1 = kCB + 1;              // phase-1 transpose pitch (doubles): conflict-free both ways
+constexpr int PS2 = T + 1;                // phase-2 transpose pitch
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+__device__ __forceinline__ void wait_count(const int *p, int target) {
+    while (ld_acquire(p) < target) __nanosleep(32);
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
-// ---- mbarrier + bulk async copy (TMA engine, 1-D) ---------------------------------------------
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "GK_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra GK_DONE;\n"
-        "bra GK_WAIT;\n"
-        "GK_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_256(void *smem, const void *gmem, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(W * 8), "r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void signal_count(int *p) {
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.s32 [%0], 1;\n" ::"l"(p) : "memory");
 }
 
-__device__ __forceinline__ void pair_to_tiles(long long k, int &I, int &J) {
-    int i = (int) ((sqrt(8.0 * (double) k + 1.0) - 1.0) * 0.5);
-    while ((long long) i * (i + 1) / 2 > k) --i;
-    while ((long long) (i + 1) * (i + 2) / 2 <= k) ++i;
-    I = i;
-    J = (int) (k - (long long) i * (i + 1) / 2);
-}
-__device__ __forceinline__ void advance_pair(int &I, int &J, int step) {   // pair index += step (row-major triangle)
-    J += step;
-    while (J > I) { J -= I + 1; ++I; }
-}
-
-// descriptors of tiles I and J -> slot (2*DW int32), 16-byte cp.async
-__device__ __forceinline__ void load_desc(int32_t *slot, const int32_t *desc, int I, int J, int tid) {
-    constexpr int CH = DW / 4;
-    if (tid < 2 * CH) {
-        const int t = tid < CH ? I : J, c = tid < CH ? tid : tid - CH;
-        cp_async16(slot + (tid < CH ? 0 : DW) + 4 * c, desc + (size_t) t * DW + 4 * c);
-    }
-}
-
-// Ask the L2 to stream in the scattered parent rows of a tile that the sweep reaches two waves
-// from now: turns the first touch of those rows (otherwise random 32-byte sector misses of the
-// list x list gathers) into sequential DRAM reads.
-__device__ __forceinline__ void prefetch_list_rows(const int32_t *desc, int tile, const double *Gp, long long ldp, int lane) {
-    const int32_t *d = desc + (size_t) tile * DW;
-    const int nl = d[1] & 0xFFFF;
-    if (lane < nl || lane + 32 < nl) {
-        const unsigned row_bytes = (unsigned) (ldp * 8);
-        for (int r = lane; r < nl; r += 32) {
-            const char *p = reinterpret_cast<const char *>(Gp + (long long) d[kDescList + r] * ldp);
-            for (unsigned off = 0; off < row_bytes; off += 65536u) {
-                const unsigned n = row_bytes - off < 65536u ? row_bytes - off : 65536u;
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p + off), "r"(n) : "memory");
-            }
-        }
-    }
-}
-
-// stage E[rows(I)][cols(J)] of the previous matrix into one stage buffer (all asynchronous)
-__device__ __forceinline__ void issue_stage(double *S, unsigned long long *bar, const int32_t *dI, const int32_t *dJ,
-                                            const double *__restrict__ Gp, long long ldp, int lastrow, int tid) {
-    const int c0I = dI[0], nlI = dI[1] & 0xFFFF, c0J = dJ[0], nlJ = dJ[1] & 0xFFFF;
-    const int32_t *listI = dI + kDescList, *listJ = dJ + kDescList;
-    const int nrI = W + nlI;
-    const int lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) mbar_expect_tx(bar, (unsigned) ((nrI + nlJ) * W * 8));
-    // bulk copies, interleaved over the 8 warps (the issue loop is serial inside a warp):
-    // copy c < nrI        : L[c][:]        = G[row c of I][window of J]
-    // copy nrI <= c       : R[c - nrI][:W] = G[list row of J][window of I]
-    {
-        const int c = lane * 8 + warp;
-        if (c < nrI) {
-            int row = c < W ? c0I + c : listI[c - W];
-            row = row > lastrow ? lastrow : row;
-            bulk_copy_256(S + c * PL, Gp + (long long) row * ldp + c0J, bar);
-        } else if (c < nrI + nlJ) {
-            const int j = c - nrI;
-            bulk_copy_256(S + OFFR + j * PR, Gp + (long long) listJ[j] * ldp + c0I, bar);
-        }
-    }
-    {   // R[j][W + r] = G[list row r of I][list col j of J]: 8-byte gathers (L2-resident across the I sweep)
-        const char *rowp[CAP / 8];
+__device__ __forceinline__ double *row_ptr(const RowTable &t, int row, long long ld) {
+    double *base = t.base[0];
+    int r0 = 0;
 #pragma unroll
-        for (int u = 0; u < CAP / 8; u++) {
-            const int r = warp + 8 * u;
-            rowp[u] = r < nlI ? reinterpret_cast<const char *>(Gp + (long long) listI[r] * ldp) : nullptr;
-        }
-        for (int j = lane; j < nlJ; j += 32) {
-            const unsigned col8 = (unsigned) listJ[j] * 8u;
-            double *dst = S + OFFR + j * PR + W + warp;
-#pragma unroll
-            for (int u = 0; u < CAP / 8; u++)
-                if (rowp[u]) cp_async8(dst + 8 * u, rowp[u] + col8);
-        }
-    }
+    for (int q = 1; q < kMaxShards; q++)
+        if (q < t.n && row >= t.row0[q]) { base = t.base[q]; r0 = t.row0[q]; }
+    return base + (long long) (row - r0) * ld;
 }
 
-template <bool RANKED, int NSTAGE>
-__global__ void __launch_bounds__(kThreads, NSTAGE == 1 ? 4 : 2) phi_step_kernel(const StepDev s) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *Sbuf = reinterpret_cast<double *>(smem_raw);                  // NSTAGE stage buffers
-    double *O = NSTAGE > 1 ? Sbuf + NSTAGE * kStageDoubles : Sbuf;         // T x (T+1) transpose buffer (aliased when NSTAGE == 1)
-    int32_t *Dbuf = reinterpret_cast<int32_t *>(Sbuf + NSTAGE * kStageDoubles + (NSTAGE > 1 ? T * (T + 1) : 0));   // 3 slots x (desc I, desc J)
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(Dbuf + 3 * 2 * DW);   // one mbarrier per stage
-
-    const int tid = threadIdx.x;
-    const long long np = s.npairs;
-    const int stride = (int) gridDim.x;
-    const double *__restrict__ Gp = s.Gprev;
-    const long long ldp = s.ld_prev, ldn = s.ld_new;
-    const int lastrow = (int) (s.K_prev - 1);
-    long long k = blockIdx.x;
-    if (k >= np) return;
-
-    // ---- one-time setup: zero rows / columns for unknown parents, mbarriers ---------------------
-    for (int b = 0; b < NSTAGE; b++) {
-        double *S = Sbuf + b * kStageDoubles;
-        for (int i = tid; i < PL; i += kThreads) S[ZIDX * PL + i] = 0.0;            // L zero row
-        for (int i = tid; i < PR; i += kThreads) S[OFFR + CAP * PR + i] = 0.0;       // R zero row
-        for (int i = tid; i < CAP; i += kThreads) S[OFFR + i * PR + ZIDX] = 0.0;     // R zero column
-    }
-    if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    int I, J, In, Jn, Inn, Jnn;              // tiles of pair k, k+stride, k+2*stride
-    pair_to_tiles(k, I, J);
-    In = I; Jn = J; advance_pair(In, Jn, stride);
-    Inn = In; Jnn = Jn; advance_pair(Inn, Jnn, stride);
-
-    // ---- prologue: descriptors of the first pair, then its rows + the second pair's descriptors
-    load_desc(Dbuf, s.desc, I, J, tid);
-    cp_async_commit();
-    cp_async_wait_all();
-    __syncthreads();
-    issue_stage(Sbuf, &bars[0], Dbuf, Dbuf + DW, Gp, ldp, lastrow, tid);
-    if (k + stride < np) load_desc(Dbuf + 2 * DW, s.desc, In, Jn, tid);
-    cp_async_commit();
-
-    for (int it = 0; k < np; k += stride, ++it) {
-        const int32_t *dI = Dbuf + (it % 3) * 2 * DW, *dJ = dI + DW;
-        double *S = Sbuf + (NSTAGE > 1 ? (it & 1) : 0) * kStageDoubles;
-        cp_async_wait_all();
-        if (NSTAGE > 1) mbar_wait(&bars[it & 1], (unsigned) ((it >> 1) & 1));
-        else mbar_wait(&bars[0], (unsigned) (it & 1));
-        __syncthreads();       // pair k staged, next descriptors landed, everyone done with pair k-1
-        if (NSTAGE > 1) {
-            // ---- keep the memory system busy: rows of pair k+1, descriptors of pair k+2 -----------
-            if (k + stride < np) {
-                const int32_t *nI = Dbuf + ((it + 1) % 3) * 2 * DW;
-                issue_stage(Sbuf + ((it + 1) & 1) * kStageDoubles, &bars[(it + 1) & 1], nI, nI + DW, Gp, ldp, lastrow, tid);
-                if (k + 2 * (long long) stride < np) load_desc(Dbuf + ((it + 2) % 3) * 2 * DW, s.desc, Inn, Jnn, tid);
-            }
-            cp_async_commit();
-        }
-
-        // ---- pair k -----------------------------------------------------------------------------
-        const int c0I = dI[0], cntI = dI[1] >> 16, cntJ = dJ[1] >> 16;
-        const long long startI = dI[3], startJ = dJ[3];
-        const int32_t *listI = dI + kDescList;
-        bool slow = (I == J) || dI[2] < 0 || dJ[2] < 0;      // do the two tiles share a parent individual?
-        if (!slow)
-            for (int c = 0; c < dI[2]; c++) slow |= (dI[kDescConf + c] == J);
-
-        constexpr int CPT = T * T / kThreads;                 // 4 cells per thread: rows a = tid/32 + 8c, column b = tid%32
-        const int b = tid & 31, a_base = tid >> 5;
-        const int lb = dJ[kDescLa + b];
-        const int b0 = min(lb & 0xFFFF, ZIDX), b1 = min((lb >> 16) & 0xFFFF, ZIDX);
-        // E(ra, cb) = cb < W ? L[ra][cb] : R[cb - W][ra]  ==  S[base(cb) + ra * stride(cb)]
-        const int base0 = b0 < W ? b0 : OFFR + (b0 - W) * PR, str0 = b0 < W ? PL : 1;
-        const int base1 = b1 < W ? b1 : OFFR + (b1 - W) * PR, str1 = b1 < W ? PL : 1;
-        double v[CPT];
-        if (!slow) {
+__global__ void __launch_bounds__(kThreads, 4) phi_step_kernel(const StepDev s) {
+    __shared__ double S[T * PS1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int g = 0;
+    int ready_panel = -1;        // phase-1 of this panel is known complete
+    int freed_panel = -1;        // phase-2 of this panel is known complete (its ring slot is free)
+    for (long long q = blockIdx.x; q < s.total_items; q += gridDim.x) {
+        while (q >= s.grp_off[g + 1]) ++g;
+        const int info = s.grp_info[g];
+        const int I = info & 0x3FFFFFFF;
+        const int local = (int) (q - s.grp_off[g]);
+        double *buf = s.ring + (long long) ((I - s.panel_begin) % kRing) * s.ring_stride;
+        if ((info >> 30) == 0) {
+            // ---------------- phase 1: N^T[c][i] for c in [c0, c0 + 64) -------------------------
+            const int c0 = local * kCB;
+            double a[4][2], b[4][2];
 #pragma unroll
-            for (int c = 0; c < CPT; c++) {
-                const int a = a_base + 8 * c;
-                const int la = dI[kDescLa + a];
-                const int a0 = min(la & 0xFFFF, ZIDX), a1 = min((la >> 16) & 0xFFFF, ZIDX);
-                const double p = S[base0 + a0 * str0], q = S[base0 + a1 * str0];
-                const double r = S[base1 + a0 * str1], t = S[base1 + a1 * str1];
-                if (RANKED) {
-                    // lib/compute.cpp:529-548: the higher-ranked individual is expanded first, so the
-                    // inner sums run over the LOWER-ranked one's parents.
-                    v[c] = (dI[kDescRank + a] < dJ[kDescRank + b]) ? 0.25 * (__dadd_rn(p, q) + __dadd_rn(r, t))
-                                                                  : 0.25 * (__dadd_rn(p, r) + __dadd_rn(q, t));
-                } else {
-                    v[c] = 0.25 * ((p + q) + (r + t));
+            for (int t = 0; t < 4; t++) {
+                const int i = I * T + warp + 8 * t;
+                const int F = s.pF[i], M = s.pM[i];
+                const double *rf = F >= 0 ? row_ptr(s.prev, F, s.ld_prev) : nullptr;
+                const double *rm = M >= 0 ? row_ptr(s.prev, M, s.ld_prev) : nullptr;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int c = c0 + lane + 32 * h;
+                    const bool ok = c < s.Kpad_prev;
+                    a[t][h] = (rf && ok) ? __ldg(rf + c) : 0.0;
+                    b[t][h] = (rm && ok) ? __ldg(rm + c) : 0.0;
                 }
             }
-        } else {
-            const int ib0 = dJ[kDescPind + 2 * b], ib1 = dJ[kDescPind + 2 * b + 1];
 #pragma unroll
-            for (int c = 0; c < CPT; c++) {
-                const int a = a_base + 8 * c;
-                const int la = dI[kDescLa + a];
-                const int a0 = min(la & 0xFFFF, ZIDX), a1 = min((la >> 16) & 0xFFFF, ZIDX);
-                const int ia0 = dI[kDescPind + 2 * a], ia1 = dI[kDescPind + 2 * a + 1];
-                double p = S[base0 + a0 * str0], q = S[base0 + a1 * str0];
-                double r = S[base1 + a0 * str1], t = S[base1 + a1 * str1];
-                // same individual on both sides -> its self kinship (lib/compute.cpp:522-528)
-                if (ia0 >= 0 && (ia0 == ib0 || ia0 == ib1)) {
-                    const double d = s.dprev[a0 < W ? c0I + a0 : listI[a0 - W]];
-                    if (ia0 == ib0) p = d;
-                    if (ia0 == ib1) r = d;
-                }
-                if (ia1 >= 0 && (ia1 == ib0 || ia1 == ib1)) {
-                    const double d = s.dprev[a1 < W ? c0I + a1 : listI[a1 - W]];
-                    if (ia1 == ib0) q = d;
-                    if (ia1 == ib1) t = d;
-                }
-                if (RANKED) {
-                    v[c] = (dI[kDescRank + a] < dJ[kDescRank + b]) ? 0.25 * (__dadd_rn(p, q) + __dadd_rn(r, t))
-                                                                  : 0.25 * (__dadd_rn(p, r) + __dadd_rn(q, t));
-                } else {
-                    v[c] = 0.25 * ((p + q) + (r + t));
-                }
-            }
-        }
-        {
-            double *g = s.Gnew + (startI + a_base) * ldn + startJ + b;
-            const bool colok = b < cntJ;
+            for (int t = 0; t < 4; t++)
 #pragma unroll
-            for (int c = 0; c < CPT; c++) {
-                if (colok && a_base + 8 * c < cntI) *g = v[c];
-                g += 8 * ldn;
-                if (NSTAGE > 1) O[(a_base + 8 * c) * (T + 1) + b] = v[c];
+                for (int h = 0; h < 2; h++) S[(warp + 8 * t) * PS1 + lane + 32 * h] = 0.5 * (a[t][h] + b[t][h]);
+            // the ring slot must have been drained by phase 2 of the panel that used it before
+            const int old = I - kRing;
+            if (old >= s.panel_begin && old > freed_panel) {
+                if (tid == 0) wait_count(s.done2 + old, s.full_rows ? s.np : old + 1);
+                freed_panel = old;
             }
-        }
-        if (I == J) {
-            // self kinship of the new classes (lib/compute.cpp:553-568): a kept individual copies its
-            // value (bitwise what the reference recomputes); a new one gets 1/2 + 1/2 phi(father, mother)
-            if (tid < cntI) {
-                const int la = dI[kDescLa + tid];
-                const int a0 = la & 0xFFFF, a1 = (la >> 16) & 0xFFFF;
-                const int i0 = dI[kDescPind + 2 * tid], i1 = dI[kDescPind + 2 * tid + 1];
-                double d = 0.5;
-                if (a0 != 0xFFFF && i0 == i1) d = s.dprev[a0 < W ? c0I + a0 : listI[a0 - W]];
-                else if (a0 != 0xFFFF && a1 != 0xFFFF) d = 0.5 + 0.5 * (a1 < W ? S[a0 * PL + a1] : S[OFFR + (a1 - W) * PR + a0]);
-                s.dnew[startI + tid] = d;
-            }
-            if (NSTAGE == 1) __syncthreads();      // all reads of the single stage buffer are done
-        } else {
             __syncthreads();
-            if (NSTAGE == 1) {                     // the transpose buffer aliases the (now dead) stage buffer
 #pragma unroll
-                for (int c = 0; c < CPT; c++) O[(a_base + 8 * c) * (T + 1) + b] = v[c];
+            for (int t = 0; t < kCB / 8; t++) {
+                const int cl = warp + 8 * t, c = c0 + cl;
+                if (c < s.Kpad_prev) __stcg(buf + (long long) c * T + lane, S[lane * PS1 + cl]);
+            }
+            __syncthreads();
+            if (tid == 0) signal_count(s.done1 + I);
+        } else {
+            // ---------------- phase 2: tile (J, I) and its mirror --------------------------------
+            const int J = local;
+            if (I != ready_panel) {
+                if (tid == 0) wait_count(s.done1 + I, s.ncb);
+                ready_panel = I;
                 __syncthreads();
             }
-            // mirror tile (J,I): thread (row bb = a_base + 8c of tile J, column aa = b of tile I); lanes along aa -> coalesced
-            double *g = s.Gnew + (startJ + a_base) * ldn + startI + b;
-            const bool colok = b < cntI;
-            const double *o = O + b * (T + 1) + a_base;
+            double v[4];
 #pragma unroll
-            for (int c = 0; c < CPT; c++) {
-                if (colok && a_base + 8 * c < cntJ) *g = o[8 * c];
-                g += 8 * ldn;
+            for (int t = 0; t < 4; t++) {
+                const int j = J * T + warp + 8 * t;
+                const int F = s.pF[j], M = s.pM[j];
+                const double x = F >= 0 ? __ldcg(buf + (long long) F * T + lane) : 0.0;
+                const double y = M >= 0 ? __ldcg(buf + (long long) M * T + lane) : 0.0;
+                v[t] = 0.5 * (x + y);
             }
-            if (NSTAGE == 1) __syncthreads();      // before the next stage overwrites the aliased buffer
-        }
-        if (NSTAGE == 1) {
-            if (k + stride < np) {
-                const int32_t *nI = Dbuf + ((it + 1) % 3) * 2 * DW;
-                // (the aliased transpose buffer covers L rows 0..32 only: the zero rows / columns survive)
-                issue_stage(S, &bars[0], nI, nI + DW, Gp, ldp, lastrow, tid);
-                if (k + 2 * (long long) stride < np) load_desc(Dbuf + ((it + 2) % 3) * 2 * DW, s.desc, Inn, Jnn, tid);
+#pragma unroll
+            for (int t = 0; t < 4; t++) S[(warp + 8 * t) * PS2 + lane] = v[t];        // S[j][i]
+            if (!s.full_rows && J != I) {
+                // direct: row j of tile J, columns of panel I (the mirror of what this panel owns)
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int j = J * T + warp + 8 * t;
+                    row_ptr(s.out, j, s.ld_new)[I * T + lane] = v[t];
+                }
             }
-            cp_async_commit();
+            __syncthreads();
+            if (J != I || s.full_rows) {
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int il = warp + 8 * t;
+                    row_ptr(s.out, I * T + il, s.ld_new)[J * T + lane] = S[lane * PS2 + il];    // B[i][j] = S[j][i]
+                }
+            } else {
+                // diagonal tile: element (j, i) is valid where j <= i (in RANKED mode that is the
+                // reference's grouping); the other triangle is its mirror
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int r = warp + 8 * t;
+                    row_ptr(s.out, I * T + r, s.ld_new)[I * T + lane] = r <= lane ? S[r * PS2 + lane] : S[lane * PS2 + r];
+                }
+            }
+            __syncthreads();
+            if (tid == 0) signal_count(s.done2 + I);
         }
-        // L2 prefetch duty: the CTA that will open tile row Inn (two strides ahead) streams its list rows in
-        if (s.prefetch && Jnn == 0 && (tid >> 5) == 7 && k + 2 * (long long) stride < np) prefetch_list_rows(s.desc, Inn, Gp, ldp, tid & 31);
-        I = In; J = Jn; In = Inn; Jn = Jnn;
-        advance_pair(Inn, Jnn, stride);
+    }
+}
+
+// Self kinship of the new classes (lib/compute.cpp:553-568) and the "same individual" corrections
+// (:522-528) on top of the step kernel's B = P A P^T.
+__global__ void __launch_bounds__(256) phi_diag_kernel(const DiagDev d) {
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int c = d.c_begin + t0; c < d.c_end; c += stride) {
+        const int F = d.pF[c], M = d.pM[c], fl = d.flags[c];
+        double self = 0.5;
+        if (fl & kFlagKept) self = d.dprev[F];                      // bitwise what the reference recomputes
+        else if (fl & kFlagBoth) self = 0.5 + 0.5 * row_ptr(d.prev, F, d.ld_prev)[M];
+        d.dnew[c] = self;
+        if (fl & kFlagSingleton) row_ptr(d.out, c, d.ld_new)[c] = self;
+    }
+    for (int gidx = t0; gidx < d.ngroups; gidx += stride) {
+        const int i = d.pg_i[gidx], j = d.pg_j[gidx];
+        const bool own_i = i >= d.c_begin && i < d.c_end, own_j = j >= d.c_begin && j < d.c_end;
+        if (!own_i && !own_j) continue;
+        double add = 0.0;
+        for (int k = d.pg_off[gidx]; k < d.pg_off[gidx + 1]; k++) {
+            const int c = d.pt_cls[k];
+            add += 0.25 * (double) d.pt_mult[k] * (d.dprev[c] - row_ptr(d.prev, c, d.ld_prev)[c]);
+        }
+        if (own_i) { double *p = row_ptr(d.out, i, d.ld_new) + j; *p = *p + add; }
+        if (own_j && i != j) { double *p = row_ptr(d.out, j, d.ld_new) + i; *p = *p + add; }
     }
 }
 
 // Founders' matrix (lib/compute.cpp:655-661): classes of cut 0 are unrelated; self kinship 1/2.
-__global__ void init_kernel(double *G0, double *d0, long long K0, long long ld0) {
-    const long long total = K0 * ld0;
+// A class of several founders keeps 0 on its diagonal (two DISTINCT members), a singleton 1/2.
+__global__ void init_kernel(double *G0, double *d0, const int32_t *flags, long long K0, long long Kpad0) {
+    const long long total = Kpad0 * Kpad0;
     for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total;
-         i += (long long) gridDim.x * blockDim.x)
-        G0[i] = 0.0;
-    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < K0;
+         i += (long long) gridDim.x * blockDim.x) {
+        const long long r = i / Kpad0, c = i - r * Kpad0;
+        G0[i] = (r == c && r < K0 && (flags[r] & kFlagSingleton)) ? 0.5 : 0.0;
+    }
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < Kpad0;
          i += (long long) gridDim.x * blockDim.x)
         d0[i] = 0.5;
+}
+
+// Multi-GPU start of an uncompressed job: the rows [row_begin, row_begin + rows) of the founders'
+// matrix are zero (memset by the caller) except the diagonal; d0 is replicated on every rank.
+__global__ void init_rows_kernel(double *G0, double *d0, const int32_t *flags, long long K0, long long Kpad0,
+                                 long long row_begin, long long rows, long long dlen) {
+    const long long stride = (long long) gridDim.x * blockDim.x, t0 = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    for (long long r = t0; r < rows; r += stride) {
+        const long long c = row_begin + r;
+        if (c < K0 && (flags[c] & kFlagSingleton)) G0[r * Kpad0 + c] = 0.5;
+    }
+    for (long long i = t0; i < dlen; i += stride) d0[i] = 0.5;
+}
+
+// Multi-GPU expansion: copy the class rows this rank's probands need from their owners (peer
+// reads over NVLink, 16-byte vectorised, one CTA per row) into a compact local matrix.
+__global__ void __launch_bounds__(256) fetch_rows_kernel(const RowTable t, long long ld, const int32_t *rows, double *dst) {
+    const double2 *src = reinterpret_cast<const double2 *>(row_ptr(t, rows[blockIdx.x], ld));
+    double2 *out = reinterpret_cast<double2 *>(dst + (long long) blockIdx.x * ld);
+    for (long long c = threadIdx.x; c < ld / 2; c += 256) out[c] = src[c];
 }
 
 // Final expansion to the caller's proband order (duplicates, ancestors-as-probands) fused with
@@ -362,7 +231,7 @@ __global__ void __launch_bounds__(256) expand_kernel(const ExpandDev e) {
     const long long j0 = (long long) chunk * kExpandCols + threadIdx.x;
     double v[4];
     int uj[4];
-    const double *row = e.G + (long long) c * e.ld;
+    const double *row = e.G + (long long) (e.compact ? a : c) * e.ld;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const long long j = j0 + 256 * k;
@@ -475,61 +344,57 @@ __global__ void __launch_bounds__(256) gc_gather_kernel(const double *V, long lo
 
 }  // namespace
 
-static int g_stages = 2, g_prefetch = 1;
-int step_prefetch_default() { return g_prefetch; }
-size_t step_smem_bytes() { return step_smem(g_stages); }
-
-static int g_step_grid[2][2] = { { 0, 0 }, { 0, 0 } };    // [ranked][nstage - 1]
-
-template <bool RANKED, int NSTAGE>
-static cudaError_t configure_one(int sms) {
-    cudaError_t e;
-    const size_t smem = step_smem(NSTAGE);
-    if ((e = cudaFuncSetAttribute(phi_step_kernel<RANKED, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem))) return e;
-    int occ = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phi_step_kernel<RANKED, NSTAGE>, kThreads, smem))) return e;
-    g_step_grid[RANKED ? 1 : 0][NSTAGE - 1] = sms * (occ > 0 ? occ : 1);     // persistent: one wave, every CTA resident
-    return cudaSuccess;
-}
+static int g_step_grid = 0;
+int step_grid() { return g_step_grid; }
 
 cudaError_t configure_kernels() {
     cudaError_t e;
-    int dev = 0, sms = 0;
+    int dev = 0, sms = 0, occ = 0;
     if ((e = cudaGetDevice(&dev))) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev))) return e;
-    if ((e = configure_one<false, 1>(sms))) return e;
-    if ((e = configure_one<false, 2>(sms))) return e;
-    if ((e = configure_one<true, 1>(sms))) return e;
-    if ((e = configure_one<true, 2>(sms))) return e;
-    const char *env = getenv("GK_STAGES");
-    if (env && (env[0] == '1' || env[0] == '2')) g_stages = env[0] - '0';
-    env = getenv("GK_PREFETCH");
-    if (env && (env[0] == '0' || env[0] == '1')) g_prefetch = env[0] - '0';
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phi_step_kernel, kThreads, 0))) return e;
+    const char *env = getenv("GK_CTAS_PER_SM");
+    if (env && atoi(env) > 0 && atoi(env) < occ) occ = atoi(env);
+    g_step_grid = sms * (occ > 0 ? occ : 1);     // persistent: one wave, every CTA resident (the waits rely on it)
     return cudaSuccess;
 }
 
-cudaError_t launch_step(const StepDev &s, bool ranked, cudaStream_t st) {
-    if (s.nt <= 0) return cudaSuccess;
-    long long grid = g_step_grid[ranked ? 1 : 0][g_stages - 1];
-    if (grid <= 0) grid = 296;
-    if (grid > s.npairs) grid = s.npairs;
-    const size_t smem = step_smem(g_stages);
-    if (g_stages == 1) {
-        if (ranked) phi_step_kernel<true, 1><<<(unsigned) grid, kThreads, smem, st>>>(s);
-        else phi_step_kernel<false, 1><<<(unsigned) grid, kThreads, smem, st>>>(s);
-    } else {
-        if (ranked) phi_step_kernel<true, 2><<<(unsigned) grid, kThreads, smem, st>>>(s);
-        else phi_step_kernel<false, 2><<<(unsigned) grid, kThreads, smem, st>>>(s);
-    }
+cudaError_t launch_step(const StepDev &s, cudaStream_t st) {
+    if (s.total_items <= 0) return cudaSuccess;
+    long long grid = g_step_grid > 0 ? g_step_grid : 148;
+    if (grid > s.total_items) grid = s.total_items;
+    phi_step_kernel<<<(unsigned) grid, kThreads, 0, st>>>(s);
     return cudaGetLastError();
 }
 
-cudaError_t launch_init(double *G0, double *d0, int64_t K0, int64_t ld0, cudaStream_t st) {
-    long long total = (long long) K0 * ld0;
-    int blocks = (int) ((total + 255) / 256);
+cudaError_t launch_diag(const DiagDev &d, cudaStream_t st) {
+    long long work = (long long) (d.c_end - d.c_begin);
+    if (d.ngroups > work) work = d.ngroups;
+    if (work <= 0) return cudaSuccess;
+    long long blocks = (work + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    phi_diag_kernel<<<(unsigned) blocks, 256, 0, st>>>(d);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_init(double *G0, double *d0, const int32_t *flags, int64_t K0, int64_t Kpad0, cudaStream_t st) {
+    long long total = (long long) Kpad0 * Kpad0;
+    long long blocks = (total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    init_kernel<<<blocks, 256, 0, st>>>(G0, d0, K0, ld0);
+    init_kernel<<<(unsigned) blocks, 256, 0, st>>>(G0, d0, flags, K0, Kpad0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_init_rows(double *G0, double *d0, const int32_t *flags, int64_t K0, int64_t Kpad0,
+                             int64_t row_begin, int64_t rows, int64_t dlen, cudaStream_t st) {
+    init_rows_kernel<<<148 * 2, 256, 0, st>>>(G0, d0, flags, K0, Kpad0, row_begin, rows, dlen);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fetch_rows(const RowTable &t, int64_t ld, const int32_t *rows, int32_t nrows, double *dst, cudaStream_t st) {
+    if (nrows <= 0) return cudaSuccess;
+    fetch_rows_kernel<<<(unsigned) nrows, 256, 0, st>>>(t, ld, rows, dst);
     return cudaGetLastError();
 }
 

@@ -5,18 +5,48 @@
 
 namespace gk {
 
+constexpr int kMaxShards = 8;     // GPUs of one box
+constexpr int kRing = 3;          // L2-resident panel buffers (transposed N panels)
+constexpr int kCB = 64;           // columns of the previous matrix per phase-1 work item
+
+// Where the rows of a (possibly row-sharded) class matrix live: row r is owned by the shard q with
+// row0[q] <= r < row0[q+1] and sits at base[q] + (r - row0[q]) * ld.  Peer shards are CUDA-IPC
+// mappings of the other ranks' buffers (NVLink); a single GPU has n = 1.
+struct RowTable {
+    double *base[kMaxShards];
+    int32_t row0[kMaxShards + 1];
+    int32_t n;
+};
+
 // Everything one recurrence step needs, by value.
 struct StepDev {
-    const double *Gprev;     // K_prev x ld_prev class matrix of cut g-1 (row-major, symmetric)
-    const double *dprev;     // self kinship of each class of cut g-1
-    double *Gnew;            // K x ld class matrix of cut g
-    double *dnew;            // self kinship of each class of cut g
+    RowTable prev;            // class matrix of cut g-1: Kpad_prev rows x ld_prev
+    RowTable out;             // class matrix of cut g:   Kpad rows x ld_new
     int64_t ld_prev, ld_new;
-    int64_t K_prev, K;
-    const int32_t *desc;     // nt tile descriptors of kDescWords int32 (layout: gk_plan.hpp)
-    int64_t npairs;          // nt*(nt+1)/2 unordered tile pairs
-    int32_t nt;
-    int32_t prefetch;        // 1: stream the list rows of upcoming tile rows into L2
+    int32_t Kpad_prev;
+    int32_t np;               // panels / tiles of the new cut (global)
+    const int32_t *pF, *pM;   // Kpad: parent rows of every new class in the previous matrix (-1 none)
+    double *ring;             // kRing x ring_stride doubles: N^T panels, [Kpad_prev][32]
+    int64_t ring_stride;
+    int32_t *done1, *done2;   // np counters each: finished phase-1 / phase-2 items of a panel
+    const int64_t *grp_off;   // ngroups + 1: first work item of each group
+    const int32_t *grp_info;  // ngroups: panel | (phase - 1) << 30
+    int64_t total_items;
+    int32_t ngroups;
+    int32_t ncb;              // phase-1 items per panel
+    int32_t panel_begin, panel_end;   // panels this launch (rank) owns
+    int32_t full_rows;        // 0: tiles J <= I, mirror stored too; 1: every tile J, own rows only
+};
+
+struct DiagDev {
+    RowTable prev, out;
+    int64_t ld_prev, ld_new;
+    const double *dprev;      // self kinship per class of cut g-1 (replicated)
+    double *dnew;             // self kinship per class of cut g (this launch writes [c_begin, c_end))
+    const int32_t *pF, *pM, *flags;
+    int32_t c_begin, c_end;   // classes whose rows this launch owns
+    const int32_t *pg_i, *pg_j, *pg_off, *pt_cls, *pt_mult;
+    int32_t ngroups;
 };
 
 struct ExpandDev {
@@ -31,19 +61,23 @@ struct ExpandDev {
     double *out;             // (row1 - row0) x m, row-major, caller order
     int64_t m, row0, row1;
     int32_t nact, nchunks;
+    int32_t compact;         // 1: G holds only the active classes' rows, row a <-> cact[a] (multi-GPU)
     double *partials;        // nact*nchunks*2 : per-CTA (sum all, sum diag)
 };
 
-size_t step_smem_bytes();
-int step_prefetch_default();
-cudaError_t launch_step(const StepDev &s, bool ranked, cudaStream_t st);
-cudaError_t launch_init(double *G0, double *d0, int64_t K0, int64_t ld0, cudaStream_t st);
+int step_grid();             // CTAs of the persistent step kernel (SMs x resident CTAs)
+cudaError_t launch_step(const StepDev &s, cudaStream_t st);
+cudaError_t launch_diag(const DiagDev &d, cudaStream_t st);
+cudaError_t launch_init(double *G0, double *d0, const int32_t *flags, int64_t K0, int64_t Kpad0, cudaStream_t st);
+cudaError_t launch_init_rows(double *G0, double *d0, const int32_t *flags, int64_t K0, int64_t Kpad0,
+                             int64_t row_begin, int64_t rows, int64_t dlen, cudaStream_t st);
+cudaError_t launch_fetch_rows(const RowTable &t, int64_t ld, const int32_t *rows, int32_t nrows, double *dst, cudaStream_t st);
 constexpr int kExpandCols = 1024;     // result columns per CTA of the expansion kernel
 cudaError_t launch_expand(const ExpandDev &e, cudaStream_t st);
 cudaError_t launch_eye(double *out, int64_t m, int64_t row0, int64_t row1, double *partials, cudaStream_t st);
 // two-stage deterministic reduction of the per-CTA partials: scratch holds 2*256 doubles
 cudaError_t launch_mean_finish(const double *partials, int64_t nblocks, double *scratch, double *sums /*2*/, cudaStream_t st);
-cudaError_t configure_kernels();   // cudaFuncSetAttribute for large dynamic shared memory
+cudaError_t configure_kernels();
 
 // gen.gc propagation: out row = 0.5*w0*row(p0) + 0.5*w1*row(p1), then seed own ancestor columns.
 struct GcStepDev {

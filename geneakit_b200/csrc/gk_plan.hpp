@@ -1,6 +1,6 @@
 // Host planner of the B200 kinship path (pure C++17, no CUDA).
 //
-// Turns a rank-space pedigree + proband list into the per-generation TILE PLAN the sm_100a
+// Turns a rank-space pedigree + proband list into the per-generation STEP PLAN the sm_100a
 // kernels consume.  It replaces, on the host, the reference's cut_vertices()
 // (lib/compute.cpp:119-135 and helpers :28-114) and the slot bookkeeping of compute_kinships()
 // (:678-689), but not with their std::set algebra:
@@ -12,18 +12,27 @@
 //     identical kinship rows (except with themselves), so one matrix row per sibship ("class")
 //     is stored; individuals kept from the previous cut are singleton classes whose two
 //     "parents" are their own old row.  compress=0 gives one class per individual.
-//   * order: classes are stored sorted by the class index of their first known parent in the
-//     previous matrix, so that the parents of T consecutive classes form a contiguous WINDOW
-//     of T columns (coalesced / bulk-copied) plus a LIST of scattered rows (the other parent).
-//   * tiles: per tile of T classes one fixed-size DESCRIPTOR (window start, list of scattered
-//     parent rows, and the few other tiles that share a parent INDIVIDUAL with it: only those
-//     tile pairs need the "same individual -> self kinship" rule of lib/compute.cpp:522-528),
-//     and per class the local indices + individual ids of its two parents.
+//     Convention for the class matrix A of a cut: A[c][c'] (c != c') = kinship between any member
+//     of c and any member of c';  A[c][c] = kinship between two DISTINCT members of c when the
+//     class has several members, and the self kinship when it is a singleton.  d[c] = self kinship.
+//   * one recurrence step is B = P A P^T (+ sparse corrections), P = the K x K_prev matrix with
+//     1/2 at (i, F_i) and (i, M_i) (F_i / M_i = class rows of the parents of class i).  The kernel
+//     factorises it:  N_I = P_I A  for a PANEL I of 32 classes (whole rows of A: contiguous),
+//     kept transposed in an L2-resident ring, then  B[I][J] = N_I P_J^T  for every tile J.
+//     Nothing constrains the ORDER of the classes any more, so they are ordered for locality:
+//     a greedy walk over the "shares a parent class" graph makes consecutive classes share parent
+//     rows (fewer distinct rows of A per panel = fewer HBM reads).
+//   * corrections ("same individual -> self kinship", lib/compute.cpp:522-528): wherever the two
+//     classes i, j have a parent INDIVIDUAL p in common, the term A[c_p][c_p] must read d[c_p]:
+//     B[i][j] += 1/4 * mult * (d[c_p] - A[c_p][c_p]).  They form a short sparse list (one entry per
+//     parent individual in monogamous pedigrees) applied by the diagonal kernel.
 //
 // Rounding: for G-1 <= 26 cuts below the founders every value is a dyadic rational that FP64
 // holds exactly, so any evaluation order is bit-identical to the reference.  Deeper pedigrees
-// switch to RANKED mode (no compression, per-pair choice of the summation grouping by rank,
-// exactly as lib/compute.cpp:529-548 does).
+// switch to RANKED mode: no compression (no corrections either: every class is a singleton whose
+// diagonal already is the self kinship) and classes in DESCENDING rank order, so that the tile
+// pairs J <= I the kernel evaluates are exactly "N of the lower-ranked individual, parents of the
+// higher-ranked one" -- the grouping lib/compute.cpp:529-548 rounds with.
 #pragma once
 #include <algorithm>
 #include <chrono>
@@ -33,39 +42,32 @@
 
 namespace gk {
 
-constexpr int kMissing = 0xFFFF;   // la half-word for "parent unknown"
-constexpr int kConfMax = 12;       // conflicting tiles stored inline per descriptor
-constexpr int kTile = 32;          // classes per tile (at most)
-constexpr int kWin = 32;           // window width (columns of the previous matrix)
-constexpr int kListCap = 40;       // scattered parent rows per tile (a tile is closed early rather than exceed it)
-// Tile descriptor, int32 words (16-byte aligned blocks, fetched with cp.async):
-//   [0] c0  [1] nl | count << 16  [2] nconf (-1: always apply the identity rule)  [3] first class
-//   [4, 4+cap)  list   [.., +kConfMax) conflicting tiles   [.., +T) la   [.., +2T) pind   [.., +T) rank
-constexpr int kDescList = 4;
-constexpr int kDescConf = kDescList + kListCap;
-constexpr int kDescLa = kDescConf + kConfMax;
-constexpr int kDescPind = kDescLa + kTile;
-constexpr int kDescRank = kDescPind + 2 * kTile;
-constexpr int kDescWords = kDescRank + kTile;      // 184 words = 736 bytes
-static_assert(kDescWords % 4 == 0, "descriptor must be a multiple of 16 bytes");
+constexpr int kPanel = 32;          // classes per panel / tile
+constexpr int kFlagSingleton = 1;   // class has exactly one member: its diagonal holds the self kinship
+constexpr int kFlagKept = 2;        // member kept from the previous cut (both "parents" = its own old row)
+constexpr int kFlagBoth = 4;        // new class with both parents known
 
 struct StepPlan {
-    int64_t K = 0, ld = 0, K_prev = 0;
-    int nt = 0, nr_max = 0;
-    int64_t cut_size = 0;     // |cut_g| as the reference counts it (last cut: m, duplicates included)
-    int64_t n_kept = 0;       // members also in the previous cut
-    int64_t P_ref = 0;        // distinct individuals of cut g-1 that are a parent of a NEW member
-    int64_t P_cls = 0;        // distinct rows of matrix g-1 read by this step
-    int64_t kept_cls = 0;     // singleton classes of kept individuals
-    std::vector<int32_t> cls_rank;  // K (ranked mode only; host copy, the device reads the descriptors)
-    std::vector<int32_t> desc;      // nt * kDescWords
+    int64_t K = 0, Kpad = 0, K_prev = 0, Kpad_prev = 0;
+    int np = 0;                // panels = Kpad / 32
+    int64_t cut_size = 0;      // |cut_g| as the reference counts it (last cut: m, duplicates included)
+    int64_t n_kept = 0;        // members also in the previous cut
+    int64_t P_ref = 0;         // distinct individuals of cut g-1 that are a parent of a NEW member
+    int64_t P_cls = 0;         // distinct rows of matrix g-1 read by this step
+    int64_t kept_cls = 0;      // singleton classes of kept individuals
+    int64_t panel_rows = 0;    // sum over panels of the distinct parent rows the panel reads
+    std::vector<int32_t> pF, pM;       // Kpad: parent class rows in matrix g-1, -1 = none (padding: -1, -1)
+    std::vector<int32_t> flags;        // Kpad
+    std::vector<int32_t> cls_ind;      // K: lowest-ranked member (= the individual, uncompressed)
+    std::vector<int32_t> cls_size;     // K: members
+    // corrections, CSR over (i, j) groups with i >= j
+    std::vector<int32_t> pg_i, pg_j, pg_off, pt_cls, pt_mult;
 };
 
 struct PhiPlan {
     int32_t n = 0, m = 0, G = 0;
-    int tile = kTile, win = kWin, lmax = kListCap;
     bool compressed = true, ranked = false, single_cut = false;
-    std::vector<StepPlan> steps;            // steps[g], g = 0 .. G-1 (steps[0]: K only)
+    std::vector<StepPlan> steps;            // steps[g], g = 0 .. G-1 (steps[0]: founders' cut, no parents)
     std::vector<int32_t> final_cls, final_ind;   // m entries, caller order
     double plan_seconds = 0.0;
     std::string error;
@@ -109,21 +111,73 @@ inline int cut_sizes_only(int32_t n, const int32_t *sire, const int32_t *dam, in
 
 struct MemberRec {
     int32_t ind;        // individual (rank)
-    int32_t pi0, pi1;   // parent individuals (window parent first), -1 missing; kept: both = ind
+    int32_t pi0, pi1;   // parent individuals, -1 missing; kept: both = ind
     int32_t pc0, pc1;   // their class rows in the previous matrix, -1 missing
     uint8_t kept;
 };
 
 struct ClassRec {
     int32_t pi0, pi1, pc0, pc1;
-    int32_t first_member;   // lowest individual rank (tie-break; rank in ranked mode)
-    uint8_t section;        // 0 = some member is the window parent of a class of the next cut
+    int32_t first_member;   // lowest individual rank
+    int32_t size;
     uint8_t kept;
     int32_t member_begin, member_end;   // range in the sorted member array
 };
 
+// Greedy walk over the classes of the new cut: move from a class to an unvisited class that shares
+// one of its parent rows (preferring the row we did NOT arrive through), so that consecutive
+// classes -- hence panels of 32 -- read few distinct rows of the previous matrix.
+inline void locality_order(const std::vector<ClassRec> &cls, int64_t K_prev, std::vector<int32_t> &order) {
+    const int32_t K = (int32_t) cls.size();
+    order.clear();
+    order.reserve(K);
+    if (K_prev <= 0) { for (int32_t i = 0; i < K; i++) order.push_back(i); return; }
+    std::vector<int32_t> off((size_t) K_prev + 1, 0);
+    auto rows_of = [&](const ClassRec &c, int32_t r[2]) {
+        int k = 0;
+        if (c.pc0 >= 0) r[k++] = c.pc0;
+        if (c.pc1 >= 0 && c.pc1 != c.pc0) r[k++] = c.pc1;
+        return k;
+    };
+    for (int32_t i = 0; i < K; i++) { int32_t r[2]; int k = rows_of(cls[i], r); for (int q = 0; q < k; q++) off[r[q] + 1]++; }
+    for (int64_t c = 0; c < K_prev; c++) off[c + 1] += off[c];
+    std::vector<int32_t> adj(off[K_prev]), cur(off.begin(), off.end() - 1);
+    for (int32_t i = 0; i < K; i++) { int32_t r[2]; int k = rows_of(cls[i], r); for (int q = 0; q < k; q++) adj[cur[r[q]]++] = i; }
+    std::copy(off.begin(), off.end() - 1, cur.begin());      // cursor: first possibly-unvisited entry of each row's list
+    std::vector<uint8_t> visited(K, 0);
+    auto next_unvisited = [&](int32_t row) -> int32_t {
+        int32_t &p = cur[row];
+        while (p < off[row + 1] && visited[adj[p]]) p++;
+        return p < off[row + 1] ? adj[p] : -1;
+    };
+    // walk starts: classes whose parent rows have the fewest users first (path ends before path middles)
+    std::vector<int32_t> starts(K);
+    std::vector<int32_t> deg(K);
+    for (int32_t i = 0; i < K; i++) {
+        int32_t r[2]; int k = rows_of(cls[i], r);
+        int32_t d = 0;
+        for (int q = 0; q < k; q++) d += off[r[q] + 1] - off[r[q]];
+        deg[i] = d; starts[i] = i;
+    }
+    std::stable_sort(starts.begin(), starts.end(), [&](int32_t a, int32_t b) { return deg[a] < deg[b]; });
+    size_t sp = 0;
+    while ((int32_t) order.size() < K) {
+        while (visited[starts[sp]]) sp++;
+        int32_t x = starts[sp], came = -1;
+        for (;;) {
+            visited[x] = 1; order.push_back(x);
+            int32_t r[2]; int k = rows_of(cls[x], r);
+            if (k == 2 && came == r[0]) std::swap(r[0], r[1]);     // try the row we did not arrive through first
+            int32_t nxt = -1;
+            for (int q = 0; q < k && nxt < 0; q++) { nxt = next_unvisited(r[q]); if (nxt >= 0) came = r[q]; }
+            if (nxt < 0) break;
+            x = nxt;
+        }
+    }
+}
+
 inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m,
-                           const int32_t *pro, int compress_opt, int tile_opt, PhiPlan &P) {
+                           const int32_t *pro, int compress_opt, int order_opt, PhiPlan &P) {
     auto t0 = std::chrono::steady_clock::now();
     P = PhiPlan();
     P.n = n; P.m = m;
@@ -155,8 +209,6 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
     P.single_cut = (G == 1);
     P.ranked = (G - 1 > 26);
     P.compressed = P.ranked ? false : (compress_opt != 0);
-    (void) tile_opt;                   // one tile shape: 32 classes, 32-column window, <= 40 list rows
-    const int T = kTile, W = kWin;
     P.steps.resize(G);
 
     // members entering each cut: enter(x) = G-1-maxp, last cut containing x = G-1-minp
@@ -171,20 +223,20 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
     auto leave = [&](int32_t x) { return G - 1 - minp[x]; };
 
     std::vector<int32_t> cls_prev(n, -1), cls_cur(n, -1);
-    std::vector<int32_t> win_stamp(n, -1);            // step stamp: individual is a window parent for the next cut
-    std::vector<int64_t> use_stamp(n, -1);            // (step << 32 | tile): individual already recorded for this tile
-    std::vector<std::pair<int32_t, int32_t>> use_pairs, conf_pairs;
     std::vector<int32_t> par_stamp(n, -1);            // distinct-parent counting
-    std::vector<int32_t> prow_stamp;                  // distinct parent rows of previous matrix
-    std::vector<int32_t> row_tile_stamp, row_loc;     // per previous-matrix row: local list slot in the current tile
-
+    std::vector<int32_t> prow_stamp, prow_panel;      // distinct parent rows of the previous matrix / per panel
     std::vector<int32_t> cur;                         // members of the current cut (individuals)
     std::vector<MemberRec> mem;
     std::vector<ClassRec> cls;
     std::vector<int32_t> order;
+    struct Use { int32_t ind, cls, mult; };
+    std::vector<Use> uses;
+    struct Term { int32_t i, j, c, mult; };
+    std::vector<Term> terms;
 
     for (int g = 0; g < G; g++) {
         StepPlan &S = P.steps[g];
+        const StepPlan *Sp = g > 0 ? &P.steps[g - 1] : nullptr;
         // ---- members of cut g ------------------------------------------------------------
         std::vector<int32_t> nxt;
         nxt.reserve(cur.size() + (new_off[g + 1] - new_off[g]));
@@ -198,8 +250,7 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
         for (int64_t e = new_off[g]; e < new_off[g + 1]; e++) {
             int32_t x = new_mem[e];
             MemberRec r; r.ind = x; r.kept = 0;
-            int32_t f = sire[x], d = dam[x];
-            if (f >= 0) { r.pi0 = f; r.pi1 = d; } else { r.pi0 = d; r.pi1 = -1; }
+            r.pi0 = sire[x]; r.pi1 = dam[x];
             r.pc0 = r.pi0 >= 0 ? cls_prev[r.pi0] : -1;
             r.pc1 = r.pi1 >= 0 ? cls_prev[r.pi1] : -1;
             if ((r.pi0 >= 0 && r.pc0 < 0) || (r.pi1 >= 0 && r.pc1 < 0)) {
@@ -213,17 +264,8 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
         }
         S.P_ref = pref;
         S.cut_size = (g == G - 1) ? (int64_t) m : (int64_t) mem.size();
-        S.K_prev = g > 0 ? P.steps[g - 1].K : 0;
-
-        // ---- window parents of the next cut (section flag) -------------------------------
-        if (g + 1 < G) {
-            for (const MemberRec &r : mem) if (leave(r.ind) >= g + 1) win_stamp[r.ind] = g;   // kept next: own row
-            for (int64_t e = new_off[g + 1]; e < new_off[g + 2]; e++) {
-                int32_t y = new_mem[e];
-                int32_t w = sire[y] >= 0 ? sire[y] : dam[y];
-                if (w >= 0) win_stamp[w] = g;
-            }
-        }
+        S.K_prev = Sp ? Sp->K : 0;
+        S.Kpad_prev = Sp ? Sp->Kpad : 0;
 
         // ---- classes: new members with equal (pi0, pi1) share a row; kept are singletons ----
         auto key_of = [&](const MemberRec &r) -> uint64_t {
@@ -244,130 +286,108 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
             ClassRec c;
             c.pi0 = mem[i].pi0; c.pi1 = mem[i].pi1; c.pc0 = mem[i].pc0; c.pc1 = mem[i].pc1;
             c.first_member = mem[i].ind; c.kept = mem[i].kept; c.member_begin = i; c.member_end = j;
-            c.section = 1;
-            for (int32_t q = i; q < j; q++) if (win_stamp[mem[q].ind] == g) { c.section = 0; break; }
+            c.size = j - i;
             cls.push_back(c);
             i = j;
         }
         const int64_t K = (int64_t) cls.size();
-        order.resize(K);
-        for (int64_t i = 0; i < K; i++) order[i] = (int32_t) i;
-        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-            const ClassRec &x = cls[a], &y = cls[b];
-            if (x.section != y.section) return x.section < y.section;
-            if (x.pc0 != y.pc0) return x.pc0 < y.pc0;
-            if (x.pc1 != y.pc1) return x.pc1 < y.pc1;
-            return x.first_member < y.first_member;
-        });
+        // ---- order ---------------------------------------------------------------------------
+        if (P.ranked) {
+            order.resize(K);
+            for (int64_t i = 0; i < K; i++) order[i] = (int32_t) i;
+            std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cls[a].first_member > cls[b].first_member; });
+        } else if (order_opt == 0 || g == 0) {
+            order.resize(K);
+            for (int64_t i = 0; i < K; i++) order[i] = (int32_t) i;
+            std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+                const ClassRec &x = cls[a], &y = cls[b];
+                if (x.pc0 != y.pc0) return x.pc0 < y.pc0;
+                if (x.pc1 != y.pc1) return x.pc1 < y.pc1;
+                return x.first_member < y.first_member;
+            });
+        } else {
+            locality_order(cls, S.K_prev, order);
+        }
         S.K = K;
-        S.ld = round_up(std::max<int64_t>(K, 1), 16);
+        S.Kpad = round_up(std::max<int64_t>(K, 1), kPanel);
+        S.np = (int) (S.Kpad / kPanel);
+        S.pF.assign((size_t) S.Kpad, -1); S.pM.assign((size_t) S.Kpad, -1); S.flags.assign((size_t) S.Kpad, 0);
+        S.cls_ind.resize(K); S.cls_size.resize(K);
         for (int64_t pos = 0; pos < K; pos++) {
             const ClassRec &c = cls[order[pos]];
             for (int32_t q = c.member_begin; q < c.member_end; q++) cls_cur[mem[q].ind] = (int32_t) pos;
-        }
-        if (P.ranked) {
-            S.cls_rank.resize(K);
-            for (int64_t pos = 0; pos < K; pos++) S.cls_rank[pos] = cls[order[pos]].first_member;
+            S.pF[pos] = c.pc0; S.pM[pos] = c.pc1;
+            S.flags[pos] = (c.size == 1 ? kFlagSingleton : 0) | (c.kept ? kFlagKept : 0) |
+                           ((!c.kept && c.pc0 >= 0 && c.pc1 >= 0) ? kFlagBoth : 0);
+            S.cls_ind[pos] = c.first_member; S.cls_size[pos] = c.size;
+            if (c.kept) S.kept_cls++;
         }
 
-        // ---- tiles (only steps that read a previous matrix) -------------------------------
         if (g > 0) {
-            const int DW = kDescWords;
-            S.desc.clear();
+            // ---- traffic statistics: distinct parent rows overall and per panel ----------------
             prow_stamp.assign((size_t) S.K_prev, -1);
-            row_tile_stamp.assign((size_t) S.K_prev, -1);
-            row_loc.assign((size_t) S.K_prev, 0);
-            use_pairs.clear();
-            int64_t pcls = 0, keptc = 0;
-            int t = -1, nl = 0, cnt = 0;
-            int32_t c0 = 0;
-            uint8_t tile_section = 0;
-            auto open_tile = [&](int64_t pos) {
-                t++;
-                S.desc.resize((size_t) (t + 1) * DW, 0);
-                int32_t *d = &S.desc[(size_t) t * DW];
-                for (int k = 0; k < T; k++) { d[kDescLa + k] = kMissing | (kMissing << 16); d[kDescPind + 2 * k] = d[kDescPind + 2 * k + 1] = -1; }
-                // window start: first known father class from here on inside this section (sorted => the minimum)
-                int32_t cmin = -1;
-                for (int64_t q = pos; q < K && q < pos + T; q++) {
-                    const ClassRec &c = cls[order[q]];
-                    if (c.section != cls[order[pos]].section) break;
-                    if (c.pc0 >= 0) { cmin = c.pc0; break; }
+            prow_panel.assign((size_t) S.K_prev, -1);
+            int64_t pcls = 0, prow = 0;
+            for (int64_t pos = 0; pos < K; pos++) {
+                const int32_t panel = (int32_t) (pos / kPanel);
+                for (int q = 0; q < 2; q++) {
+                    const int32_t pc = q ? S.pM[pos] : S.pF[pos];
+                    if (pc < 0) continue;
+                    if (prow_stamp[pc] != g) { prow_stamp[pc] = g; pcls++; }
+                    if (prow_panel[pc] != panel) { prow_panel[pc] = panel; prow++; }
                 }
-                c0 = cmin < 0 ? 0 : (cmin & ~1);                 // even: 16-byte aligned row segments
-                nl = 0; cnt = 0; tile_section = cls[order[pos]].section;
-                d[0] = c0; d[3] = (int32_t) pos;
-            };
-            auto close_tile = [&]() {
-                int32_t *d = &S.desc[(size_t) t * DW];
-                d[1] = nl | (cnt << 16);
-                S.nr_max = std::max(S.nr_max, W + nl);
-            };
+            }
+            S.P_cls = pcls; S.panel_rows = prow;
+
+            // ---- corrections: class pairs that share a parent INDIVIDUAL whose class has several members
+            uses.clear(); terms.clear();
             for (int64_t pos = 0; pos < K; pos++) {
                 const ClassRec &c = cls[order[pos]];
-                // how many new list rows would this class add to the open tile?
-                auto extra = [&]() {
-                    int e = 0;
-                    int32_t seen = -1;
-                    for (int q = 0; q < 2; q++) {
-                        const int32_t pi = q ? c.pi1 : c.pi0, pc = q ? c.pc1 : c.pc0;
-                        if (pi < 0 || (pc >= c0 && pc < c0 + W) || row_tile_stamp[pc] == t || pc == seen) continue;
-                        seen = pc; e++;
-                    }
-                    return e;
-                };
-                if (t < 0 || cnt == T || c.section != tile_section || nl + extra() > kListCap) {
-                    if (t >= 0) close_tile();
-                    open_tile(pos);
-                }
-                int32_t *d = &S.desc[(size_t) t * DW];
-                if (c.kept) keptc++;
-                int la[2] = { kMissing, kMissing };
+                bool pushed0 = false;
                 for (int q = 0; q < 2; q++) {
                     const int32_t pi = q ? c.pi1 : c.pi0, pc = q ? c.pc1 : c.pc0;
-                    d[kDescPind + 2 * cnt + q] = pi;
-                    if (pi < 0) continue;
-                    if (prow_stamp[pc] != g) { prow_stamp[pc] = g; pcls++; }
-                    const int64_t us = ((int64_t) g << 32) | (uint32_t) t;
-                    if (use_stamp[pi] != us) { use_stamp[pi] = us; use_pairs.emplace_back(pi, t); }
-                    if (pc >= c0 && pc < c0 + W) { la[q] = pc - c0; continue; }
-                    if (row_tile_stamp[pc] != t) {
-                        row_tile_stamp[pc] = t; row_loc[pc] = W + nl;
-                        d[kDescList + nl++] = pc;
+                    if (pi < 0 || Sp->cls_size[pc] <= 1) continue;     // singleton parent class: diagonal already = self kinship
+                    if (q == 1 && pushed0 && pi == c.pi0) { uses.back().mult++; continue; }   // kept: the same individual twice
+                    uses.push_back({ pi, (int32_t) pos, 1 });
+                    if (q == 0) pushed0 = true;
+                }
+            }
+            std::sort(uses.begin(), uses.end(), [](const Use &a, const Use &b) { return a.ind != b.ind ? a.ind < b.ind : a.cls < b.cls; });
+            int64_t budget = (int64_t) 1 << 27;
+            for (size_t a = 0; a < uses.size();) {
+                size_t b = a + 1;
+                while (b < uses.size() && uses[b].ind == uses[a].ind) b++;
+                const int64_t k = (int64_t) (b - a);
+                budget -= k * (k + 1) / 2;
+                if (budget < 0) {
+                    P.error = "an individual of a multi-member sibship has too many mates for the correction list (compress=0 avoids it)";
+                    P.error_code = 1; return false;
+                }
+                const int32_t pc = cls_prev[uses[a].ind];
+                for (size_t x = a; x < b; x++)
+                    for (size_t y = a; y <= x; y++) {
+                        if (x == y && (S.flags[uses[x].cls] & kFlagSingleton)) continue;   // diagonal of a singleton := d_new
+                        terms.push_back({ uses[x].cls, uses[y].cls, pc, uses[x].mult * uses[y].mult });
                     }
-                    la[q] = row_loc[pc];
-                }
-                d[kDescLa + cnt] = la[0] | (la[1] << 16);
-                d[kDescRank + cnt] = P.ranked ? c.first_member : 0;
-                cnt++;
+                a = b;
             }
-            if (t >= 0) close_tile();
-            S.nt = t + 1;
-            S.P_cls = pcls; S.kept_cls = keptc;
-            // tiles that share a parent individual: only those pairs apply the identity rule
-            std::sort(use_pairs.begin(), use_pairs.end());
-            conf_pairs.clear();
-            for (size_t i = 0; i < use_pairs.size();) {
-                size_t j = i + 1;
-                while (j < use_pairs.size() && use_pairs[j].first == use_pairs[i].first) j++;
-                for (size_t a = i; a < j; a++)
-                    for (size_t b = i; b < j; b++)
-                        if (a != b) conf_pairs.emplace_back(use_pairs[a].second, use_pairs[b].second);
-                i = j;
-            }
-            std::sort(conf_pairs.begin(), conf_pairs.end());
-            conf_pairs.erase(std::unique(conf_pairs.begin(), conf_pairs.end()), conf_pairs.end());
-            for (size_t i = 0; i < conf_pairs.size();) {
-                size_t j = i;
-                const int tt = conf_pairs[i].first;
-                while (j < conf_pairs.size() && conf_pairs[j].first == tt) j++;
-                int32_t *d = &S.desc[(size_t) tt * DW];
-                if ((int) (j - i) > kConfMax) d[2] = -1;
-                else {
-                    d[2] = (int32_t) (j - i);
-                    for (size_t q = i; q < j; q++) d[kDescConf + (q - i)] = conf_pairs[q].second;
+            std::sort(terms.begin(), terms.end(), [](const Term &a, const Term &b) {
+                if (a.i != b.i) return a.i < b.i;
+                if (a.j != b.j) return a.j < b.j;
+                return a.c < b.c;
+            });
+            S.pg_off.push_back(0);
+            for (size_t a = 0; a < terms.size();) {
+                size_t b = a;
+                while (b < terms.size() && terms[b].i == terms[a].i && terms[b].j == terms[a].j) {
+                    if (!S.pt_cls.empty() && (size_t) S.pg_off.back() < S.pt_cls.size() && S.pt_cls.back() == terms[b].c)
+                        S.pt_mult.back() += terms[b].mult;                          // same class twice (two shared siblings... same individual listed once per class)
+                    else { S.pt_cls.push_back(terms[b].c); S.pt_mult.push_back(terms[b].mult); }
+                    b++;
                 }
-                i = j;
+                S.pg_i.push_back(terms[a].i); S.pg_j.push_back(terms[a].j);
+                S.pg_off.push_back((int32_t) S.pt_cls.size());
+                a = b;
             }
         }
         cur.swap(nxt);

@@ -36,9 +36,9 @@ typedef struct gk_opts {
     int32_t device;        /* CUDA device ordinal, -1 = current device */
     int32_t verbose;       /* 1: print the cut sizes / "Cut k out of n" lines of lib/compute.cpp:662-676 */
     int32_t compress;      /* -1 auto (default), 0 one matrix row per individual, 1 one row per sibship */
-    int32_t tile;          /* 0 auto; 32 or 64: classes per tile */
-    int32_t rank;          /* column shard owned by this process (multi-GPU), 0 .. world-1 */
-    int32_t world;         /* number of column shards, 0/1 = single GPU */
+    int32_t order;         /* -1/1 auto: classes ordered by a locality walk; 0: sorted by parent rows (debug) */
+    int32_t rank;          /* row shard owned by this process (multi-GPU), 0 .. world-1 */
+    int32_t world;         /* number of row shards (<= 8), 0/1 = single GPU */
     int32_t reserved0;
     void   *stream;        /* cudaStream_t to enqueue on, NULL = the library's own stream */
 } gk_opts;
@@ -86,7 +86,7 @@ int32_t gk_cut_sizes(int32_t n, const int32_t *sire, const int32_t *dam,
 
 /* Multi-GPU: the final m x m matrix is sharded by contiguous blocks of result ROWS (== columns,
  * the matrix is symmetric), one block per rank; opts->rank / opts->world select the block a job
- * produces.  Host only. */
+ * produces (the class matrices of the cuts are sharded the same way, by panels of 32 rows).  Host only. */
 void gk_shard_rows(int32_t m, int32_t rank, int32_t world, int64_t *row0, int64_t *row1);
 
 const char *gk_last_error(void);
@@ -119,7 +119,9 @@ typedef struct gk_phi_stats {
     int64_t  device_bytes;      /* HBM allocated for matrices + plan */
     int64_t  kernel_launches;   /* launches one gk_phi_run enqueues */
     double   plan_seconds;      /* host planning time */
-    int64_t  plan_bytes;        /* int32 tile-plan arrays copied host->device by gk_phi_upload */
+    int64_t  plan_bytes;        /* int32 plan arrays copied host->device by gk_phi_upload */
+    int64_t  panel_row_bytes;   /* bytes of previous-matrix rows phase 1 reads: 8 * sum_g sum_panels (distinct parent rows) * Kpad_{g-1} */
+    int64_t  corrections;       /* "same individual" (i, j) corrections applied by the diagonal kernel, all steps */
 } gk_phi_stats;
 
 int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam,
@@ -143,26 +145,44 @@ int gk_phi_step_times(gk_phi_job *job, float *ms, int32_t cap);
 int gk_phi_step_bytes(gk_phi_job *job, int64_t *bytes, int32_t cap);
 void gk_phi_free(gk_phi_job *job);
 
-/* Plan introspection for tests (host arrays, valid until gk_phi_free): the per-step tile
- * plan that the kernels consume.  See DESIGN.md "Plan layout". */
+/* ---- multi-GPU: one job per rank, the class matrices sharded by rows (= columns: they are symmetric) --
+ * Every rank plans the same pedigree with opts->rank / opts->world set, uploads, exchanges the CUDA-IPC
+ * handles of its two matrix buffers (gk_phi_ipc_export -> all-gather -> gk_phi_ipc_open for every other
+ * rank -> gk_phi_peers_ready), then drives the cuts in lock step:
+ *     for g in 0 .. G-1:  gk_phi_run_step(job, g);  all-gather of the self-kinship vector (gk_phi_dvec)
+ *     gk_phi_finish(job)
+ * The step kernel reads the parent rows of its own panels straight from the owners' HBM over NVLink
+ * (peer loads inside the kernel); the all-gather of d (8 bytes per class) is the only collective and
+ * doubles as the barrier between cuts.  gk_phi_set_peer wires jobs that live in ONE process
+ * (several ranks emulated on one GPU, used by the tests). */
+int gk_phi_ipc_export(gk_phi_job *job, void *handles /* 2 x 64 bytes */);
+int gk_phi_ipc_open(gk_phi_job *job, int32_t peer_rank, const void *handles);
+int gk_phi_local_buffers(gk_phi_job *job, void **buf0, void **buf1);
+int gk_phi_set_peer(gk_phi_job *job, int32_t peer_rank, void *buf0, void *buf1);
+int gk_phi_peers_ready(gk_phi_job *job);
+int gk_phi_run_step(gk_phi_job *job, int32_t step);      /* step 0 = founders' matrix, 1 .. G-1 = recurrence */
+int gk_phi_finish(gk_phi_job *job);                      /* expansion to caller order + phiMean partial sums */
+/* Self kinship per class of cut `step` (device pointer, replicated on every rank): rank r writes
+ * doubles [r*chunk, (r+1)*chunk) and the driver all-gathers the `total` = world*chunk doubles. */
+int gk_phi_dvec(gk_phi_job *job, int32_t step, void **dev, int64_t *chunk_doubles, int64_t *total_doubles);
+
+/* Plan introspection for tests (host arrays, valid until gk_phi_free): the per-step plan the kernels
+ * consume.  See DESIGN.md "Plan layout". */
 typedef struct gk_step_view {
-    int64_t K, ld, K_prev;
-    int32_t nt, tile, win, lmax, nr_max, desc_words, conf_max, ranked;
-    int32_t off_list, off_conf, off_la, off_pind, off_rank, reserved;
-    /* nt descriptors of desc_words int32:
-     *   [0] c0 (window start column in the previous matrix, even)   [1] nl | count << 16
-     *   [2] nconf (-1: always apply the identity rule)              [3] first class (row of the new matrix)
-     *   [off_list, +lmax)  scattered parent rows of the previous matrix
-     *   [off_conf, +conf_max) tiles sharing a parent individual with this one
-     *   [off_la, +tile)   per class: local parent rows la0 | la1 << 16 (0xFFFF = unknown parent)
-     *   [off_pind, +2*tile) per class: parent individuals (ranks), -1 unknown; kept member: both = itself
-     *   [off_rank, +tile) per class: rank of its individual (ranked mode) */
-    const int32_t *desc;
+    int64_t K, Kpad, K_prev, Kpad_prev;   /* classes of this cut / the previous one (padded to 32) */
+    int64_t panel_rows;                   /* sum over panels of the distinct parent rows */
+    int32_t np, panel, ranked, ngroups;   /* panels, classes per panel (32), ranked mode, correction groups */
+    int32_t panel_begin, panel_end;       /* panels owned by this job's rank */
+    const int32_t *pF, *pM;               /* Kpad: parent rows in the previous class matrix, -1 = none */
+    const int32_t *flags;                 /* Kpad: 1 singleton, 2 kept from the previous cut, 4 both parents known */
+    const int32_t *cls_ind, *cls_size;    /* K: lowest-ranked member, number of members */
+    /* corrections: group k = (pg_i[k] >= pg_j[k]); terms pg_off[k] .. pg_off[k+1]:
+     * B[i][j] += 1/4 * pt_mult * (d_prev[pt_cls] - A_prev[pt_cls][pt_cls]) */
+    const int32_t *pg_i, *pg_j, *pg_off, *pt_cls, *pt_mult;
 } gk_step_view;
-int gk_phi_step_view(gk_phi_job *job, int32_t step, gk_step_view *view);  /* step = 1 .. G-1 */
+int gk_phi_step_view(gk_phi_job *job, int32_t step, gk_step_view *view);  /* step = 0 .. G-1 */
 /* Final expansion map: for caller entry i the class row in the last matrix and the individual. */
 int gk_phi_final_view(gk_phi_job *job, const int32_t **cls, const int32_t **ind, int64_t *K_last);
-int gk_phi_initial_classes(gk_phi_job *job, int64_t *K0);
 
 #ifdef __cplusplus
 }

@@ -1,10 +1,10 @@
-"""Test helper: a numpy interpreter of the TILE PLAN (DESIGN.md "Plan layout").
+"""Test helper: a numpy interpreter of the STEP PLAN (DESIGN.md "Plan layout").
 
-It executes, on the CPU and tile pair by tile pair, exactly what phi_step_kernel does with the
-plan arrays exposed by gk_phi_step_view -- including the symmetric fetch of the window x list
-block, the conflict-list gated "same individual" rule and the mirror store -- so the host
-planner can be checked against the oracle without a GPU.  It is NOT a product path (it lives
-under tests/)."""
+It executes on the CPU exactly what phi_step_kernel + phi_diag_kernel do with the plan arrays
+exposed by gk_phi_step_view: phase 1 (N = 1/2 (A[F] + A[M]) per new class), phase 2
+(B[j][i] = 1/2 (N[i][F_j] + N[i][M_j]), evaluated only where position j <= position i and mirrored),
+then the self-kinship / "same individual" corrections -- so the host planner can be checked against
+the reference fixtures without a GPU.  It is NOT a product path (it lives under tests/)."""
 import ctypes as C
 
 import numpy as np
@@ -12,7 +12,7 @@ import numpy as np
 from geneakit_b200 import _lib
 from geneakit_b200._lib import lib, check
 
-MISS = 0xFFFF
+SINGLETON, KEPT, BOTH = 1, 2, 4
 
 
 def _arr(ptr, n):
@@ -24,18 +24,48 @@ def _arr(ptr, n):
 def step_view(job, g):
     v = _lib.gk_step_view()
     check(lib.gk_phi_step_view(job._h, g, C.byref(v)))
-    nt, W, LMAX, DW, T = v.nt, v.win, v.lmax, v.desc_words, v.tile
-    d = dict(K=v.K, ld=v.ld, K_prev=v.K_prev, nt=nt, T=T, W=W, LMAX=LMAX, nr_max=v.nr_max,
-             conf_max=v.conf_max, ranked=bool(v.ranked))
-    desc = _arr(v.desc, nt * DW).reshape(nt, DW)
-    d["c0"], d["nl"], d["cnt"] = desc[:, 0], desc[:, 1] & 0xFFFF, desc[:, 1] >> 16
-    d["nconf"], d["start"] = desc[:, 2], desc[:, 3]
-    d["list"] = desc[:, v.off_list:v.off_list + LMAX]
-    d["conf"] = desc[:, v.off_conf:v.off_conf + v.conf_max]
-    d["la"] = desc[:, v.off_la:v.off_la + T]
-    d["pind"] = desc[:, v.off_pind:v.off_pind + 2 * T].reshape(nt, T, 2)
-    d["rank"] = desc[:, v.off_rank:v.off_rank + T]
+    K, Kpad, ng = v.K, v.Kpad, v.ngroups
+    d = dict(K=K, Kpad=Kpad, K_prev=v.K_prev, Kpad_prev=v.Kpad_prev, np=v.np, panel=v.panel,
+             ranked=bool(v.ranked), panel_rows=v.panel_rows, panel_begin=v.panel_begin, panel_end=v.panel_end)
+    d["pF"], d["pM"], d["flags"] = _arr(v.pF, Kpad), _arr(v.pM, Kpad), _arr(v.flags, Kpad)
+    d["cls_ind"], d["cls_size"] = _arr(v.cls_ind, K), _arr(v.cls_size, K)
+    d["pg_i"], d["pg_j"], d["pg_off"] = _arr(v.pg_i, ng), _arr(v.pg_j, ng), _arr(v.pg_off, ng + 1 if ng else 0)
+    nt = int(d["pg_off"][-1]) if ng else 0
+    d["pt_cls"], d["pt_mult"] = _arr(v.pt_cls, nt), _arr(v.pt_mult, nt)
     return d
+
+
+def emulate_step(v, A, dprev):
+    """One cut: (A, dprev) of the previous cut -> (B, dnew); A is Kpad_prev x Kpad_prev."""
+    K, Kpad = v["K"], v["Kpad"]
+    assert A.shape == (v["Kpad_prev"], v["Kpad_prev"]) and v["np"] * v["panel"] == Kpad
+    F, M, fl = v["pF"], v["pM"], v["flags"]
+    assert np.all(F[K:] == -1) and np.all(M[K:] == -1) and F.max(initial=-1) < v["K_prev"] and M.max(initial=-1) < v["K_prev"]
+    Aext = np.vstack([A, np.zeros((1, A.shape[1]))])                     # row -1 = zeros (unknown parent)
+    N = 0.5 * (Aext[F] + Aext[M])                                         # phase 1: Kpad x Kpad_prev
+    Next = np.hstack([N, np.zeros((Kpad, 1))])
+    V = 0.5 * (Next[:, F].T + Next[:, M].T)                               # V[j][i] = 1/2 (N[i][F_j] + N[i][M_j])
+    B = np.triu(V) + np.triu(V, 1).T                                      # valid where j <= i; mirrored
+    dnew = np.full(Kpad, 0.5)
+    for c in range(K):
+        if fl[c] & KEPT:
+            assert F[c] == M[c] and F[c] >= 0
+            dnew[c] = dprev[F[c]]
+        elif fl[c] & BOTH:
+            dnew[c] = 0.5 + 0.5 * A[F[c], M[c]]
+        if fl[c] & SINGLETON:
+            B[c, c] = dnew[c]
+    for k in range(len(v["pg_i"])):
+        i, j = int(v["pg_i"][k]), int(v["pg_j"][k])
+        assert i >= j and not (i == j and (fl[i] & SINGLETON))
+        add = 0.0
+        for t in range(v["pg_off"][k], v["pg_off"][k + 1]):
+            c = int(v["pt_cls"][t])
+            add += 0.25 * float(v["pt_mult"][t]) * (dprev[c] - A[c, c])
+        B[i, j] += add
+        if i != j:
+            B[j, i] += add
+    return B, dnew
 
 
 def emulate(job):
@@ -46,77 +76,14 @@ def emulate(job):
     fcls, find = _arr(cls_p, m), _arr(ind_p, m)
     if G == 1:
         return 0.5 * np.eye(m)
-    k0 = C.c_int64()
-    check(lib.gk_phi_initial_classes(job._h, C.byref(k0)))
-    Gp = np.zeros((k0.value, k0.value))
-    dp = np.full(k0.value, 0.5)
+    v0 = step_view(job, 0)
+    A = np.zeros((v0["Kpad"], v0["Kpad"]))
+    for c in range(v0["K"]):
+        if v0["flags"][c] & SINGLETON:
+            A[c, c] = 0.5
+    d = np.full(v0["Kpad"], 0.5)
     for g in range(1, G):
-        v = step_view(job, g)
-        K, T, W, nt = v["K"], v["T"], v["W"], v["nt"]
-        assert v["K_prev"] == Gp.shape[0]
-        assert int(v["cnt"].sum()) == K and np.array_equal(v["start"], np.concatenate([[0], np.cumsum(v["cnt"])[:-1]]))
-        assert v["nl"].max(initial=0) <= v["LMAX"] and v["cnt"].max(initial=0) <= T
-        Gn = np.full((K, K), np.nan)
-        dn = np.full(K, np.nan)
-        last = Gp.shape[0] - 1
-
-        def local_classes(t):
-            nl = v["nl"][t]
-            win = np.minimum(v["c0"][t] + np.arange(W), last)
-            return np.concatenate([win, v["list"][t, :nl]]).astype(np.int64), nl
-
-        for I in range(nt):
-            rI, nlI = local_classes(I)
-            nI, sI = v["cnt"][I], v["start"][I]
-            for J in range(I + 1):
-                cJ, nlJ = local_classes(J)
-                nJ, sJ = v["cnt"][J], v["start"][J]
-                S = np.empty((W + nlI, W + nlJ))
-                S[:, :W] = Gp[np.ix_(rI, cJ[:W])]                      # rows x window columns
-                S[:W, W:] = Gp[np.ix_(cJ[W:], rI[:W])].T               # window rows x list cols via symmetry
-                S[W:, W:] = Gp[np.ix_(rI[W:], cJ[W:])]                 # list x list
-                slow = I == J or v["nconf"][I] < 0 or v["nconf"][J] < 0 or \
-                    J in [int(x) for x in v["conf"][I, :max(v["nconf"][I], 0)]]
-                laI, laJ = v["la"][I, :nI], v["la"][J, :nJ]
-                A = [laI & 0xFFFF, (laI >> 16) & 0xFFFF]
-                B = [laJ & 0xFFFF, (laJ >> 16) & 0xFFFF]
-                IA = [v["pind"][I, :nI, 0], v["pind"][I, :nI, 1]]
-                IB = [v["pind"][J, :nJ, 0], v["pind"][J, :nJ, 1]]
-
-                def take(qa, qb):
-                    ra, cb = A[qa], B[qb]
-                    ok = (ra[:, None] != MISS) & (cb[None, :] != MISS)
-                    rr = np.where(ra == MISS, 0, ra)
-                    cc = np.where(cb == MISS, 0, cb)
-                    assert rr.max(initial=0) < S.shape[0] and cc.max(initial=0) < S.shape[1]
-                    val = S[np.ix_(rr, cc)]
-                    same = IA[qa][:, None] == IB[qb][None, :]
-                    if not slow:
-                        assert not (ok & same).any(), "identity needed on a fast-path tile pair"
-                    else:
-                        val = np.where(same, dp[rI[rr]][:, None], val)
-                    return np.where(ok, val, 0.0)
-
-                p, q, r, s = take(0, 0), take(1, 0), take(0, 1), take(1, 1)
-                if v["ranked"]:
-                    lower = v["rank"][I, :nI][:, None] < v["rank"][J, :nJ][None, :]
-                    out = np.where(lower, 0.25 * ((p + q) + (r + s)), 0.25 * ((p + r) + (q + s)))
-                else:
-                    out = 0.25 * ((p + q) + (r + s))
-                Gn[sI:sI + nI, sJ:sJ + nJ] = out
-                if I != J:
-                    Gn[sJ:sJ + nJ, sI:sI + nI] = out.T
-                else:
-                    for k in range(nI):
-                        x0, x1 = A[0][k], A[1][k]
-                        if x0 != MISS and IA[0][k] == IA[1][k]:
-                            dn[sI + k] = dp[rI[x0]]
-                        elif x0 != MISS and x1 != MISS:
-                            dn[sI + k] = 0.5 + 0.5 * S[x0, x1]
-                        else:
-                            dn[sI + k] = 0.5
-        assert not np.isnan(Gn).any() and not np.isnan(dn).any()
-        Gp, dp = Gn, dn
-    out = Gp[np.ix_(fcls, fcls)]
+        A, d = emulate_step(step_view(job, g), A, d)
+    out = A[np.ix_(fcls, fcls)]
     same = find[:, None] == find[None, :]
-    return np.where(same, dp[fcls][:, None] * np.ones((1, m)), out)
+    return np.where(same, d[fcls][:, None] * np.ones((1, m)), out)
