@@ -162,6 +162,7 @@ def main():
     import geneakit_b200 as gk
     from geneakit_b200 import _lib
     from geneakit_b200._lib import lib, check
+    from geneakit_b200.distributed import ShardedPhi
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -169,48 +170,57 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
-    if world > 1:
-        from geneakit_b200.distributed import bench_sharded
-        return bench_sharded(args, rank, world, local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     ped, pro, gen_s = make_workload(args.workload)
     m = len(pro)
     stream = torch.cuda.Stream()          # a real stream: the default stream's handle is NULL
     torch.cuda.set_stream(stream)
-    job = gk.cgeneakit.DevicePhi(ped, pro, compress=args.compress, order=args.order, device=local,
-                                 stream=stream.cuda_stream)
-    job.upload()                                   # plan + buffers resident in HBM before timing
+    sp = ShardedPhi(ped, pro, rank=rank, world=world, compress=args.compress, order=args.order, device=local,
+                    stream=stream.cuda_stream)
+    sp.upload()                                    # plan + buffers resident in HBM before timing
+    job = sp.job
     st = job.stats()
-    for _ in range(max(args.warmup, 3)):
-        job.run()
-    torch.cuda.synchronize()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        sp.run()
+    barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    barrier()
     e0.record(stream)
     for _ in range(args.steps):
-        job.run()
+        sp.run()
     e1.record(stream)
-    torch.cuda.synchronize()
+    barrier()
     sampler.stop.set()
-    sampler.join()
     ms = e0.elapsed_time(e1) / args.steps
-    mean = job.mean()
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)             # device time, max over ranks
+        ms = float(t[0])
+    mean = sp.mean()
     pairs = m * (m + 1) / 2
     value = pairs / (ms * 1e-3)
 
     # dominant kernel: phi_step_kernel, one launch per generation; CUDA events recorded by the
-    # library on this same stream around every launch of the LAST timed pass
+    # library on this same stream around every launch of the LAST timed pass (this rank's launches)
     t_ms = job.step_times_ms()
     b = job.step_bytes()
     nstep = st["n_steps"]
-    step_ms, step_bytes = sum(t_ms[:nstep]), sum(b[:nstep])
+    step_ms, step_bytes = sum(t_ms[:nstep]), sum(b[:nstep]) / world      # a rank produces 1/world of every cut's matrix
     peak, peak_src = peaks()
     achieved = step_bytes / (step_ms * 1e-3) / 1e9 if step_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "phi_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -218,58 +228,92 @@ def main():
                 "launches": nstep, "bytes_per_launch_avg": step_bytes / max(nstep, 1),
                 "ms_per_launch_avg": step_ms / max(nstep, 1), "share_of_step": step_ms / ms,
                 "expand_ms": t_ms[nstep] if len(t_ms) > nstep else None,
-                "expand_gbs": (b[nstep] / (t_ms[nstep] * 1e-3) / 1e9) if len(t_ms) > nstep and t_ms[nstep] > 0 else None}
+                "expand_gbs": (b[nstep] / world / (t_ms[nstep] * 1e-3) / 1e9) if len(t_ms) > nstep and t_ms[nstep] > 0 else None}
+    if world > 1:
+        roofline["note"] = "per GPU (rank 0): 1/%d of every cut's algorithmic bytes over this rank's launch time" % world
+        roofline["nvlink_bytes_per_pass_rank0"] = int(st["rank_remote_row_bytes"])
+        roofline["nvlink_gbs_rank0"] = st["rank_remote_row_bytes"] / (step_ms * 1e-3) / 1e9 if step_ms > 0 else None
     tr = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
-    if os.path.exists(tr):
+    if os.path.exists(tr) and world == 1:
         try:
             roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
         except Exception:
             pass
 
-    # end to end through the host-buffer C-ABI entry point (plan + H2D + kernels + D2H inside)
+    # end to end through the host-buffer entry points (plan + H2D of the plan + kernels + D2H of the
+    # result rows inside the timed region).  One GPU: the one-shot C-ABI call gk_phi_f64.
     e2e = None
     if args.e2e_steps > 0:
-        nbytes = m * m * 8
+        rows = job.row1 - job.row0
+        nbytes = rows * m * 8
         ptr = lib.gk_host_alloc(nbytes)
         pinned = bool(ptr)
         if not pinned:
-            host = np.empty((m, m), dtype=np.float64)
-            ptr = host.ctypes.data
+            hostbuf = np.empty((rows, m), dtype=np.float64)
+            ptr = hostbuf.ctypes.data
+        host = np.frombuffer((C.c_double * (rows * m)).from_address(ptr), dtype=np.float64).reshape(rows, m)
         r = ped.ranks(pro)
-        opts = _lib.make_opts(device=local, compress=args.compress, order=args.order)
         mu = C.c_double()
-        check(lib.gk_phi_f64(len(ped), ped.sire, ped.dam, m, r, ptr, C.byref(mu), C.byref(opts)))   # warm
-        t0 = time.time()
-        for _ in range(args.e2e_steps):
-            check(lib.gk_phi_f64(len(ped), ped.sire, ped.dam, m, r, ptr, C.byref(mu), C.byref(opts)))
-        dt = (time.time() - t0) / args.e2e_steps
-        assert mu.value == mean, (mu.value, mean)
+        dts = []
+        for it in range(args.e2e_steps + 1):
+            barrier()
+            t0 = time.time()
+            if world == 1:
+                opts = _lib.make_opts(device=local, compress=args.compress, order=args.order)
+                check(lib.gk_phi_f64(len(ped), ped.sire, ped.dam, m, r, ptr, C.byref(mu), C.byref(opts)))
+                got = mu.value
+            else:
+                j2 = ShardedPhi(ped, pro, rank=rank, world=world, compress=args.compress, order=args.order,
+                                device=local, stream=stream.cuda_stream)
+                j2.upload().run()
+                j2.to_host(host)
+                got = j2.mean()
+                j2.close()
+            barrier()
+            if it > 0:
+                dts.append(time.time() - t0)
+        assert got == mean, (got, mean)
+        dt = sum(dts) / len(dts)
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
         e2e = {"value": pairs / dt, "unit": "pairs/s", "seconds_per_step": dt,
-               "h2d_bytes_per_step": int(st["plan_bytes"]),
-               "d2h_bytes_per_step": int(nbytes + 16), "host_buffer": "pinned" if pinned else "pageable",
+               "h2d_bytes_per_step": int(st["plan_bytes"]) * world,
+               "d2h_bytes_per_step": int(m) * int(m) * 8 + 16 * world, "host_buffer": "pinned" if pinned else "pageable",
                "plan_seconds": st["plan_seconds"], "steps": args.e2e_steps}
         if pinned:
             lib.gk_host_free(ptr)
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and rank == 0 and world == 1:
         cpu = cpu_sample(args.workload)
 
-    w = WORKLOADS[args.workload]
-    line = {"metric": "kinship pairs/sec for gen.phi", "value": value, "unit": "pairs/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "individuals": len(ped), "generations": w["gens"], "probands": m,
-                       "seed": w["seed"], "cuts": job.cut_sizes(), "classes": job.class_sizes(),
-                       "compressed": bool(st["compressed"]), "ranked": bool(st["ranked"]), "tile": st["tile"],
-                       "l2": "inputs larger than L2 (%.1f GB of matrices per pass)" % (st["algorithmic_bytes_device"] / 1e9),
-                       "cells_reference": st["cells_reference"], "cells_device": st["cells_device"],
-                       "phi_mean": mean, "pedigree_build_s": gen_s},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
-            "gpu_launches": int(st["kernel_launches"]) * args.steps,
-            "reference_algorithmic_gbs": st["algorithmic_bytes_reference"] / (ms * 1e-3) / 1e9}
-    job.close()
-    print(json.dumps(line))
+    if rank == 0:
+        sampler.join()
+        w = WORKLOADS[args.workload]
+        sharding = ("one GPU" if world == 1 else
+                    "rows of every cut's class matrix and of the result sharded %d-way; parent rows read from the owners' "
+                    "HBM over NVLink inside the step kernel; collectives: all-gather of the self-kinship vector per cut "
+                    "+ all-reduce of 2 doubles (phiMean)" % world)
+        line = {"metric": "kinship pairs/sec for gen.phi", "value": value, "unit": "pairs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": w["desc"], "individuals": len(ped), "generations": w["gens"], "probands": m,
+                           "seed": w["seed"], "cuts": job.cut_sizes(), "classes": job.class_sizes(),
+                           "compressed": bool(st["compressed"]), "ranked": bool(st["ranked"]), "panel": st["tile"],
+                           "sharding": sharding, "rows_per_rank": job.row1 - job.row0,
+                           "l2": "inputs larger than L2 (%.1f GB of matrices per pass)" % (st["algorithmic_bytes_device"] / 1e9),
+                           "cells_reference": st["cells_reference"], "cells_device": st["cells_device"],
+                           "parent_row_bytes_per_pass": st["panel_row_bytes"], "corrections": st["corrections"],
+                           "phi_mean": mean, "pedigree_build_s": gen_s},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
+                "gpu_launches": int(st["kernel_launches"]) * args.steps * world,
+                "reference_algorithmic_gbs": st["algorithmic_bytes_reference"] / (ms * 1e-3) / 1e9}
+        print(json.dumps(line))
+    sp.close()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -32,7 +32,8 @@ class gk_phi_stats(C.Structure):
                 ("algorithmic_bytes_reference", C.c_int64), ("algorithmic_bytes_device", C.c_int64),
                 ("device_bytes", C.c_int64), ("kernel_launches", C.c_int64),
                 ("plan_seconds", C.c_double), ("plan_bytes", C.c_int64),
-                ("panel_row_bytes", C.c_int64), ("corrections", C.c_int64)]
+                ("panel_row_bytes", C.c_int64), ("corrections", C.c_int64),
+                ("rank_row_bytes", C.c_int64), ("rank_remote_row_bytes", C.c_int64)]
 
 
 class gk_step_view(C.Structure):
@@ -96,6 +97,7 @@ def _load():
     L.gk_phi_run_step.argtypes = [vp, i32]
     L.gk_phi_finish.argtypes = [vp]
     L.gk_phi_dvec.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
+    L.gk_phi_dvec_copy_from.argtypes = [vp, vp, i32]
     L.gk_phi_free.argtypes = [vp]; L.gk_phi_free.restype = None
     return L
 
@@ -109,7 +111,7 @@ EXPORTS = [
     "gk_phi_device_result", "gk_phi_get_stats", "gk_phi_cut_sizes", "gk_phi_class_sizes",
     "gk_phi_step_times", "gk_phi_step_bytes", "gk_phi_free", "gk_phi_step_view", "gk_phi_final_view",
     "gk_phi_ipc_export", "gk_phi_ipc_open", "gk_phi_local_buffers", "gk_phi_set_peer", "gk_phi_peers_ready",
-    "gk_phi_run_step", "gk_phi_finish", "gk_phi_dvec",
+    "gk_phi_run_step", "gk_phi_finish", "gk_phi_dvec", "gk_phi_dvec_copy_from",
 ]
 
 

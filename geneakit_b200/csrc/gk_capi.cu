@@ -2,6 +2,7 @@
 // plan on the host (gk_plan.hpp), keep matrices in HBM, enqueue the sm_100a kernels
 // (gk_kernels.cu) on one stream.  There is no CPU compute path in this file.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -36,6 +37,7 @@ struct StepOffsets {
     int32_t ngroups = 0, npatch = 0;
     int64_t total_items = 0;
     int32_t pb = 0, pe = 0, cpp = 0;      // own panels [pb, pe), panels per rank
+    int32_t lag = 1, ring_n = 3;          // phase 2 trails phase 1 by `lag` panels; panel buffers in the ring
 };
 
 }  // namespace
@@ -56,7 +58,9 @@ struct gk_phi_job {
     double *dvec[2] = { nullptr, nullptr };           // self kinship per class (full length, replicated)
     int64_t dvec_len = 0;
     double *ring = nullptr;
-    int64_t ring_stride = 0;
+    double *zero_row = nullptr;
+    int full_rows = 0;                // phase 2 evaluates every tile J and stores only the own rows (multi-GPU; GK_FULL_ROWS=1 forces it)
+    int lag_env = 0, ring_env = 0, lag_scale_pct = 70;   // tuning overrides (GK_LAG, GK_RING, GK_LAG_PCT)
     double *out = nullptr;            // result rows; single GPU: aliases the buffer the last step does not use
     double *out_own = nullptr;        // separately allocated result (world > 1)
     double *gloc = nullptr;           // world > 1: class rows needed by the expansion, fetched from their owners
@@ -72,9 +76,10 @@ struct gk_phi_job {
     int32_t nact = 0, nchunks = 0;
     int64_t nblocks_expand = 0;
     double *scratch = nullptr;
-    std::vector<cudaEvent_t> ev;      // G + 2 events around the step launches
+    std::vector<cudaEvent_t> ev;      // start / end events of every step (2g, 2g+1); 0, 1: the final expansion
     int64_t device_bytes = 0;
     int64_t launches = 0;
+    int64_t row_bytes = 0, remote_row_bytes = 0;   // bytes of parent rows this rank's phase 1 reads / reads from peers
 };
 
 namespace {
@@ -87,6 +92,7 @@ void destroy(gk_phi_job *j) {
             if (j->peer_ipc[q][p] && j->peer[q][p]) cudaIpcCloseMemHandle(j->peer[q][p]);
     for (int p = 0; p < 2; p++) { if (j->buf[p]) cudaFree(j->buf[p]); if (j->dvec[p]) cudaFree(j->dvec[p]); }
     if (j->ring) cudaFree(j->ring);
+    if (j->zero_row) cudaFree(j->zero_row);
     if (j->out_own) cudaFree(j->out_own);
     if (j->gloc) cudaFree(j->gloc);
     if (j->partials) cudaFree(j->partials);
@@ -257,7 +263,7 @@ int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, c
     if (j->opts.world > gk::kMaxShards) { delete j; return fail(GK_ERR_ARG, "world > 8 shards"); }
     if (j->opts.rank < 0 || j->opts.rank >= j->opts.world) { delete j; return fail(GK_ERR_ARG, "rank outside [0, world)"); }
     j->rank = j->opts.rank; j->world = j->opts.world;
-    if (!gk::build_phi_plan(n, sire, dam, m, pro, j->opts.compress, j->opts.order, j->plan)) {
+    if (!gk::build_phi_plan(n, sire, dam, m, pro, j->opts.compress, j->opts.order, j->world, j->plan)) {
         int code = j->plan.error_code == 2 ? GK_ERR_INDEX : GK_ERR_ARG;
         std::string msg = j->plan.error;
         delete j;
@@ -267,11 +273,32 @@ int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, c
         delete j;
         return fail(GK_ERR_ARG, "pedigrees deeper than 26 generations (ranked rounding) run on one GPU per job");
     }
+    j->full_rows = j->world > 1 ? 1 : 0;
+    if (const char *e = std::getenv("GK_FULL_ROWS")) if (e[0] == '1' && !j->plan.ranked) j->full_rows = 1;
+    if (const char *e = std::getenv("GK_LAG")) j->lag_env = std::atoi(e);
+    if (const char *e = std::getenv("GK_RING")) j->ring_env = std::atoi(e);
+    if (const char *e = std::getenv("GK_LAG_PCT")) j->lag_scale_pct = std::max(1, std::atoi(e));
     const int G = j->plan.G;
     j->off.assign(G, StepOffsets{});
     for (int g = 0; g < G; g++)
         panel_range(j->plan.steps[g].np, j->rank, j->world, &j->off[g].pb, &j->off[g].pe, &j->off[g].cpp);
     gk_shard_rows(j->plan.m, j->rank, j->world, &j->row0, &j->row1);
+    // rows of the previous matrix this rank's panels read, and how many of them live on a peer (NVLink)
+    for (int g = 1; g < G; g++) {
+        const gk::StepPlan &S = j->plan.steps[g];
+        const StepOffsets &o = j->off[g];
+        const int64_t rps = (int64_t) j->off[g - 1].cpp * gk::kPanel;
+        std::vector<int32_t> stamp((size_t) std::max<int64_t>(S.K_prev, 1), -1);
+        for (int p = o.pb; p < o.pe; p++)
+            for (int i = p * gk::kPanel; i < (p + 1) * gk::kPanel; i++)
+                for (int q = 0; q < 2; q++) {
+                    const int32_t r = q ? S.pM[i] : S.pF[i];
+                    if (r < 0 || stamp[r] == p) continue;
+                    stamp[r] = p;
+                    j->row_bytes += 8 * S.Kpad_prev;
+                    if (r / rps != j->rank) j->remote_row_bytes += 8 * S.Kpad_prev;
+                }
+    }
     *job = j;
     return GK_OK;
 }
@@ -305,20 +332,29 @@ int gk_phi_upload(gk_phi_job *j) {
         o.pg_i = push(S.pg_i); o.pg_j = push(S.pg_j); o.pg_off = push(S.pg_off);
         o.pt_cls = push(S.pt_cls); o.pt_mult = push(S.pt_mult);
         o.npatch = (int32_t) S.pg_i.size();
-        // work queue of the own panels: P1(pb), then P1(s), P2(s-1) ..., then P2(pe-1)
+        // work queue of the own panels: phase 2 trails phase 1 by `lag` panels: P1(s), P2(s - lag), ...
         const int ncb = (int) ((S.Kpad_prev + gk::kCB - 1) / gk::kCB);
         std::vector<int64_t> goff(1, 0);
         std::vector<int32_t> ginfo;
         auto add = [&](int phase, int panel) {
-            const int64_t items = phase == 1 ? ncb : (j->world > 1 ? S.np : panel + 1);
+            const int64_t items = phase == 1 ? ncb : (j->full_rows ? S.np : panel + 1);
             ginfo.push_back(panel | ((phase - 1) << 30));
             goff.push_back(goff.back() + items);
         };
-        for (int s = o.pb; s < o.pe; s++) {
-            add(1, s);
-            if (s > o.pb) add(2, s - 1);
+        // The resident warps work on a window of ~nwarps consecutive queue items: phase 2 of a panel
+        // should start only after that many items have been dealt since its phase 1 ended.
+        {
+            const int64_t nwarps = (int64_t) gk::step_grid() * gk::kStepWarps;
+            int lag = (int) ((nwarps * j->lag_scale_pct / 100 + ncb - 1) / ncb);
+            lag = std::max(1, std::min(lag, (int) gk::kRingMax - 2));
+            if (j->lag_env > 0) lag = std::min(j->lag_env, (int) gk::kRingMax - 1);
+            o.lag = lag;
+            o.ring_n = j->ring_env > 0 ? std::max(lag + 1, std::min(j->ring_env, (int) gk::kRingMax)) : lag + 2;
         }
-        if (o.pe > o.pb) add(2, o.pe - 1);
+        for (int s = o.pb; s < o.pe + o.lag; s++) {
+            if (s < o.pe) add(1, s);
+            if (s - o.lag >= o.pb) add(2, s - o.lag);
+        }
         o.ngroups = (int32_t) ginfo.size();
         o.total_items = goff.back();
         std::vector<int32_t> g32(goff.size() * 2);
@@ -389,15 +425,18 @@ int gk_phi_upload(gk_phi_job *j) {
     }
     j->dvec_len = dlen;
     for (int p = 0; p < 2; p++) { GK_CUDA(cudaMalloc(&j->dvec[p], (size_t) dlen * sizeof(double))); j->device_bytes += dlen * 8; }
-    j->ring_stride = max_prev * gk::kPanel;
-    GK_CUDA(cudaMalloc(&j->ring, (size_t) gk::kRing * j->ring_stride * sizeof(double)));
-    j->device_bytes += gk::kRing * j->ring_stride * 8;
+    int64_t ring_doubles = 32;
+    for (int g = 1; g < G; g++) ring_doubles = std::max(ring_doubles, (int64_t) j->off[g].ring_n * P.steps[g].Kpad_prev * gk::kPanel);
+    GK_CUDA(cudaMalloc(&j->ring, (size_t) ring_doubles * sizeof(double)));
+    GK_CUDA(cudaMalloc(&j->zero_row, 64 * sizeof(double)));
+    GK_CUDA(cudaMemsetAsync(j->zero_row, 0, 64 * sizeof(double), j->stream));
+    j->device_bytes += ring_doubles * 8;
     GK_CUDA(cudaMalloc(&j->partials, (size_t) std::max<int64_t>(j->nblocks_expand, 1) * 2 * sizeof(double)));
     GK_CUDA(cudaMalloc(&j->scratch, 2 * 256 * sizeof(double)));
     j->device_bytes += j->nblocks_expand * 16;
     GK_CUDA(cudaMalloc(&j->sums_dev, 2 * sizeof(double)));
     GK_CUDA(cudaHostAlloc(&j->sums_host, 2 * sizeof(double), cudaHostAllocDefault));
-    j->ev.resize(G + 2);
+    j->ev.resize(2 * (G + 1));
     for (auto &e : j->ev) GK_CUDA(cudaEventCreate(&e));
     j->uploaded = true;
     return GK_OK;
@@ -454,6 +493,17 @@ int gk_phi_dvec(gk_phi_job *j, int32_t step, void **dev, int64_t *chunk_doubles,
     return GK_OK;
 }
 
+// Same-process emulation of the all-gather (several ranks' jobs on ONE GPU, one stream): copy the
+// chunk rank `src` owns of the self-kinship vector of cut `step` into this job's replica.
+int gk_phi_dvec_copy_from(gk_phi_job *j, gk_phi_job *src, int32_t step) {
+    if (!j || !src || !j->uploaded || !src->uploaded || step < 0 || step >= j->plan.G) return fail(GK_ERR_ARG, "bad argument");
+    if (j == src) return GK_OK;
+    const int64_t chunk = (int64_t) j->off[step].cpp * gk::kPanel;
+    GK_CUDA(cudaMemcpyAsync(j->dvec[step & 1] + src->rank * chunk, src->dvec[step & 1] + src->rank * chunk,
+                            (size_t) chunk * sizeof(double), cudaMemcpyDeviceToDevice, j->stream));
+    return GK_OK;
+}
+
 // One cut: step 0 initialises the founders' matrix, step g >= 1 runs the recurrence kernel and the
 // diagonal kernel.  With world > 1 the driver all-gathers the self-kinship vector (gk_phi_dvec) after
 // every step -- that collective is also the barrier that makes the rows written here readable by
@@ -488,21 +538,41 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     }
     if (j->opts.verbose && j->rank == 0) std::printf("Cut %d out of %d\n", g, P.G);
     gk::StepDev d{};
-    d.prev = row_table(j, g - 1); d.out = row_table(j, g);
+    d.prev = row_table(j, g - 1);
+    d.out_base = j->buf[g & 1]; d.out_row0 = (int64_t) o.pb * gk::kPanel;
     d.ld_prev = S.Kpad_prev; d.ld_new = S.Kpad;
     d.Kpad_prev = (int32_t) S.Kpad_prev; d.np = S.np;
     d.pF = j->ints + o.pF; d.pM = j->ints + o.pM;
-    d.ring = j->ring; d.ring_stride = j->ring_stride;
+    d.zero_row = j->zero_row;
+    d.ring = j->ring; d.ring_stride = S.Kpad_prev * gk::kPanel; d.ring_n = o.ring_n;
     d.done1 = j->counters + o.done; d.done2 = d.done1 + S.np;
     d.grp_off = reinterpret_cast<const int64_t *>(j->ints + o.grp_off); d.grp_info = j->ints + o.grp_info;
     d.total_items = o.total_items; d.ngroups = o.ngroups;
     d.ncb = (int32_t) ((S.Kpad_prev + gk::kCB - 1) / gk::kCB);
     d.panel_begin = o.pb; d.panel_end = o.pe;
-    d.full_rows = j->world > 1 ? 1 : 0;
-    GK_CUDA(cudaEventRecord(j->ev[g], st));
+    d.full_rows = j->full_rows;
+    { const char *e = std::getenv("GK_OUT_POLICY"); d.out_policy = e ? std::atoi(e) : 0; }
+    { const char *e = std::getenv("GK_P1_L1"); d.p1_l1 = e ? std::atoi(e) : 0; }
+    { const char *e = std::getenv("GK_DEBUG_NOWAIT"); d.debug_nowait = (e && e[0] == '1') ? 1 : 0; }
+    static unsigned long long *g_prof = nullptr;
+    const bool profiling = std::getenv("GK_PROFILE") != nullptr;
+    if (profiling) {
+        if (!g_prof) GK_CUDA(cudaMalloc(&g_prof, 8 * sizeof(unsigned long long)));
+        GK_CUDA(cudaMemsetAsync(g_prof, 0, 8 * sizeof(unsigned long long), st));
+        d.prof = g_prof;
+    }
+    GK_CUDA(cudaEventRecord(j->ev[2 * g], st));
     GK_CUDA(gk::launch_step(d, st));
+    if (profiling) {
+        unsigned long long h[6];
+        GK_CUDA(cudaMemcpyAsync(h, g_prof, sizeof h, cudaMemcpyDeviceToHost, st));
+        GK_CUDA(cudaStreamSynchronize(st));
+        const double items = (double) o.total_items;
+        std::fprintf(stderr, "[gk profile] step %d items %.0f cycles/item: issueP2 %.0f decode+depend+publish %.0f issueP1 %.0f land %.0f computeP1 %.0f computeP2 %.0f\n",
+                     g, items, h[0] / items, h[1] / items, h[2] / items, h[3] / items, h[4] / items, h[5] / items);
+    }
     gk::DiagDev q{};
-    q.prev = d.prev; q.out = d.out; q.ld_prev = d.ld_prev; q.ld_new = d.ld_new;
+    q.prev = d.prev; q.out = row_table(j, g); q.ld_prev = d.ld_prev; q.ld_new = d.ld_new;
     q.dprev = j->dvec[(g - 1) & 1]; q.dnew = j->dvec[g & 1];
     q.pF = d.pF; q.pM = d.pM; q.flags = j->ints + o.flags;
     q.c_begin = (int32_t) std::min<int64_t>(S.K, (int64_t) o.pb * gk::kPanel);
@@ -510,7 +580,7 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     q.pg_i = j->ints + o.pg_i; q.pg_j = j->ints + o.pg_j; q.pg_off = j->ints + o.pg_off;
     q.pt_cls = j->ints + o.pt_cls; q.pt_mult = j->ints + o.pt_mult; q.ngroups = o.npatch;
     GK_CUDA(gk::launch_diag(q, st));
-    GK_CUDA(cudaEventRecord(j->ev[g + 1], st));        // (overwritten by the next step's start record: same instant)
+    GK_CUDA(cudaEventRecord(j->ev[2 * g + 1], st));
     j->launches += 2;
     j->steps_done = g + 1;
     return GK_OK;
@@ -525,7 +595,7 @@ int gk_phi_finish(gk_phi_job *j) {
     GK_CUDA(cudaSetDevice(j->device));
     cudaStream_t st = j->stream;
     const int last = G - 1;
-    GK_CUDA(cudaEventRecord(j->ev[G], st));
+    GK_CUDA(cudaEventRecord(j->ev[0], st));
     if (P.single_cut) {
         GK_CUDA(gk::launch_eye(j->out, P.m, j->row0, j->row1, j->partials, st));
     } else {
@@ -545,7 +615,7 @@ int gk_phi_finish(gk_phi_job *j) {
         GK_CUDA(gk::launch_expand(e, st));
     }
     GK_CUDA(gk::launch_mean_finish(j->partials, j->nblocks_expand, j->scratch, j->sums_dev, st));
-    GK_CUDA(cudaEventRecord(j->ev[G + 1], st));
+    GK_CUDA(cudaEventRecord(j->ev[1], st));
     j->launches += 3;
     GK_CUDA(cudaMemcpyAsync(j->sums_host, j->sums_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     j->ran = true;
@@ -631,6 +701,7 @@ int gk_phi_get_stats(gk_phi_job *j, gk_phi_stats *s) {
     s->kernel_launches = j->launches ? j->launches : (P.single_cut ? 3 : 2 * (P.G - 1) + 4);
     s->plan_seconds = P.plan_seconds;
     s->plan_bytes = (int64_t) j->ints_count * 4;
+    s->rank_row_bytes = j->row_bytes; s->rank_remote_row_bytes = j->remote_row_bytes;
     return GK_OK;
 }
 
@@ -651,8 +722,8 @@ int gk_phi_step_times(gk_phi_job *j, float *ms, int32_t cap) {
     if (rc) return rc;
     const int G = j->plan.G;
     if (j->plan.single_cut) return GK_OK;
-    for (int g = 1; g < G && g - 1 < cap; g++) GK_CUDA(cudaEventElapsedTime(&ms[g - 1], j->ev[g], j->ev[g + 1]));
-    if (G - 1 < cap) GK_CUDA(cudaEventElapsedTime(&ms[G - 1], j->ev[G], j->ev[G + 1]));   // expansion + mean
+    for (int g = 1; g < G && g - 1 < cap; g++) GK_CUDA(cudaEventElapsedTime(&ms[g - 1], j->ev[2 * g], j->ev[2 * g + 1]));
+    if (G - 1 < cap) GK_CUDA(cudaEventElapsedTime(&ms[G - 1], j->ev[0], j->ev[1]));   // expansion + mean
     return GK_OK;
 }
 

@@ -35,22 +35,218 @@ namespace gk {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kWarps = kStepWarps;        // 3 per SM sub-partition, one CTA per SM
+constexpr int kThreads = kWarps * 32;
 constexpr int T = kPanel;                 // 32
-constexpr int PS1 = kCB + 1;              // phase-1 transpose pitch (doubles): conflict-free both ways
-constexpr int PS2 = T + 1;                // phase-2 transpose pitch
+constexpr int PS = T + 2;                 // staging pitch (doubles): 16-byte aligned rows, conflict-free 128-bit transposed reads
+constexpr int kStageDoubles = 2 * T * PS; // 64 staged rows per warp: slot i = father row of class i, slot 32 + i = mother row
+constexpr size_t kStepSmem = (size_t) kWarps * kStageDoubles * sizeof(double);
 
-__device__ __forceinline__ int ld_acquire(const int *p) {
+__device__ __forceinline__ int ld_relaxed(const int *p) {
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Poll a completion counter.  Relaxed loads (an acquire would invalidate the whole L1 on every
+// iteration); everything read after the wait comes from L2 (bulk copies / stores to fresh lines).
 __device__ __forceinline__ void wait_count(const int *p, int target) {
-    while (ld_acquire(p) < target) __nanosleep(32);
+    while (ld_relaxed(p) < target) __nanosleep(100);
 }
 __device__ __forceinline__ void signal_count(int *p) {
-    __threadfence();
     asm volatile("red.release.gpu.global.add.s32 [%0], 1;\n" ::"l"(p) : "memory");
+}
+
+// L2 eviction priorities: the panel ring must stay resident (evict_last), the streams must not push it out
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long policy_evict_normal() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_hint(double *p, double v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;\n" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+
+// 16-byte asynchronous copy global -> shared through L2 only (LDGSTS); bytes = 0 zero-fills (unknown parent)
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src, unsigned bytes, unsigned long long pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(dst), "l"(src), "r"(bytes), "l"(pol) : "memory");
+}
+// same, allocating in L1 (read-only rows of the previous matrix: parent rows shared by neighbouring classes hit there)
+__device__ __forceinline__ void cp_async16_ca(unsigned dst, const void *src, unsigned bytes, unsigned long long pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(dst), "l"(src), "r"(bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// Row r of a row-sharded matrix: shard q = r / rows_per_shard (every rank owns the same number of
+// panels), local row r - q * rows_per_shard.  One shard: no lookup at all.
+struct RowLookup {
+    double *const *bases;     // shared-memory copy of RowTable::base
+    double *base0;
+    int rps;                  // rows per shard
+    int n;
+    long long ld;
+    __device__ __forceinline__ const double *operator()(int row) const {
+        if (n == 1) return base0 + (long long) row * ld;
+        const int q = row / rps;
+        return bases[q] + (long long) (row - q * rps) * ld;
+    }
+};
+
+// One CTA per SM, WARP-AUTONOMOUS: every warp walks the work queue on its own (items gw, gw + nwarps,
+// ...) with a private 17 KB shared-memory stage.  An item's 64 parent rows (256 bytes each: 32
+// columns of rows of the previous matrix for phase 1, rows of the L2-resident panel for phase 2)
+// are staged with asynchronous 16-byte copies (LDGSTS: two rows per instruction, no registers
+// held), then the warp produces the 32 x 32 tile(s) straight from shared memory.  No CTA-wide barrier.
+// (Measured alternatives, all slower on B200: 1-D TMA bulk copies sustain only ~1 row per 70 cycles
+// per SM, 4x too slow for 256-byte rows; dedicated producer warps feeding mbarrier stages serialise
+// behind the dependency waits; issuing the next item's copies before publishing the current one
+// delays the release fence by a full memory latency.)
+struct StepItem {
+    int info, local, myF, myM;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) phi_step_kernel(const StepDev s) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double *sprev[kMaxShards];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < kMaxShards) sprev[threadIdx.x] = s.prev.base[threadIdx.x];
+    __syncthreads();
+    const RowLookup prev{ sprev, s.prev.base[0], s.prev.n > 1 ? s.prev.row0[1] : 1, s.prev.n, s.ld_prev };
+    const unsigned long long pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+    const unsigned long long pol_out = s.out_policy == 0 ? pol_stream : (s.out_policy == 2 ? pol_keep : policy_evict_normal());
+    double *const S = smem + (size_t) warp * kStageDoubles;
+    const int half = lane >> 4, l16 = lane & 15;
+    // copy r < 16: father rows of classes r (lanes 0-15) and r + 16 (lanes 16-31); r >= 16: mother rows
+    const unsigned sdst = smem_u32(S) + (unsigned) ((half * 16 * PS + l16 * 2) * sizeof(double));
+    const double2 *sf = reinterpret_cast<const double2 *>(S + lane * PS), *sm = reinterpret_cast<const double2 *>(S + (T + lane) * PS);
+    double *const out = s.out_base;              // own rows of the new matrix: global row r at out + (r - out_row0) * ld_new
+    const long long ldn = s.ld_new;
+    const long long nw = (long long) gridDim.x * kWarps;
+    int g = 0;
+    int ready_panel = -1;        // phase 1 of this panel is known complete
+    int freed_panel = -1;        // phase 2 of this panel is known complete (its ring slot is free)
+
+    auto decode = [&](long long q, StepItem &it) {
+        while (q >= s.grp_off[g + 1]) ++g;
+        it.info = s.grp_info[g];
+        it.local = (int) (q - s.grp_off[g]);
+        const int cls = ((it.info >> 30) == 0 ? (it.info & 0x3FFFFFFF) : it.local) * T + lane;
+        it.myF = s.pF[cls]; it.myM = s.pM[cls];
+    };
+    // phase 2 reads the panel: phase 1 of panel I must be complete.  `pending` = a finished item of this
+    // warp that has not been published yet: it is published BEFORE blocking (the counter we wait for may
+    // be waiting for it).
+    auto depend = [&](const StepItem &it, int *pending) -> bool {
+        const int I = it.info & 0x3FFFFFFF;
+        if ((it.info >> 30) == 0 || I == ready_panel || s.debug_nowait) return false;
+        bool published = false;
+        int ok = lane == 0 ? (ld_relaxed(s.done1 + I) >= s.ncb) : 0;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) {
+            if (pending) { if (lane == 0) signal_count(pending); published = true; }
+            if (lane == 0) wait_count(s.done1 + I, s.ncb);
+            __syncwarp();
+        }
+        ready_panel = I;
+        return published;
+    };
+    auto issue = [&](const StepItem &it) {
+        const int I = it.info & 0x3FFFFFFF;
+        const bool p1 = (it.info >> 30) == 0;
+        const double *buf = s.ring + (long long) ((I - s.panel_begin) % s.ring_n) * s.ring_stride;
+        const unsigned long long pol = p1 ? pol_stream : pol_keep;
+        const long long coff = p1 ? (long long) it.local * T + l16 * 2 : (long long) l16 * 2;
+#pragma unroll 8
+        for (int r = 0; r < T; r++) {
+            const int row = __shfl_sync(0xffffffffu, r < 16 ? it.myF : it.myM, (r & 15) + 16 * half);
+            const double *src = row < 0 ? s.zero_row : (p1 ? prev(row) : buf + (long long) row * T) + coff;
+            if (p1 && s.p1_l1) cp_async16_ca(sdst + (unsigned) (((r & 15) + (r >> 4) * T) * PS * sizeof(double)), src, row >= 0 ? 16u : 0u, pol);
+            else cp_async16(sdst + (unsigned) (((r & 15) + (r >> 4) * T) * PS * sizeof(double)), src, row >= 0 ? 16u : 0u, pol);
+        }
+    };
+
+    StepItem cur;
+    long long tp[6] = { 0, 0, 0, 0, 0, 0 }, tc = 0;     // GK_PROFILE: cycles in decode / depend / issue / land / compute / publish
+    for (long long q = (long long) blockIdx.x * kWarps + warp; q < s.total_items; q += nw) {
+        if (s.prof) tc = clock64();
+        decode(q, cur);
+        if (s.prof) { if (cur.myF == -12345) tp[5]++; const long long t = clock64(); tp[1] += t - tc; tc = t; }
+        depend(cur, nullptr);
+        if (s.prof) { const long long t = clock64(); tp[1] += t - tc; tc = t; }
+        issue(cur);
+        if (s.prof) { const long long t = clock64(); tp[(cur.info >> 30) == 0 ? 2 : 0] += t - tc; tc = t; }
+        const int I = cur.info & 0x3FFFFFFF, local = cur.local;
+        double *buf = s.ring + (long long) ((I - s.panel_begin) % s.ring_n) * s.ring_stride;
+        int *done;
+        if ((cur.info >> 30) == 0) {
+            // -------- phase 1: N^T[c][i], c in [c0, c0 + 32): lane = class i, two columns per 128-bit read
+            const int old = I - s.ring_n;    // the ring slot must have been drained by phase 2 of its previous panel
+            if (old >= s.panel_begin && old > freed_panel) {
+                if (lane == 0 && !s.debug_nowait) wait_count(s.done2 + old, s.full_rows ? s.np : old + 1);
+                freed_panel = old;
+            }
+            cp_async_wait_all();
+            __syncwarp();
+            if (s.prof) { const long long t = clock64(); tp[3] += t - tc; tc = t; }
+            double *dst = buf + (long long) local * T * T + lane;
+#pragma unroll 8
+            for (int c2 = 0; c2 < T / 2; c2++) {
+                const double2 x = sf[c2], y = sm[c2];
+                st_hint(dst + (2 * c2) * T, 0.5 * (x.x + y.x), pol_keep);
+                st_hint(dst + (2 * c2 + 1) * T, 0.5 * (x.y + y.y), pol_keep);
+            }
+            done = s.done1 + I;
+        } else {
+            // -------- phase 2: tile (J, I) and its mirror ---------------------------------------
+            const int J = local;
+            double *drow = out + ((long long) J * T - s.out_row0) * ldn + I * T + lane;    // row j of tile J, columns of panel I
+            double *mrow = out + ((long long) I * T - s.out_row0) * ldn + J * T + lane;    // row i of panel I, columns of tile J
+            cp_async_wait_all();
+            __syncwarp();
+            if (s.prof) { const long long t = clock64(); tp[3] += t - tc; tc = t; }
+            if (J != I || s.full_rows) {
+                if (!s.full_rows) {
+                    // direct: lane = class i of the panel, row j: B[j][i] = 1/2 (N^T[F_j][i] + N^T[M_j][i])
+#pragma unroll 8
+                    for (int j = 0; j < T; j++)
+                        st_hint(drow + (long long) j * ldn, 0.5 * (S[j * PS + lane] + S[(T + j) * PS + lane]), pol_out);
+                }
+                // mirror: lane = class j of the tile, rows i, i + 1: B[i][j] = the same value
+#pragma unroll 8
+                for (int i2 = 0; i2 < T / 2; i2++) {
+                    const double2 x = sf[i2], y = sm[i2];
+                    st_hint(mrow + (long long) (2 * i2) * ldn, 0.5 * (x.x + y.x), pol_out);
+                    st_hint(mrow + (long long) (2 * i2 + 1) * ldn, 0.5 * (x.y + y.y), pol_out);
+                }
+            } else {
+                // diagonal tile: V[j][i] is valid where j <= i (in RANKED mode that is the reference's
+                // grouping); the other triangle is its mirror.  out[r][lane] = r <= lane ? V[r][lane] : V[lane][r]
+#pragma unroll 4
+                for (int r = 0; r < T; r++) {
+                    const double a = 0.5 * (S[r * PS + lane] + S[(T + r) * PS + lane]);          // V[r][lane]
+                    const double b = 0.5 * (S[lane * PS + r] + S[(T + lane) * PS + r]);          // V[lane][r]
+                    st_hint(mrow + (long long) r * ldn, r <= lane ? a : b, pol_out);
+                }
+            }
+            done = s.done2 + I;
+        }
+        __syncwarp();                                    // every lane is done reading the stage (and has issued its stores)
+        if (s.prof) { const long long t = clock64(); tp[(cur.info >> 30) == 0 ? 4 : 5] += t - tc; tc = t; }
+        if (lane == 0) signal_count(done);
+        if (s.prof) { __syncwarp(); const long long t = clock64(); tp[1] += t - tc; tc = t; }
+    }
+    if (s.prof && lane == 0)
+        for (int i = 0; i < 6; i++) atomicAdd(s.prof + i, (unsigned long long) tp[i]);
 }
 
 __device__ __forceinline__ double *row_ptr(const RowTable &t, int row, long long ld) {
@@ -60,103 +256,6 @@ __device__ __forceinline__ double *row_ptr(const RowTable &t, int row, long long
     for (int q = 1; q < kMaxShards; q++)
         if (q < t.n && row >= t.row0[q]) { base = t.base[q]; r0 = t.row0[q]; }
     return base + (long long) (row - r0) * ld;
-}
-
-__global__ void __launch_bounds__(kThreads, 4) phi_step_kernel(const StepDev s) {
-    __shared__ double S[T * PS1];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int g = 0;
-    int ready_panel = -1;        // phase-1 of this panel is known complete
-    int freed_panel = -1;        // phase-2 of this panel is known complete (its ring slot is free)
-    for (long long q = blockIdx.x; q < s.total_items; q += gridDim.x) {
-        while (q >= s.grp_off[g + 1]) ++g;
-        const int info = s.grp_info[g];
-        const int I = info & 0x3FFFFFFF;
-        const int local = (int) (q - s.grp_off[g]);
-        double *buf = s.ring + (long long) ((I - s.panel_begin) % kRing) * s.ring_stride;
-        if ((info >> 30) == 0) {
-            // ---------------- phase 1: N^T[c][i] for c in [c0, c0 + 64) -------------------------
-            const int c0 = local * kCB;
-            double a[4][2], b[4][2];
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const int i = I * T + warp + 8 * t;
-                const int F = s.pF[i], M = s.pM[i];
-                const double *rf = F >= 0 ? row_ptr(s.prev, F, s.ld_prev) : nullptr;
-                const double *rm = M >= 0 ? row_ptr(s.prev, M, s.ld_prev) : nullptr;
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int c = c0 + lane + 32 * h;
-                    const bool ok = c < s.Kpad_prev;
-                    a[t][h] = (rf && ok) ? __ldg(rf + c) : 0.0;
-                    b[t][h] = (rm && ok) ? __ldg(rm + c) : 0.0;
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < 4; t++)
-#pragma unroll
-                for (int h = 0; h < 2; h++) S[(warp + 8 * t) * PS1 + lane + 32 * h] = 0.5 * (a[t][h] + b[t][h]);
-            // the ring slot must have been drained by phase 2 of the panel that used it before
-            const int old = I - kRing;
-            if (old >= s.panel_begin && old > freed_panel) {
-                if (tid == 0) wait_count(s.done2 + old, s.full_rows ? s.np : old + 1);
-                freed_panel = old;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int t = 0; t < kCB / 8; t++) {
-                const int cl = warp + 8 * t, c = c0 + cl;
-                if (c < s.Kpad_prev) __stcg(buf + (long long) c * T + lane, S[lane * PS1 + cl]);
-            }
-            __syncthreads();
-            if (tid == 0) signal_count(s.done1 + I);
-        } else {
-            // ---------------- phase 2: tile (J, I) and its mirror --------------------------------
-            const int J = local;
-            if (I != ready_panel) {
-                if (tid == 0) wait_count(s.done1 + I, s.ncb);
-                ready_panel = I;
-                __syncthreads();
-            }
-            double v[4];
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const int j = J * T + warp + 8 * t;
-                const int F = s.pF[j], M = s.pM[j];
-                const double x = F >= 0 ? __ldcg(buf + (long long) F * T + lane) : 0.0;
-                const double y = M >= 0 ? __ldcg(buf + (long long) M * T + lane) : 0.0;
-                v[t] = 0.5 * (x + y);
-            }
-#pragma unroll
-            for (int t = 0; t < 4; t++) S[(warp + 8 * t) * PS2 + lane] = v[t];        // S[j][i]
-            if (!s.full_rows && J != I) {
-                // direct: row j of tile J, columns of panel I (the mirror of what this panel owns)
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const int j = J * T + warp + 8 * t;
-                    row_ptr(s.out, j, s.ld_new)[I * T + lane] = v[t];
-                }
-            }
-            __syncthreads();
-            if (J != I || s.full_rows) {
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const int il = warp + 8 * t;
-                    row_ptr(s.out, I * T + il, s.ld_new)[J * T + lane] = S[lane * PS2 + il];    // B[i][j] = S[j][i]
-                }
-            } else {
-                // diagonal tile: element (j, i) is valid where j <= i (in RANKED mode that is the
-                // reference's grouping); the other triangle is its mirror
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const int r = warp + 8 * t;
-                    row_ptr(s.out, I * T + r, s.ld_new)[I * T + lane] = r <= lane ? S[r * PS2 + lane] : S[lane * PS2 + r];
-                }
-            }
-            __syncthreads();
-            if (tid == 0) signal_count(s.done2 + I);
-        }
-    }
 }
 
 // Self kinship of the new classes (lib/compute.cpp:553-568) and the "same individual" corrections
@@ -352,7 +451,8 @@ cudaError_t configure_kernels() {
     int dev = 0, sms = 0, occ = 0;
     if ((e = cudaGetDevice(&dev))) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev))) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phi_step_kernel, kThreads, 0))) return e;
+    if ((e = cudaFuncSetAttribute(phi_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kStepSmem))) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phi_step_kernel, kThreads, kStepSmem))) return e;
     const char *env = getenv("GK_CTAS_PER_SM");
     if (env && atoi(env) > 0 && atoi(env) < occ) occ = atoi(env);
     g_step_grid = sms * (occ > 0 ? occ : 1);     // persistent: one wave, every CTA resident (the waits rely on it)
@@ -362,8 +462,9 @@ cudaError_t configure_kernels() {
 cudaError_t launch_step(const StepDev &s, cudaStream_t st) {
     if (s.total_items <= 0) return cudaSuccess;
     long long grid = g_step_grid > 0 ? g_step_grid : 148;
-    if (grid > s.total_items) grid = s.total_items;
-    phi_step_kernel<<<(unsigned) grid, kThreads, 0, st>>>(s);
+    const long long need = (s.total_items + kWarps - 1) / kWarps;
+    if (grid > need) grid = need;
+    phi_step_kernel<<<(unsigned) grid, kThreads, kStepSmem, st>>>(s);
     return cudaGetLastError();
 }
 

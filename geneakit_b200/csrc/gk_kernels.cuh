@@ -6,8 +6,9 @@
 namespace gk {
 
 constexpr int kMaxShards = 8;     // GPUs of one box
-constexpr int kRing = 3;          // L2-resident panel buffers (transposed N panels)
-constexpr int kCB = 64;           // columns of the previous matrix per phase-1 work item
+constexpr int kRingMax = 40;      // L2-resident panel buffers (transposed N panels), at most
+constexpr int kStepWarps = 12;     // warps per CTA of the step kernel (one CTA per SM), each with a private 17 KB stage
+constexpr int kCB = 32;           // columns of the previous matrix per phase-1 work item
 
 // Where the rows of a (possibly row-sharded) class matrix live: row r is owned by the shard q with
 // row0[q] <= r < row0[q+1] and sits at base[q] + (r - row0[q]) * ld.  Peer shards are CUDA-IPC
@@ -21,13 +22,16 @@ struct RowTable {
 // Everything one recurrence step needs, by value.
 struct StepDev {
     RowTable prev;            // class matrix of cut g-1: Kpad_prev rows x ld_prev
-    RowTable out;             // class matrix of cut g:   Kpad rows x ld_new
+    double *out_base;         // own rows of the class matrix of cut g (Kpad columns): global row r at out_base + (r - out_row0) * ld_new
+    int64_t out_row0;
     int64_t ld_prev, ld_new;
     int32_t Kpad_prev;
     int32_t np;               // panels / tiles of the new cut (global)
     const int32_t *pF, *pM;   // Kpad: parent rows of every new class in the previous matrix (-1 none)
-    double *ring;             // kRing x ring_stride doubles: N^T panels, [Kpad_prev][32]
+    const double *zero_row;   // >= 32 zeros (the parent row of a class with an unknown parent)
+    double *ring;             // ring_n x ring_stride doubles: N^T panels, [Kpad_prev][32]
     int64_t ring_stride;
+    int32_t ring_n;
     int32_t *done1, *done2;   // np counters each: finished phase-1 / phase-2 items of a panel
     const int64_t *grp_off;   // ngroups + 1: first work item of each group
     const int32_t *grp_info;  // ngroups: panel | (phase - 1) << 30
@@ -36,6 +40,10 @@ struct StepDev {
     int32_t ncb;              // phase-1 items per panel
     int32_t panel_begin, panel_end;   // panels this launch (rank) owns
     int32_t full_rows;        // 0: tiles J <= I, mirror stored too; 1: every tile J, own rows only
+    int32_t p1_l1;            // 1: phase-1 copies allocate in L1 (cp.async.ca)
+    int32_t out_policy;       // L2 eviction priority of the stores to the new matrix: 0 evict_first, 1 normal, 2 evict_last
+    unsigned long long *prof; // GK_PROFILE=1: 6 cycle counters (decode, depend, issue, land, compute, publish) summed over warps
+    int32_t debug_nowait;     // timing experiments only (GK_DEBUG_NOWAIT=1): skip the dependency waits, results are garbage
 };
 
 struct DiagDev {

@@ -124,14 +124,15 @@ struct ClassRec {
     int32_t member_begin, member_end;   // range in the sorted member array
 };
 
-// Greedy walk over the classes of the new cut: move from a class to an unvisited class that shares
-// one of its parent rows (preferring the row we did NOT arrive through), so that consecutive
-// classes -- hence panels of 32 -- read few distinct rows of the previous matrix.
-inline void locality_order(const std::vector<ClassRec> &cls, int64_t K_prev, std::vector<int32_t> &order) {
-    const int32_t K = (int32_t) cls.size();
-    order.clear();
-    order.reserve(K);
-    if (K_prev <= 0) { for (int32_t i = 0; i < K; i++) order.push_back(i); return; }
+// Greedy walk over (a subset of) the classes of the new cut: move from a class to an unvisited class
+// that shares one of its parent rows (preferring the row we did NOT arrive through), so that
+// consecutive classes -- hence panels of 32 -- read few distinct rows of the previous matrix.
+// `subset` lists the classes to order (indices into cls); their order is appended to `order`.
+inline void locality_order(const std::vector<ClassRec> &cls, const std::vector<int32_t> &subset, int64_t K_prev,
+                           std::vector<int32_t> &order) {
+    const int32_t K = (int32_t) subset.size();
+    if (K == 0) return;
+    if (K_prev <= 0) { for (int32_t i : subset) order.push_back(i); return; }
     std::vector<int32_t> off((size_t) K_prev + 1, 0);
     auto rows_of = [&](const ClassRec &c, int32_t r[2]) {
         int k = 0;
@@ -139,10 +140,11 @@ inline void locality_order(const std::vector<ClassRec> &cls, int64_t K_prev, std
         if (c.pc1 >= 0 && c.pc1 != c.pc0) r[k++] = c.pc1;
         return k;
     };
-    for (int32_t i = 0; i < K; i++) { int32_t r[2]; int k = rows_of(cls[i], r); for (int q = 0; q < k; q++) off[r[q] + 1]++; }
+    // local ids 0..K-1 <-> subset[local]
+    for (int32_t i = 0; i < K; i++) { int32_t r[2]; int k = rows_of(cls[subset[i]], r); for (int q = 0; q < k; q++) off[r[q] + 1]++; }
     for (int64_t c = 0; c < K_prev; c++) off[c + 1] += off[c];
     std::vector<int32_t> adj(off[K_prev]), cur(off.begin(), off.end() - 1);
-    for (int32_t i = 0; i < K; i++) { int32_t r[2]; int k = rows_of(cls[i], r); for (int q = 0; q < k; q++) adj[cur[r[q]]++] = i; }
+    for (int32_t i = 0; i < K; i++) { int32_t r[2]; int k = rows_of(cls[subset[i]], r); for (int q = 0; q < k; q++) adj[cur[r[q]]++] = i; }
     std::copy(off.begin(), off.end() - 1, cur.begin());      // cursor: first possibly-unvisited entry of each row's list
     std::vector<uint8_t> visited(K, 0);
     auto next_unvisited = [&](int32_t row) -> int32_t {
@@ -151,22 +153,22 @@ inline void locality_order(const std::vector<ClassRec> &cls, int64_t K_prev, std
         return p < off[row + 1] ? adj[p] : -1;
     };
     // walk starts: classes whose parent rows have the fewest users first (path ends before path middles)
-    std::vector<int32_t> starts(K);
-    std::vector<int32_t> deg(K);
+    std::vector<int32_t> starts(K), deg(K);
     for (int32_t i = 0; i < K; i++) {
-        int32_t r[2]; int k = rows_of(cls[i], r);
+        int32_t r[2]; int k = rows_of(cls[subset[i]], r);
         int32_t d = 0;
         for (int q = 0; q < k; q++) d += off[r[q] + 1] - off[r[q]];
         deg[i] = d; starts[i] = i;
     }
     std::stable_sort(starts.begin(), starts.end(), [&](int32_t a, int32_t b) { return deg[a] < deg[b]; });
     size_t sp = 0;
-    while ((int32_t) order.size() < K) {
+    int32_t done = 0;
+    while (done < K) {
         while (visited[starts[sp]]) sp++;
         int32_t x = starts[sp], came = -1;
         for (;;) {
-            visited[x] = 1; order.push_back(x);
-            int32_t r[2]; int k = rows_of(cls[x], r);
+            visited[x] = 1; order.push_back(subset[x]); done++;
+            int32_t r[2]; int k = rows_of(cls[subset[x]], r);
             if (k == 2 && came == r[0]) std::swap(r[0], r[1]);     // try the row we did not arrive through first
             int32_t nxt = -1;
             for (int q = 0; q < k && nxt < 0; q++) { nxt = next_unvisited(r[q]); if (nxt >= 0) came = r[q]; }
@@ -177,7 +179,7 @@ inline void locality_order(const std::vector<ClassRec> &cls, int64_t K_prev, std
 }
 
 inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m,
-                           const int32_t *pro, int compress_opt, int order_opt, PhiPlan &P) {
+                           const int32_t *pro, int compress_opt, int order_opt, int world, PhiPlan &P) {
     auto t0 = std::chrono::steady_clock::now();
     P = PhiPlan();
     P.n = n; P.m = m;
@@ -306,7 +308,27 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
                 return x.first_member < y.first_member;
             });
         } else {
-            locality_order(cls, S.K_prev, order);
+            // Multi-GPU: the rows of every matrix are sharded in equal blocks of panels.  Group the new
+            // classes by the rank that owns their first known parent's row (so that row is a LOCAL read
+            // for the rank that will own the class -- up to the spill at the block boundaries), then
+            // order each group for locality.
+            order.clear();
+            order.reserve(K);
+            std::vector<int32_t> subset;
+            if (world <= 1 || S.K_prev <= 0) {
+                subset.resize(K);
+                for (int64_t i = 0; i < K; i++) subset[i] = (int32_t) i;
+                locality_order(cls, subset, S.K_prev, order);
+            } else {
+                const int64_t rps = (int64_t) ((Sp->np + world - 1) / world) * kPanel;     // rows per shard of the previous matrix
+                std::vector<std::vector<int32_t>> groups(world);
+                for (int64_t i = 0; i < K; i++) {
+                    const int32_t pc = cls[i].pc0 >= 0 ? cls[i].pc0 : cls[i].pc1;
+                    const int q = pc < 0 ? (int) (i % world) : (int) std::min<int64_t>(world - 1, pc / rps);
+                    groups[q].push_back((int32_t) i);
+                }
+                for (int q = 0; q < world; q++) locality_order(cls, groups[q], S.K_prev, order);
+            }
         }
         S.K = K;
         S.Kpad = round_up(std::max<int64_t>(K, 1), kPanel);

@@ -1,20 +1,21 @@
 """Multi-GPU driver: one process per GPU (torchrun), torch.distributed for the plumbing.
 
-Sharding (DESIGN.md "Multi-GPU"): the final m x m kinship matrix is sharded by contiguous blocks
-of result rows (= columns: the matrix is symmetric), one block per rank -- each rank holds
-m/P x m doubles in its own HBM and copies only that block to the host.  The per-generation
-recurrence runs replicated on every rank (with sibship compression it is 3-4x smaller than the
-result matrix, and sharding it needs, every generation, the other parent's rows from remote
-shards: ~1/2 shard of NVLink traffic per generation against ~2 shards of HBM traffic, i.e.
-NVLink-bound at 8 GPUs -- SURVEY.md 8e).  The only data-path collective is therefore the
-all-reduce of the two phiMean partial sums.
+Sharding (DESIGN.md "Multi-GPU"): the class matrix of EVERY cut is sharded by blocks of rows
+(= columns: the matrices are symmetric), in panels of 32 classes, one block per rank; the final
+m x m matrix is sharded the same way by result rows.  A rank computes, for its own panels,
+phase 1 from the parent rows -- read straight out of the owners' HBM by the step kernel (CUDA-IPC
+mappings, peer loads over NVLink inside the kernel: the exchange is fused with the gather-average,
+there is no separate pack / send / unpack) -- and phase 2 against every tile, storing only its own
+rows.  The one collective per cut is the all-gather of the new classes' self kinships (8 bytes per
+class: the "diagonal inputs" of the next cut), which also is the barrier that makes a cut's rows
+readable by the peers' next step.  phiMean adds one all-reduce of two doubles.
 """
 import ctypes as C
 
 import numpy as np
 
 from . import cgeneakit
-from ._lib import lib
+from ._lib import lib, check
 
 
 def shard_rows(m, rank, world):
@@ -37,9 +38,23 @@ def combine_mean(sum_all, sum_diag, m, group=None):
     return (total - diag) / (float(m) * float(m) - float(m))
 
 
+class _DevArray:
+    """A raw device pointer as a __cuda_array_interface__ object (so torch can wrap it, zero copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def _dvec(job, g):
+    p, chunk, total = C.c_void_p(), C.c_int64(), C.c_int64()
+    check(lib.gk_phi_dvec(job._h, g, C.byref(p), C.byref(chunk), C.byref(total)))
+    return p.value, chunk.value, total.value
+
+
 class ShardedPhi:
-    """gen.phi across the ranks of the default process group: `.local` is this rank's row block
-    of the kinship matrix (device resident), `.mean()` the global gen.phiMean."""
+    """gen.phi across the ranks of the default process group: `.local` rows stay in this rank's
+    HBM, `.mean()` is the global gen.phiMean, `.to_host()` copies this rank's row block."""
 
     def __init__(self, pedigree, proband_ids=(), rank=None, world=None, **gk):
         import torch.distributed as dist
@@ -48,15 +63,49 @@ class ShardedPhi:
         self.job = cgeneakit.DevicePhi(pedigree, proband_ids, rank=self.rank, world=self.world, **gk)
         self.m = self.job.m
         self.row0, self.row1 = self.job.row0, self.job.row1
+        self.G = self.job.stats()["n_cuts"]
+        self._dv = None
 
     def upload(self):
-        self.job.upload(); return self
+        """Allocate, then make every rank's matrix buffers addressable by every rank (CUDA IPC)."""
+        import torch
+        import torch.distributed as dist
+        self.job.upload()
+        if self.world > 1:
+            mine = (C.c_ubyte * 128)()
+            check(lib.gk_phi_ipc_export(self.job._h, mine))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(mine))
+            for q in range(self.world):
+                if q != self.rank:
+                    buf = (C.c_ubyte * 128).from_buffer_copy(handles[q])
+                    check(lib.gk_phi_ipc_open(self.job._h, q, buf))
+            check(lib.gk_phi_peers_ready(self.job._h))
+            # self-kinship vectors of both parities as torch views (all-gathered in place after every cut)
+            self._dv = []
+            for g in range(self.G):
+                p, chunk, total = _dvec(self.job, g)
+                self._dv.append((torch.as_tensor(_DevArray(p, total), device="cuda"), chunk))
+            dist.barrier()
+        return self
 
     def run(self):
-        self.job.run(); return self
+        import torch.distributed as dist
+        if self.world == 1:
+            self.job.run()
+            return self
+        for g in range(self.G):
+            check(lib.gk_phi_run_step(self.job._h, g))
+            full, chunk = self._dv[g]
+            # the only per-cut collective: 8 bytes per class, and the barrier between cuts
+            dist.all_gather_into_tensor(full, full[self.rank * chunk:(self.rank + 1) * chunk])
+        check(lib.gk_phi_finish(self.job._h))
+        return self
 
     def mean(self):
         s, d = self.job.sums()
+        if self.world == 1:
+            return (s - d) / (float(self.m) * float(self.m) - float(self.m))
         return combine_mean(s, d, self.m)
 
     def to_host(self, out=None):
@@ -64,105 +113,70 @@ class ShardedPhi:
 
     def gather(self):
         """Full m x m matrix on every rank (host), for tests: all_gather of the row blocks."""
-        import torch
         import torch.distributed as dist
-        mine = torch.from_numpy(np.ascontiguousarray(self.to_host()))
+        mine = np.ascontiguousarray(self.to_host())
         parts = [None] * self.world
-        dist.all_gather_object(parts, mine.numpy())
+        dist.all_gather_object(parts, mine)
         return np.concatenate(parts, axis=0)
 
     def close(self):
+        self._dv = None
         self.job.close()
 
 
-def bench_sharded(args, rank, world, local):
-    """bench.py body for N > 1 (launched by torch.distributed.run, one rank per GPU)."""
-    import json
-    import time
-    import torch
-    import torch.distributed as dist
-    from bench import WORKLOADS, ClockSampler, make_workload, peaks
+class VirtualShardedPhi:
+    """The sharded algorithm with all `world` ranks emulated in ONE process on ONE GPU: every
+    rank's job runs its step back to back on one stream, peers are plain pointers, the all-gather
+    is a device copy.  Used by the GPU tests (a fresh box has one GPU) and to study the sharded
+    kernels without NVLink."""
 
-    ped, pro, gen_s = make_workload(args.workload)
-    m = len(pro)
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    sp = ShardedPhi(ped, pro, rank=rank, world=world, compress=args.compress, device=local,
-                    stream=stream.cuda_stream)
-    sp.upload()
-    st = sp.job.stats()
-    for _ in range(max(args.warmup, 3)):
-        sp.run()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0.record(stream)
-    for _ in range(args.steps):
-        sp.run()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    dist.barrier()
-    t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)             # device time, max over ranks
-    ms = float(t[0])
-    mean = sp.mean()
-    sampler.stop.set()
-    pairs = m * (m + 1) / 2
+    def __init__(self, pedigree, proband_ids=(), world=2, **gk):
+        self.world = world
+        self.jobs = [cgeneakit.DevicePhi(pedigree, proband_ids, rank=q, world=world, **gk) for q in range(world)]
+        self.m = self.jobs[0].m
+        self.G = self.jobs[0].stats()["n_cuts"]
 
-    # end to end: plan + upload + kernels + device->host copy of this rank's rows, every rank in parallel
-    e2e = None
-    if args.e2e_steps > 0:
-        rows = sp.row1 - sp.row0
-        ptr = lib.gk_host_alloc(rows * m * 8)
-        host = np.frombuffer((C.c_double * (rows * m)).from_address(ptr), dtype=np.float64).reshape(rows, m) if ptr \
-            else np.empty((rows, m), dtype=np.float64)
-        dts = []
-        for it in range(args.e2e_steps + 1):
-            dist.barrier()
-            t0 = time.time()
-            j = ShardedPhi(ped, pro, rank=rank, world=world, compress=args.compress, device=local)
-            j.upload().run()
-            j.to_host(host)
-            mu = j.mean()
+    def upload(self):
+        for j in self.jobs:
+            j.upload()
+        bufs = []
+        for j in self.jobs:
+            b0, b1 = C.c_void_p(), C.c_void_p()
+            check(lib.gk_phi_local_buffers(j._h, C.byref(b0), C.byref(b1)))
+            bufs.append((b0, b1))
+        for q, j in enumerate(self.jobs):
+            for p in range(self.world):
+                if p != q:
+                    check(lib.gk_phi_set_peer(j._h, p, bufs[p][0], bufs[p][1]))
+            check(lib.gk_phi_peers_ready(j._h))
+        return self
+
+    def run(self):
+        for g in range(self.G):
+            for j in self.jobs:
+                check(lib.gk_phi_run_step(j._h, g))
+            for j in self.jobs:
+                j.sync()
+            for j in self.jobs:
+                for src in self.jobs:
+                    check(lib.gk_phi_dvec_copy_from(j._h, src._h, g))
+            for j in self.jobs:
+                j.sync()
+        for j in self.jobs:
+            check(lib.gk_phi_finish(j._h))
+        return self
+
+    def mean(self):
+        s = d = 0.0
+        for j in self.jobs:
+            a, b = j.sums()
+            s += a
+            d += b
+        return (s - d) / (float(self.m) * float(self.m) - float(self.m))
+
+    def to_host(self):
+        return np.concatenate([np.asarray(j.to_host()) for j in self.jobs], axis=0)
+
+    def close(self):
+        for j in self.jobs:
             j.close()
-            dist.barrier()
-            if it > 0:
-                dts.append(time.time() - t0)
-        assert mu == mean, (mu, mean)
-        dt = torch.tensor([sum(dts) / len(dts)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": pairs / float(dt[0]), "unit": "pairs/s", "seconds_per_step": float(dt[0]),
-               "h2d_bytes_per_step": int(st["plan_bytes"]) * world, "d2h_bytes_per_step": int(m) * int(m) * 8 + 16 * world,
-               "host_buffer": "pinned" if ptr else "pageable", "steps": args.e2e_steps}
-        if ptr:
-            lib.gk_host_free(ptr)
-
-    if rank == 0:
-        sampler.join()
-        t_ms, b = sp.job.step_times_ms(), sp.job.step_bytes()
-        nstep = st["n_steps"]
-        step_ms, step_bytes = sum(t_ms[:nstep]), sum(b[:nstep])
-        peak, peak_src = peaks()
-        achieved = step_bytes / (step_ms * 1e-3) / 1e9 if step_ms > 0 else 0.0
-        w = WORKLOADS[args.workload]
-        line = {"metric": "kinship pairs/sec for gen.phi", "value": pairs / (ms * 1e-3), "unit": "pairs/s",
-                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
-                "config": {"workload": w["desc"], "individuals": len(ped), "generations": w["gens"], "probands": m,
-                           "seed": w["seed"], "sharding": "result rows sharded %d-way; recurrence replicated per rank; "
-                           "collective = all-reduce of 2 doubles (phiMean)" % world,
-                           "rows_per_rank": sp.row1 - sp.row0, "compressed": bool(st["compressed"]),
-                           "l2": "inputs larger than L2", "phi_mean": mean},
-                "roofline": {"bound": "hbm", "kernel": "phi_step_kernel", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                             "note": "per GPU (rank 0); every rank runs the same recurrence launches"},
-                "cpu_baseline": None, "e2e": e2e, "clocks": sampler.summary(),
-                "gpu_launches": int(st["kernel_launches"]) * args.steps * world}
-        print(json.dumps(line))
-    sp.close()
-    dist.destroy_process_group()

@@ -122,6 +122,8 @@ typedef struct gk_phi_stats {
     int64_t  plan_bytes;        /* int32 plan arrays copied host->device by gk_phi_upload */
     int64_t  panel_row_bytes;   /* bytes of previous-matrix rows phase 1 reads: 8 * sum_g sum_panels (distinct parent rows) * Kpad_{g-1} */
     int64_t  corrections;       /* "same individual" (i, j) corrections applied by the diagonal kernel, all steps */
+    int64_t  rank_row_bytes;    /* parent-row bytes THIS rank's phase 1 reads (its own panels) */
+    int64_t  rank_remote_row_bytes; /* ... of which from rows owned by another rank: NVLink bytes per pass */
 } gk_phi_stats;
 
 int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam,
@@ -165,6 +167,8 @@ int gk_phi_finish(gk_phi_job *job);                      /* expansion to caller 
 /* Self kinship per class of cut `step` (device pointer, replicated on every rank): rank r writes
  * doubles [r*chunk, (r+1)*chunk) and the driver all-gathers the `total` = world*chunk doubles. */
 int gk_phi_dvec(gk_phi_job *job, int32_t step, void **dev, int64_t *chunk_doubles, int64_t *total_doubles);
+/* one-process emulation of that all-gather (tests): copy rank src's chunk of cut `step` into job's replica */
+int gk_phi_dvec_copy_from(gk_phi_job *job, gk_phi_job *src, int32_t step);
 
 /* Plan introspection for tests (host arrays, valid until gk_phi_free): the per-step plan the kernels
  * consume.  See DESIGN.md "Plan layout". */

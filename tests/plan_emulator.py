@@ -87,3 +87,34 @@ def emulate(job):
     out = A[np.ix_(fcls, fcls)]
     same = find[:, None] == find[None, :]
     return np.where(same, d[fcls][:, None] * np.ones((1, m)), out)
+
+
+def emulate_step_rows(v, A, dprev):
+    """Sharded mode (a rank of a multi-GPU job): only the rows of this job's own panels, every tile J
+    evaluated, nothing mirrored: returns (c0, c1, B[c0:c1, :], dnew[c0:c1])."""
+    K, Kpad, T = v["K"], v["Kpad"], v["panel"]
+    c0, c1 = v["panel_begin"] * T, v["panel_end"] * T
+    F, M, fl = v["pF"], v["pM"], v["flags"]
+    Aext = np.vstack([A, np.zeros((1, A.shape[1]))])
+    N = 0.5 * (Aext[F[c0:c1]] + Aext[M[c0:c1]])                          # phase 1 of the own panels (rows may be remote)
+    Next = np.hstack([N, np.zeros((c1 - c0, 1))])
+    B = 0.5 * (Next[:, F] + Next[:, M])                                   # B[i][j] = 1/2 (N[i][F_j] + N[i][M_j]), every j
+    dnew = np.full(c1 - c0, 0.5)
+    for c in range(c0, min(c1, K)):
+        if fl[c] & KEPT:
+            dnew[c - c0] = dprev[F[c]]
+        elif fl[c] & BOTH:
+            dnew[c - c0] = 0.5 + 0.5 * A[F[c], M[c]]
+        if fl[c] & SINGLETON:
+            B[c - c0, c] = dnew[c - c0]
+    for k in range(len(v["pg_i"])):
+        i, j = int(v["pg_i"][k]), int(v["pg_j"][k])
+        add = 0.0
+        for t in range(v["pg_off"][k], v["pg_off"][k + 1]):
+            c = int(v["pt_cls"][t])
+            add += 0.25 * float(v["pt_mult"][t]) * (dprev[c] - A[c, c])
+        if c0 <= i < c1:
+            B[i - c0, j] += add
+        if i != j and c0 <= j < c1:
+            B[j - c0, i] += add
+    return c0, c1, B, dnew
