@@ -552,25 +552,9 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     d.panel_begin = o.pb; d.panel_end = o.pe;
     d.full_rows = j->full_rows;
     { const char *e = std::getenv("GK_OUT_POLICY"); d.out_policy = e ? std::atoi(e) : 0; }
-    { const char *e = std::getenv("GK_P1_L1"); d.p1_l1 = e ? std::atoi(e) : 0; }
     { const char *e = std::getenv("GK_DEBUG_NOWAIT"); d.debug_nowait = (e && e[0] == '1') ? 1 : 0; }
-    static unsigned long long *g_prof = nullptr;
-    const bool profiling = std::getenv("GK_PROFILE") != nullptr;
-    if (profiling) {
-        if (!g_prof) GK_CUDA(cudaMalloc(&g_prof, 8 * sizeof(unsigned long long)));
-        GK_CUDA(cudaMemsetAsync(g_prof, 0, 8 * sizeof(unsigned long long), st));
-        d.prof = g_prof;
-    }
     GK_CUDA(cudaEventRecord(j->ev[2 * g], st));
     GK_CUDA(gk::launch_step(d, st));
-    if (profiling) {
-        unsigned long long h[6];
-        GK_CUDA(cudaMemcpyAsync(h, g_prof, sizeof h, cudaMemcpyDeviceToHost, st));
-        GK_CUDA(cudaStreamSynchronize(st));
-        const double items = (double) o.total_items;
-        std::fprintf(stderr, "[gk profile] step %d items %.0f cycles/item: issueP2 %.0f decode+depend+publish %.0f issueP1 %.0f land %.0f computeP1 %.0f computeP2 %.0f\n",
-                     g, items, h[0] / items, h[1] / items, h[2] / items, h[3] / items, h[4] / items, h[5] / items);
-    }
     gk::DiagDev q{};
     q.prev = d.prev; q.out = row_table(j, g); q.ld_prev = d.ld_prev; q.ld_new = d.ld_new;
     q.dprev = j->dvec[(g - 1) & 1]; q.dnew = j->dvec[g & 1];

@@ -81,10 +81,6 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) 
 __device__ __forceinline__ void cp_async16(unsigned dst, const void *src, unsigned bytes, unsigned long long pol) {
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(dst), "l"(src), "r"(bytes), "l"(pol) : "memory");
 }
-// same, allocating in L1 (read-only rows of the previous matrix: parent rows shared by neighbouring classes hit there)
-__device__ __forceinline__ void cp_async16_ca(unsigned dst, const void *src, unsigned bytes, unsigned long long pol) {
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(dst), "l"(src), "r"(bytes), "l"(pol) : "memory");
-}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // Row r of a row-sharded matrix: shard q = r / rows_per_shard (every rank owns the same number of
@@ -170,21 +166,15 @@ __global__ void __launch_bounds__(kThreads, 1) phi_step_kernel(const StepDev s) 
         for (int r = 0; r < T; r++) {
             const int row = __shfl_sync(0xffffffffu, r < 16 ? it.myF : it.myM, (r & 15) + 16 * half);
             const double *src = row < 0 ? s.zero_row : (p1 ? prev(row) : buf + (long long) row * T) + coff;
-            if (p1 && s.p1_l1) cp_async16_ca(sdst + (unsigned) (((r & 15) + (r >> 4) * T) * PS * sizeof(double)), src, row >= 0 ? 16u : 0u, pol);
-            else cp_async16(sdst + (unsigned) (((r & 15) + (r >> 4) * T) * PS * sizeof(double)), src, row >= 0 ? 16u : 0u, pol);
+            cp_async16(sdst + (unsigned) (((r & 15) + (r >> 4) * T) * PS * sizeof(double)), src, row >= 0 ? 16u : 0u, pol);
         }
     };
 
     StepItem cur;
-    long long tp[6] = { 0, 0, 0, 0, 0, 0 }, tc = 0;     // GK_PROFILE: cycles in decode / depend / issue / land / compute / publish
     for (long long q = (long long) blockIdx.x * kWarps + warp; q < s.total_items; q += nw) {
-        if (s.prof) tc = clock64();
         decode(q, cur);
-        if (s.prof) { if (cur.myF == -12345) tp[5]++; const long long t = clock64(); tp[1] += t - tc; tc = t; }
         depend(cur, nullptr);
-        if (s.prof) { const long long t = clock64(); tp[1] += t - tc; tc = t; }
         issue(cur);
-        if (s.prof) { const long long t = clock64(); tp[(cur.info >> 30) == 0 ? 2 : 0] += t - tc; tc = t; }
         const int I = cur.info & 0x3FFFFFFF, local = cur.local;
         double *buf = s.ring + (long long) ((I - s.panel_begin) % s.ring_n) * s.ring_stride;
         int *done;
@@ -197,7 +187,6 @@ __global__ void __launch_bounds__(kThreads, 1) phi_step_kernel(const StepDev s) 
             }
             cp_async_wait_all();
             __syncwarp();
-            if (s.prof) { const long long t = clock64(); tp[3] += t - tc; tc = t; }
             double *dst = buf + (long long) local * T * T + lane;
 #pragma unroll 8
             for (int c2 = 0; c2 < T / 2; c2++) {
@@ -213,7 +202,6 @@ __global__ void __launch_bounds__(kThreads, 1) phi_step_kernel(const StepDev s) 
             double *mrow = out + ((long long) I * T - s.out_row0) * ldn + J * T + lane;    // row i of panel I, columns of tile J
             cp_async_wait_all();
             __syncwarp();
-            if (s.prof) { const long long t = clock64(); tp[3] += t - tc; tc = t; }
             if (J != I || s.full_rows) {
                 if (!s.full_rows) {
                     // direct: lane = class i of the panel, row j: B[j][i] = 1/2 (N^T[F_j][i] + N^T[M_j][i])
@@ -241,12 +229,8 @@ __global__ void __launch_bounds__(kThreads, 1) phi_step_kernel(const StepDev s) 
             done = s.done2 + I;
         }
         __syncwarp();                                    // every lane is done reading the stage (and has issued its stores)
-        if (s.prof) { const long long t = clock64(); tp[(cur.info >> 30) == 0 ? 4 : 5] += t - tc; tc = t; }
         if (lane == 0) signal_count(done);
-        if (s.prof) { __syncwarp(); const long long t = clock64(); tp[1] += t - tc; tc = t; }
     }
-    if (s.prof && lane == 0)
-        for (int i = 0; i < 6; i++) atomicAdd(s.prof + i, (unsigned long long) tp[i]);
 }
 
 __device__ __forceinline__ double *row_ptr(const RowTable &t, int row, long long ld) {

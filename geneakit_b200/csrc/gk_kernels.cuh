@@ -40,9 +40,7 @@ struct StepDev {
     int32_t ncb;              // phase-1 items per panel
     int32_t panel_begin, panel_end;   // panels this launch (rank) owns
     int32_t full_rows;        // 0: tiles J <= I, mirror stored too; 1: every tile J, own rows only
-    int32_t p1_l1;            // 1: phase-1 copies allocate in L1 (cp.async.ca)
     int32_t out_policy;       // L2 eviction priority of the stores to the new matrix: 0 evict_first, 1 normal, 2 evict_last
-    unsigned long long *prof; // GK_PROFILE=1: 6 cycle counters (decode, depend, issue, land, compute, publish) summed over warps
     int32_t debug_nowait;     // timing experiments only (GK_DEBUG_NOWAIT=1): skip the dependency waits, results are garbage
 };
 

@@ -1,7 +1,11 @@
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" || exit 1
-run() { name=$1; shift; env "$@" timeout 300 python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 > gpurun_out/exp_c4_$name.json 2>> gpurun_out/exp.err; echo "$name exit $?"; }
-run base X=1
-run l1 GK_P1_L1=1
-GK_P1_L1=1 GK_PROFILE=1 timeout 300 python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 0 > gpurun_out/exp_c4_prof.json 2> gpurun_out/prof.err; tail -2 gpurun_out/prof.err
-python scripts/summarize.py gpurun_out/exp_c4_base.json gpurun_out/exp_c4_l1.json
+timeout 200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo pytest-exit $?; tail -3 gpurun_out/pytest_gpu.log
+run() { name=$1; wl=$2; shift; shift; env "$@" timeout 90 python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 > gpurun_out/exp_${wl}_$name.json 2>> gpurun_out/exp.err; echo "$name exit $?"; }
+run r3 c4 GK_RING=3
+run r4 c4 GK_RING=4
+run only1 c4 GK_DEBUG_NOWAIT=1 GK_DEBUG_ONLY=1
+run nowait c4 GK_DEBUG_NOWAIT=1
+run r4 c3 GK_RING=4
+run r8 c3 GK_RING=8
+python scripts/summarize.py gpurun_out/exp_c4_*.json gpurun_out/exp_c3_*.json
