@@ -60,7 +60,7 @@ struct gk_phi_job {
     double *ring = nullptr;
     double *zero_row = nullptr;
     int full_rows = 0;                // phase 2 evaluates every tile J and stores only the own rows (multi-GPU; GK_FULL_ROWS=1 forces it)
-    int lag_env = 0, ring_env = 0, lag_scale_pct = 70;   // tuning overrides (GK_LAG, GK_RING, GK_LAG_PCT)
+    int lag_env = 0, ring_env = 0, lag_scale_pct = 100;   // tuning overrides (GK_LAG, GK_RING, GK_LAG_PCT)
     double *out = nullptr;            // result rows; single GPU: aliases the buffer the last step does not use
     double *out_own = nullptr;        // separately allocated result (world > 1)
     double *gloc = nullptr;           // world > 1: class rows needed by the expansion, fetched from their owners
