@@ -116,7 +116,7 @@ def cpu_sample(workload, repeats=1):
                       % (SAMPLE_DIV, workload, w["n"] // SAMPLE_DIV, w["gens"], m)}
 
 
-def run_reference(args):
+def run_reference(args, out):
     """--impl reference: the reference's own CPU implementation, all host threads, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -140,7 +140,17 @@ def run_reference(args):
             "data": "synthetic", "config": {"workload": w["desc"], "sample": sample},
             "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": int(cores), "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else a library prints there (NCCL's version banner,
+    torchrun notices) goes to stderr.  Returns a file object on the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -155,8 +165,9 @@ def main():
     ap.add_argument("--compress", type=int, default=-1)
     ap.add_argument("--order", type=int, default=-1)
     args = ap.parse_args()
+    out = _claim_stdout()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import torch
     import geneakit_b200 as gk
@@ -310,7 +321,8 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
                 "gpu_launches": int(st["kernel_launches"]) * args.steps * world,
                 "reference_algorithmic_gbs": st["algorithmic_bytes_reference"] / (ms * 1e-3) / 1e9}
-        print(json.dumps(line))
+        out.write(json.dumps(line) + "\n")
+        out.flush()
     sp.close()
     if dist is not None:
         dist.destroy_process_group()
