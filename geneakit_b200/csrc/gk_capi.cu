@@ -37,6 +37,7 @@ struct StepOffsets {
     int32_t ngroups = 0, npatch = 0;
     int64_t total_items = 0;
     int32_t pb = 0, pe = 0, cpp = 0;      // own panels [pb, pe), panels per rank
+    size_t grp_off2 = 0; int64_t total1 = 0, total2 = 0; int32_t n1pp = 0, ring_tma = 4;   // multi-GPU kernel: two item streams
     int32_t lag = 1, ring_n = 3;          // phase 2 trails phase 1 by `lag` panels; panel buffers in the ring
 };
 
@@ -59,6 +60,7 @@ struct gk_phi_job {
     int64_t dvec_len = 0;
     double *ring = nullptr;
     double *zero_row = nullptr;
+    int use_tma = 0;                  // step kernel: 0 = warp-autonomous LDGSTS (one GPU), 1 = TMA phase 1 (multi-GPU; GK_STEP_KERNEL=tma|ldgsts)
     int full_rows = 0;                // phase 2 evaluates every tile J and stores only the own rows (multi-GPU; GK_FULL_ROWS=1 forces it)
     int lag_env = 0, ring_env = 0, lag_scale_pct = 100;   // tuning overrides (GK_LAG, GK_RING, GK_LAG_PCT)
     double *out = nullptr;            // result rows; single GPU: aliases the buffer the last step does not use
@@ -274,6 +276,8 @@ int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, c
         return fail(GK_ERR_ARG, "pedigrees deeper than 26 generations (ranked rounding) run on one GPU per job");
     }
     j->full_rows = j->world > 1 ? 1 : 0;
+    j->use_tma = j->world > 1 ? 1 : 0;
+    if (const char *e = std::getenv("GK_STEP_KERNEL")) j->use_tma = (e[0] == 't') ? 1 : 0;
     if (const char *e = std::getenv("GK_FULL_ROWS")) if (e[0] == '1' && !j->plan.ranked) j->full_rows = 1;
     if (const char *e = std::getenv("GK_LAG")) j->lag_env = std::atoi(e);
     if (const char *e = std::getenv("GK_RING")) j->ring_env = std::atoi(e);
@@ -360,6 +364,19 @@ int gk_phi_upload(gk_phi_job *j) {
         std::vector<int32_t> g32(goff.size() * 2);
         std::memcpy(g32.data(), goff.data(), goff.size() * 8);
         o.grp_off = push(g32); o.grp_info = push(ginfo);
+        {   // multi-GPU kernel (phi_step_tma_kernel): phase-1 items = 8 classes x 256 columns, phase-2 items = one tile
+            const int ncb256 = (int) ((S.Kpad_prev + gk::kP1Cols - 1) / gk::kP1Cols);
+            o.n1pp = (gk::kPanel / gk::kP1Classes) * ncb256;
+            o.total1 = (int64_t) (o.pe - o.pb) * o.n1pp;
+            std::vector<int64_t> goff2(1, 0);
+            for (int s = o.pb; s < o.pe; s++) goff2.push_back(goff2.back() + (j->full_rows ? S.np : s + 1));
+            o.total2 = goff2.back();
+            std::vector<int32_t> g32b(goff2.size() * 2);
+            std::memcpy(g32b.data(), goff2.data(), goff2.size() * 8);
+            o.grp_off2 = push(g32b);
+            o.ring_tma = j->ring_env > 0 ? std::max(2, std::min(j->ring_env, (int) gk::kRingMax)) : 4;
+            if (j->use_tma) o.ring_n = o.ring_tma;
+        }
         o.done = ncount; ncount += 2 * (size_t) S.np;
     }
     j->off_final_cls = push(P.final_cls);
@@ -428,8 +445,8 @@ int gk_phi_upload(gk_phi_job *j) {
     int64_t ring_doubles = 32;
     for (int g = 1; g < G; g++) ring_doubles = std::max(ring_doubles, (int64_t) j->off[g].ring_n * P.steps[g].Kpad_prev * gk::kPanel);
     GK_CUDA(cudaMalloc(&j->ring, (size_t) ring_doubles * sizeof(double)));
-    GK_CUDA(cudaMalloc(&j->zero_row, 64 * sizeof(double)));
-    GK_CUDA(cudaMemsetAsync(j->zero_row, 0, 64 * sizeof(double), j->stream));
+    GK_CUDA(cudaMalloc(&j->zero_row, gk::kP1Cols * sizeof(double)));
+    GK_CUDA(cudaMemsetAsync(j->zero_row, 0, gk::kP1Cols * sizeof(double), j->stream));
     j->device_bytes += ring_doubles * 8;
     GK_CUDA(cudaMalloc(&j->partials, (size_t) std::max<int64_t>(j->nblocks_expand, 1) * 2 * sizeof(double)));
     GK_CUDA(cudaMalloc(&j->scratch, 2 * 256 * sizeof(double)));
@@ -554,7 +571,11 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     { const char *e = std::getenv("GK_OUT_POLICY"); d.out_policy = e ? std::atoi(e) : 0; }
     { const char *e = std::getenv("GK_DEBUG_NOWAIT"); d.debug_nowait = (e && e[0] == '1') ? 1 : 0; }
     GK_CUDA(cudaEventRecord(j->ev[2 * g], st));
-    GK_CUDA(gk::launch_step(d, st));
+    d.grp_off2 = reinterpret_cast<const int64_t *>(j->ints + o.grp_off2);
+    d.total1 = o.total1; d.total2 = o.total2; d.n1pp = o.n1pp;
+    d.ncb256 = (int32_t) ((S.Kpad_prev + gk::kP1Cols - 1) / gk::kP1Cols);
+    if (j->use_tma) GK_CUDA(gk::launch_step_tma(d, st));
+    else GK_CUDA(gk::launch_step(d, st));
     gk::DiagDev q{};
     q.prev = d.prev; q.out = row_table(j, g); q.ld_prev = d.ld_prev; q.ld_new = d.ld_new;
     q.dprev = j->dvec[(g - 1) & 1]; q.dnew = j->dvec[g & 1];

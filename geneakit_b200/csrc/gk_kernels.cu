@@ -42,6 +42,18 @@ constexpr int PS = T + 2;                 // staging pitch (doubles): 16-byte al
 constexpr int kStageDoubles = 2 * T * PS; // 64 staged rows per warp: slot i = father row of class i, slot 32 + i = mother row
 constexpr size_t kStepSmem = (size_t) kWarps * kStageDoubles * sizeof(double);
 
+// ---- second step kernel (multi-GPU): phase 1 through the TMA engine ---------------------------------
+constexpr int NW2 = kStepP2Warps;         // phase-2 warps per CTA (LDGSTS, one private stage each)
+constexpr int NC1 = kStepP1Consumers;     // phase-1 consumer warps per CTA
+constexpr int NS1 = kStepP1Stages;        // phase-1 TMA stages per CTA
+static_assert(NC1 % NS1 == 0 && (32 / (NC1 / NS1)) % 4 == 0, "consumer warps per stage must divide the columns");
+constexpr int kThreadsTma = (NW2 + NC1 + 1) * 32;   // + the phase-1 producer warp
+constexpr int S1 = kP1Classes;            // phase 1: classes per item (8)
+constexpr int C1 = kP1Cols;               // phase 1: columns per item (256): 2 KB row segments, the size the TMA engine needs
+constexpr int P1PITCH = C1 * 8 + 16;      // bytes between staged rows: 516 words = 4 mod 32 -> conflict-free (class, column) reads
+constexpr int P1STAGE = 2 * S1 * P1PITCH; // 16 rows: slot i = father row of class i, slot 8 + i = mother row
+constexpr size_t kStepSmemTma = (size_t) NW2 * kStageDoubles * sizeof(double) + (size_t) NS1 * P1STAGE + 2 * NS1 * sizeof(unsigned long long);
+
 __device__ __forceinline__ int ld_relaxed(const int *p) {
     int v;
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
@@ -82,6 +94,32 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void *src, unsign
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(dst), "l"(src), "r"(bytes), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// ---- mbarrier + bulk asynchronous copy (the TMA engine, 1-D) -----------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "GK_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra GK_DONE;\n"
+        "bra GK_WAIT;\n"
+        "GK_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(unsigned dst, const void *src, unsigned bytes, unsigned bar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
 
 // Row r of a row-sharded matrix: shard q = r / rows_per_shard (every rank owns the same number of
 // panels), local row r - q * rows_per_shard.  One shard: no lookup at all.
@@ -230,6 +268,162 @@ __global__ void __launch_bounds__(kThreads, 1) phi_step_kernel(const StepDev s) 
         }
         __syncwarp();                                    // every lane is done reading the stage (and has issued its stores)
         if (lane == 0) signal_count(done);
+    }
+}
+
+// SECOND STEP KERNEL, used by the ranks of a multi-GPU job (the parent rows of phase 1 are mostly on a
+// peer: the TMA engine's deep asynchronous queue hides the NVLink latency that stalls LDGSTS issue;
+// measured at 2 GPUs: 186 ms per pass against 261 ms with the kernel above).  One CTA per SM, two
+// engines at once:
+//
+//  PHASE 1 through the TMA engine.  An item = 8 classes of a panel x 256 columns: the producer warp has
+//  the TMA engine copy the 16 parent-row segments (2 KB each -- measured on B200: 1-D bulk copies cost
+//  ~72 cycles per SM whatever their size below 1 KB and only reach HBM rate from 2 KB up, random
+//  rows included) into one of NS1 shared-memory stages, completion on the stage's mbarrier, nothing
+//  held in registers, the next stages already in flight.  NC1 consumer warps average father and
+//  mother rows straight out of the stage -- lane = (class, column) -- and store the 64-byte pieces
+//  N^T[c][8 classes] of the L2-resident panel.
+//
+//  PHASE 2 through the LSU.  NW2 autonomous warps, each with a private 17 KB stage: an item's 64
+//  panel rows (256 bytes each, L2 hits) are staged with asynchronous 16-byte copies (LDGSTS, two
+//  rows per instruction), then the warp produces tile (J, I) and its mirror straight from shared
+//  memory.
+//
+// The two item streams are dealt round-robin over the CTAs and meet only in the per-panel completion
+// counters: phase 2 of panel I waits for its n1 phase-1 items, phase 1 of panel I for phase 2 of
+// panel I - ring_n (whose ring slot it overwrites).  Every wait is on strictly earlier work, so the
+// persistent grid cannot deadlock.  No CTA-wide barrier in the loops.
+__global__ void __launch_bounds__(kThreadsTma, 1) phi_step_tma_kernel(const StepDev s) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double *sprev[kMaxShards];
+    double *smem2 = reinterpret_cast<double *>(smem_raw);                                   // NW2 phase-2 stages
+    unsigned char *smem1 = smem_raw + (size_t) NW2 * kStageDoubles * sizeof(double);        // NS1 phase-1 stages
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem1 + (size_t) NS1 * P1STAGE);   // full[NS1], empty[NS1]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < kMaxShards) sprev[threadIdx.x] = s.prev.base[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS1; i++) { mbar_init(smem_u32(bars + i), 1); mbar_init(smem_u32(bars + NS1 + i), NC1 / NS1); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const RowLookup prev{ sprev, s.prev.base[0], s.prev.n > 1 ? s.prev.row0[1] : 1, s.prev.n, s.ld_prev };
+    const unsigned long long pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+    const long long n1_cta = s.total1 > blockIdx.x ? (s.total1 - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == NW2 + NC1) {
+        // ============================ phase-1 producer (TMA) ====================================
+        for (long long k = 0; k < n1_cta; k++) {
+            const long long idx = blockIdx.x + k * gridDim.x;
+            const int panel = s.panel_begin + (int) (idx / s.n1pp), rem = (int) (idx % s.n1pp);
+            const int sg = rem / s.ncb256, cb = rem - sg * s.ncb256;
+            const int w = min(C1, s.Kpad_prev - cb * C1);                 // columns of this block (multiple of 32)
+            const int stage = (int) (k % NS1);
+            const unsigned full = smem_u32(bars + stage), empty = smem_u32(bars + NS1 + stage);
+            const double *src = s.zero_row;
+            if (lane < 2 * S1) {
+                const int cls = panel * T + sg * S1 + (lane & (S1 - 1));
+                const int row = lane < S1 ? s.pF[cls] : s.pM[cls];
+                if (row >= 0) src = prev(row) + (long long) cb * C1;
+            }
+            if (lane == 0) {
+                mbar_wait(empty, (unsigned) (((k / NS1) & 1) ^ 1));        // the consumer is done with this stage
+                mbar_arrive_expect_tx(full, (unsigned) (2 * S1 * w * sizeof(double)));
+            }
+            __syncwarp();
+            if (lane < 2 * S1)
+                bulk_copy(smem_u32(smem1 + (size_t) stage * P1STAGE + (size_t) lane * P1PITCH), src, (unsigned) (w * sizeof(double)), full, pol_stream);
+        }
+    } else if (warp >= NW2) {
+        // ============================ phase-1 consumers =========================================
+        const int i = lane & (S1 - 1), cc = lane >> 3;                    // lane = (class i of the item, column c mod 4)
+        int freed_panel = -1;                    // phase 2 of this panel is known complete (its ring slot is free)
+        // NC1 / NS1 consumer warps serve each stage (a warp only ever waits for the NEXT phase of its
+        // stage's barrier); they split the item's columns between them
+        constexpr int kPer = NC1 / NS1;
+        const int cw = warp - NW2, my_stage = cw / kPer, part = cw % kPer;
+        for (long long k = my_stage; k < n1_cta; k += NS1) {
+            const long long idx = blockIdx.x + k * gridDim.x;
+            const int panel = s.panel_begin + (int) (idx / s.n1pp), rem = (int) (idx % s.n1pp);
+            const int sg = rem / s.ncb256, cb = rem - sg * s.ncb256;
+            const int w = min(C1, s.Kpad_prev - cb * C1);
+            const int stage = (int) (k % NS1);
+            const unsigned full = smem_u32(bars + stage), empty = smem_u32(bars + NS1 + stage);
+            const int old = panel - s.ring_n;    // the ring slot must have been drained by phase 2 of its previous panel
+            if (old >= s.panel_begin && old > freed_panel) {
+                if (lane == 0 && !s.debug_nowait) wait_count(s.done2 + old, s.full_rows ? s.np : old + 1);
+                freed_panel = old;
+                __syncwarp();
+            }
+            mbar_wait(full, (unsigned) ((k / NS1) & 1));
+            const double *rf = reinterpret_cast<const double *>(smem1 + (size_t) stage * P1STAGE + (size_t) i * P1PITCH) + cc;
+            const double *rm = reinterpret_cast<const double *>(smem1 + (size_t) stage * P1STAGE + (size_t) (S1 + i) * P1PITCH) + cc;
+            double *dst = s.ring + (long long) ((panel - s.panel_begin) % s.ring_n) * s.ring_stride +
+                          ((long long) cb * C1 + cc) * T + sg * S1 + i;
+            const int cbeg = part * (w / kPer), cend = cbeg + w / kPer;      // w is a multiple of 32
+#pragma unroll 8
+            for (int c = cbeg; c < cend; c += 4) st_hint(dst + (long long) c * T, 0.5 * (rf[c] + rm[c]), pol_keep);
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(empty); signal_count(s.done1 + panel); }
+        }
+    } else {
+        // ============================ phase-2 warps (LDGSTS) ====================================
+        double *const S = smem2 + (size_t) warp * kStageDoubles;
+        const int half = lane >> 4, l16 = lane & 15;
+        // copy r < 16: father rows of classes r (lanes 0-15) and r + 16 (lanes 16-31); r >= 16: mother rows
+        const unsigned sdst = smem_u32(S) + (unsigned) ((half * 16 * PS + l16 * 2) * sizeof(double));
+        const double2 *sf = reinterpret_cast<const double2 *>(S + lane * PS), *sm = reinterpret_cast<const double2 *>(S + (T + lane) * PS);
+        double *const out = s.out_base;              // own rows of the new matrix: global row r at out + (r - out_row0) * ld_new
+        const long long ldn = s.ld_new;
+        const unsigned long long pol_out = s.out_policy == 0 ? pol_stream : (s.out_policy == 2 ? pol_keep : policy_evict_normal());
+        const long long nw2 = (long long) gridDim.x * NW2;
+        int g = 0, ready_panel = -1;
+        for (long long q = (long long) blockIdx.x * NW2 + warp; q < s.total2; q += nw2) {
+            while (q >= s.grp_off2[g + 1]) ++g;
+            const int I = s.panel_begin + g, J = (int) (q - s.grp_off2[g]);
+            const int myF = s.pF[J * T + lane], myM = s.pM[J * T + lane];
+            const double *buf = s.ring + (long long) ((I - s.panel_begin) % s.ring_n) * s.ring_stride;
+            if (I != ready_panel) {              // phase 1 of panel I must be complete before its rows are read
+                if (lane == 0 && !s.debug_nowait) wait_count(s.done1 + I, s.n1pp * (NC1 / NS1));
+                ready_panel = I;
+                __syncwarp();
+            }
+#pragma unroll 8
+            for (int r = 0; r < T; r++) {
+                const int row = __shfl_sync(0xffffffffu, r < 16 ? myF : myM, (r & 15) + 16 * half);
+                const double *src = row < 0 ? s.zero_row : buf + (long long) row * T + l16 * 2;
+                cp_async16(sdst + (unsigned) (((r & 15) + (r >> 4) * T) * PS * sizeof(double)), src, row >= 0 ? 16u : 0u, pol_keep);
+            }
+            double *drow = out + ((long long) J * T - s.out_row0) * ldn + I * T + lane;    // row j of tile J, columns of panel I
+            double *mrow = out + ((long long) I * T - s.out_row0) * ldn + J * T + lane;    // row i of panel I, columns of tile J
+            cp_async_wait_all();
+            __syncwarp();
+            if (J != I || s.full_rows) {
+                if (!s.full_rows) {
+                    // direct: lane = class i of the panel, row j: B[j][i] = 1/2 (N^T[F_j][i] + N^T[M_j][i])
+#pragma unroll 8
+                    for (int j = 0; j < T; j++)
+                        st_hint(drow + (long long) j * ldn, 0.5 * (S[j * PS + lane] + S[(T + j) * PS + lane]), pol_out);
+                }
+                // mirror: lane = class j of the tile, rows i, i + 1: B[i][j] = the same value
+#pragma unroll 8
+                for (int i2 = 0; i2 < T / 2; i2++) {
+                    const double2 x = sf[i2], y = sm[i2];
+                    st_hint(mrow + (long long) (2 * i2) * ldn, 0.5 * (x.x + y.x), pol_out);
+                    st_hint(mrow + (long long) (2 * i2 + 1) * ldn, 0.5 * (x.y + y.y), pol_out);
+                }
+            } else {
+                // diagonal tile: V[j][i] is valid where j <= i (in RANKED mode that is the reference's
+                // grouping); the other triangle is its mirror.  out[r][lane] = r <= lane ? V[r][lane] : V[lane][r]
+#pragma unroll 4
+                for (int r = 0; r < T; r++) {
+                    const double a = 0.5 * (S[r * PS + lane] + S[(T + r) * PS + lane]);          // V[r][lane]
+                    const double b = 0.5 * (S[lane * PS + r] + S[(T + lane) * PS + r]);          // V[lane][r]
+                    st_hint(mrow + (long long) r * ldn, r <= lane ? a : b, pol_out);
+                }
+            }
+            __syncwarp();                                    // every lane is done reading the stage (and has issued its stores)
+            if (lane == 0) signal_count(s.done2 + I);
+        }
     }
 }
 
@@ -437,6 +631,7 @@ cudaError_t configure_kernels() {
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev))) return e;
     if ((e = cudaFuncSetAttribute(phi_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kStepSmem))) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phi_step_kernel, kThreads, kStepSmem))) return e;
+    if ((e = cudaFuncSetAttribute(phi_step_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kStepSmemTma))) return e;
     const char *env = getenv("GK_CTAS_PER_SM");
     if (env && atoi(env) > 0 && atoi(env) < occ) occ = atoi(env);
     g_step_grid = sms * (occ > 0 ? occ : 1);     // persistent: one wave, every CTA resident (the waits rely on it)
@@ -449,6 +644,13 @@ cudaError_t launch_step(const StepDev &s, cudaStream_t st) {
     const long long need = (s.total_items + kWarps - 1) / kWarps;
     if (grid > need) grid = need;
     phi_step_kernel<<<(unsigned) grid, kThreads, kStepSmem, st>>>(s);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step_tma(const StepDev &s, cudaStream_t st) {
+    if (s.total1 + s.total2 <= 0) return cudaSuccess;
+    const long long grid = g_step_grid > 0 ? g_step_grid : 148;
+    phi_step_tma_kernel<<<(unsigned) grid, kThreadsTma, kStepSmemTma, st>>>(s);
     return cudaGetLastError();
 }
 

@@ -8,6 +8,11 @@ namespace gk {
 constexpr int kMaxShards = 8;     // GPUs of one box
 constexpr int kRingMax = 40;      // L2-resident panel buffers (transposed N panels), at most
 constexpr int kStepWarps = 12;     // warps per CTA of the step kernel (one CTA per SM), each with a private 17 KB stage
+constexpr int kStepP2Warps = 7;      // multi-GPU step kernel (phi_step_tma_kernel): phase-2 warps (LDGSTS)
+constexpr int kStepP1Consumers = 6;  // phase-1 consumer warps
+constexpr int kStepP1Stages = 3;     // phase-1 TMA stages (33 KB each)
+constexpr int kP1Classes = 8;        // phase-1 item: 8 classes of a panel ...
+constexpr int kP1Cols = 256;         // ... x 256 columns of the previous matrix (2 KB row segments)
 constexpr int kCB = 32;           // columns of the previous matrix per phase-1 work item
 
 // Where the rows of a (possibly row-sharded) class matrix live: row r is owned by the shard q with
@@ -28,11 +33,16 @@ struct StepDev {
     int32_t Kpad_prev;
     int32_t np;               // panels / tiles of the new cut (global)
     const int32_t *pF, *pM;   // Kpad: parent rows of every new class in the previous matrix (-1 none)
-    const double *zero_row;   // >= 32 zeros (the parent row of a class with an unknown parent)
+    const double *zero_row;   // >= 256 zeros (the parent row of a class with an unknown parent)
     double *ring;             // ring_n x ring_stride doubles: N^T panels, [Kpad_prev][32]
     int64_t ring_stride;
     int32_t ring_n;
     int32_t *done1, *done2;   // np counters each: finished phase-1 / phase-2 items of a panel
+    // phi_step_tma_kernel only: two item streams instead of one queue
+    const int64_t *grp_off2;  // own panels + 1: first phase-2 item of each own panel
+    int64_t total1, total2;   // phase-1 / phase-2 items of this launch
+    int32_t n1pp;             // phase-1 items per panel = 4 * ncb256
+    int32_t ncb256;           // 256-column blocks of the previous matrix
     const int64_t *grp_off;   // ngroups + 1: first work item of each group
     const int32_t *grp_info;  // ngroups: panel | (phase - 1) << 30
     int64_t total_items;
@@ -73,6 +83,7 @@ struct ExpandDev {
 
 int step_grid();             // CTAs of the persistent step kernel (SMs x resident CTAs)
 cudaError_t launch_step(const StepDev &s, cudaStream_t st);
+cudaError_t launch_step_tma(const StepDev &s, cudaStream_t st);
 cudaError_t launch_diag(const DiagDev &d, cudaStream_t st);
 cudaError_t launch_init(double *G0, double *d0, const int32_t *flags, int64_t K0, int64_t Kpad0, cudaStream_t st);
 cudaError_t launch_init_rows(double *G0, double *d0, const int32_t *flags, int64_t K0, int64_t Kpad0,
