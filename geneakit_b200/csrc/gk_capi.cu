@@ -32,6 +32,7 @@ int cuda_fail(cudaError_t e, const char *what) {
     } while (0)
 
 struct StepOffsets {
+    size_t prow = 0, pcnt = 0, slots = 0;
     size_t pF = 0, pM = 0, flags = 0, pg_i = 0, pg_j = 0, pg_off = 0, pt_cls = 0, pt_mult = 0, grp_off = 0, grp_info = 0;
     size_t done = 0;              // offset into the counter arena: done1 at +0, done2 at +np
     int32_t ngroups = 0, npatch = 0;
@@ -333,6 +334,7 @@ int gk_phi_upload(gk_phi_job *j) {
         gk::StepPlan &S = P.steps[g];
         StepOffsets &o = j->off[g];
         o.pF = push(S.pF); o.pM = push(S.pM); o.flags = push(S.flags);
+        o.prow = push(S.prow); o.pcnt = push(S.pcnt); o.slots = push(S.slots);
         o.pg_i = push(S.pg_i); o.pg_j = push(S.pg_j); o.pg_off = push(S.pg_off);
         o.pt_cls = push(S.pt_cls); o.pt_mult = push(S.pt_mult);
         o.npatch = (int32_t) S.pg_i.size();
@@ -560,6 +562,7 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     d.ld_prev = S.Kpad_prev; d.ld_new = S.Kpad;
     d.Kpad_prev = (int32_t) S.Kpad_prev; d.np = S.np;
     d.pF = j->ints + o.pF; d.pM = j->ints + o.pM;
+    d.prow = j->ints + o.prow; d.pcnt = j->ints + o.pcnt; d.slots = j->ints + o.slots;
     d.zero_row = j->zero_row;
     d.ring = j->ring; d.ring_stride = S.Kpad_prev * gk::kPanel; d.ring_n = o.ring_n;
     d.done1 = j->counters + o.done; d.done2 = d.done1 + S.np;

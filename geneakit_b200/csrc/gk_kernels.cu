@@ -39,7 +39,7 @@ constexpr int kWarps = kStepWarps;        // 3 per SM sub-partition, one CTA per
 constexpr int kThreads = kWarps * 32;
 constexpr int T = kPanel;                 // 32
 constexpr int PS = T + 2;                 // staging pitch (doubles): 16-byte aligned rows, conflict-free 128-bit transposed reads
-constexpr int kStageDoubles = 2 * T * PS; // 64 staged rows per warp: slot i = father row of class i, slot 32 + i = mother row
+constexpr int kStageDoubles = (2 * T + 1) * PS; // up to 64 distinct parent rows of a panel per warp + one all-zero row (slot 64: unknown parent)
 constexpr size_t kStepSmem = (size_t) kWarps * kStageDoubles * sizeof(double);
 
 // ---- second step kernel (multi-GPU): phase 1 through the TMA engine ---------------------------------
@@ -146,7 +146,10 @@ struct RowLookup {
 // behind the dependency waits; issuing the next item's copies before publishing the current one
 // delays the release fence by a full memory latency.)
 struct StepItem {
-    int info, local, myF, myM;
+    int info, local;
+    int r0, r1;      // lane l: distinct parent rows l and 32 + l of the item's panel (-1 past the end)
+    int n;           // how many distinct rows
+    int slots;       // lane = class: slot of its father row | slot of its mother row << 8
 };
 
 __global__ void __launch_bounds__(kThreads, 1) phi_step_kernel(const StepDev s) {
@@ -154,15 +157,15 @@ __global__ void __launch_bounds__(kThreads, 1) phi_step_kernel(const StepDev s) 
     __shared__ double *sprev[kMaxShards];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < kMaxShards) sprev[threadIdx.x] = s.prev.base[threadIdx.x];
+    double *const S = smem + (size_t) warp * kStageDoubles;
+    for (int i = lane; i < PS; i += 32) S[kZeroSlot * PS + i] = 0.0;       // the zero row is never overwritten
     __syncthreads();
     const RowLookup prev{ sprev, s.prev.base[0], s.prev.n > 1 ? s.prev.row0[1] : 1, s.prev.n, s.ld_prev };
     const unsigned long long pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
     const unsigned long long pol_out = s.out_policy == 0 ? pol_stream : (s.out_policy == 2 ? pol_keep : policy_evict_normal());
-    double *const S = smem + (size_t) warp * kStageDoubles;
     const int half = lane >> 4, l16 = lane & 15;
-    // copy r < 16: father rows of classes r (lanes 0-15) and r + 16 (lanes 16-31); r >= 16: mother rows
-    const unsigned sdst = smem_u32(S) + (unsigned) ((half * 16 * PS + l16 * 2) * sizeof(double));
-    const double2 *sf = reinterpret_cast<const double2 *>(S + lane * PS), *sm = reinterpret_cast<const double2 *>(S + (T + lane) * PS);
+    // copy r: distinct rows 2r (lanes 0-15) and 2r + 1 (lanes 16-31) of the panel -> slots 2r, 2r + 1
+    const unsigned sdst = smem_u32(S) + (unsigned) ((half * PS + l16 * 2) * sizeof(double));
     double *const out = s.out_base;              // own rows of the new matrix: global row r at out + (r - out_row0) * ld_new
     const long long ldn = s.ld_new;
     const long long nw = (long long) gridDim.x * kWarps;
@@ -170,53 +173,42 @@ __global__ void __launch_bounds__(kThreads, 1) phi_step_kernel(const StepDev s) 
     int ready_panel = -1;        // phase 1 of this panel is known complete
     int freed_panel = -1;        // phase 2 of this panel is known complete (its ring slot is free)
 
-    auto decode = [&](long long q, StepItem &it) {
-        while (q >= s.grp_off[g + 1]) ++g;
-        it.info = s.grp_info[g];
-        it.local = (int) (q - s.grp_off[g]);
-        const int cls = ((it.info >> 30) == 0 ? (it.info & 0x3FFFFFFF) : it.local) * T + lane;
-        it.myF = s.pF[cls]; it.myM = s.pM[cls];
-    };
-    // phase 2 reads the panel: phase 1 of panel I must be complete.  `pending` = a finished item of this
-    // warp that has not been published yet: it is published BEFORE blocking (the counter we wait for may
-    // be waiting for it).
-    auto depend = [&](const StepItem &it, int *pending) -> bool {
-        const int I = it.info & 0x3FFFFFFF;
-        if ((it.info >> 30) == 0 || I == ready_panel || s.debug_nowait) return false;
-        bool published = false;
-        int ok = lane == 0 ? (ld_relaxed(s.done1 + I) >= s.ncb) : 0;
-        ok = __shfl_sync(0xffffffffu, ok, 0);
-        if (!ok) {
-            if (pending) { if (lane == 0) signal_count(pending); published = true; }
-            if (lane == 0) wait_count(s.done1 + I, s.ncb);
-            __syncwarp();
-        }
-        ready_panel = I;
-        return published;
-    };
-    auto issue = [&](const StepItem &it) {
-        const int I = it.info & 0x3FFFFFFF;
-        const bool p1 = (it.info >> 30) == 0;
-        const double *buf = s.ring + (long long) ((I - s.panel_begin) % s.ring_n) * s.ring_stride;
-        const unsigned long long pol = p1 ? pol_stream : pol_keep;
-        const long long coff = p1 ? (long long) it.local * T + l16 * 2 : (long long) l16 * 2;
-#pragma unroll 8
-        for (int r = 0; r < T; r++) {
-            const int row = __shfl_sync(0xffffffffu, r < 16 ? it.myF : it.myM, (r & 15) + 16 * half);
-            const double *src = row < 0 ? s.zero_row : (p1 ? prev(row) : buf + (long long) row * T) + coff;
-            cp_async16(sdst + (unsigned) (((r & 15) + (r >> 4) * T) * PS * sizeof(double)), src, row >= 0 ? 16u : 0u, pol);
-        }
-    };
-
     StepItem cur;
     for (long long q = (long long) blockIdx.x * kWarps + warp; q < s.total_items; q += nw) {
-        decode(q, cur);
-        depend(cur, nullptr);
-        issue(cur);
+        // ---- decode: group -> (phase, panel), position in the group, the panel's distinct parent rows ----
+        while (q >= s.grp_off[g + 1]) ++g;
+        cur.info = s.grp_info[g];
+        cur.local = (int) (q - s.grp_off[g]);
         const int I = cur.info & 0x3FFFFFFF, local = cur.local;
+        const bool p1 = (cur.info >> 30) == 0;
+        const int P = p1 ? I : local;                        // the panel / tile whose parent rows are staged
+        cur.r0 = s.prow[P * 2 * T + lane]; cur.r1 = s.prow[P * 2 * T + T + lane];
+        cur.n = s.pcnt[P];
+        cur.slots = s.slots[P * T + lane];
         double *buf = s.ring + (long long) ((I - s.panel_begin) % s.ring_n) * s.ring_stride;
+        if (!p1 && I != ready_panel) {          // phase 1 of panel I must be complete before its rows are read
+            if (lane == 0 && !s.debug_nowait) wait_count(s.done1 + I, s.ncb);
+            ready_panel = I;
+            __syncwarp();
+        }
+        // ---- stage the distinct rows: 32 columns of rows of the previous matrix (phase 1) or whole rows
+        //      of the L2-resident panel (phase 2), two rows per instruction --------------------------------
+        {
+            const unsigned long long pol = p1 ? pol_stream : pol_keep;
+            const long long coff = p1 ? (long long) local * T + l16 * 2 : (long long) l16 * 2;
+            const int nops = (cur.n + 1) >> 1;
+#pragma unroll 4
+            for (int r = 0; r < nops; r++) {
+                const int row = __shfl_sync(0xffffffffu, r < 16 ? cur.r0 : cur.r1, (2 * r + half) & 31);
+                const double *src = row < 0 ? s.zero_row : (p1 ? prev(row) : buf + (long long) row * T) + coff;
+                cp_async16(sdst + (unsigned) (2 * r * PS * sizeof(double)), src, row >= 0 ? 16u : 0u, pol);
+            }
+        }
+        // lane = class: its father / mother rows as 128-bit columns pairs
+        const double2 *sf = reinterpret_cast<const double2 *>(S + (cur.slots & 0xFF) * PS);
+        const double2 *sm = reinterpret_cast<const double2 *>(S + ((cur.slots >> 8) & 0xFF) * PS);
         int *done;
-        if ((cur.info >> 30) == 0) {
+        if (p1) {
             // -------- phase 1: N^T[c][i], c in [c0, c0 + 32): lane = class i, two columns per 128-bit read
             const int old = I - s.ring_n;    // the ring slot must have been drained by phase 2 of its previous panel
             if (old >= s.panel_begin && old > freed_panel) {
@@ -244,8 +236,10 @@ __global__ void __launch_bounds__(kThreads, 1) phi_step_kernel(const StepDev s) 
                 if (!s.full_rows) {
                     // direct: lane = class i of the panel, row j: B[j][i] = 1/2 (N^T[F_j][i] + N^T[M_j][i])
 #pragma unroll 8
-                    for (int j = 0; j < T; j++)
-                        st_hint(drow + (long long) j * ldn, 0.5 * (S[j * PS + lane] + S[(T + j) * PS + lane]), pol_out);
+                    for (int j = 0; j < T; j++) {
+                        const int sl = __shfl_sync(0xffffffffu, cur.slots, j);
+                        st_hint(drow + (long long) j * ldn, 0.5 * (S[(sl & 0xFF) * PS + lane] + S[((sl >> 8) & 0xFF) * PS + lane]), pol_out);
+                    }
                 }
                 // mirror: lane = class j of the tile, rows i, i + 1: B[i][j] = the same value
 #pragma unroll 8
@@ -257,10 +251,12 @@ __global__ void __launch_bounds__(kThreads, 1) phi_step_kernel(const StepDev s) 
             } else {
                 // diagonal tile: V[j][i] is valid where j <= i (in RANKED mode that is the reference's
                 // grouping); the other triangle is its mirror.  out[r][lane] = r <= lane ? V[r][lane] : V[lane][r]
+                const double *sfl = reinterpret_cast<const double *>(sf), *sml = reinterpret_cast<const double *>(sm);
 #pragma unroll 4
                 for (int r = 0; r < T; r++) {
-                    const double a = 0.5 * (S[r * PS + lane] + S[(T + r) * PS + lane]);          // V[r][lane]
-                    const double b = 0.5 * (S[lane * PS + r] + S[(T + lane) * PS + r]);          // V[lane][r]
+                    const int sl = __shfl_sync(0xffffffffu, cur.slots, r);
+                    const double a = 0.5 * (S[(sl & 0xFF) * PS + lane] + S[((sl >> 8) & 0xFF) * PS + lane]);   // V[r][lane]
+                    const double b = 0.5 * (sfl[r] + sml[r]);                                                    // V[lane][r]
                     st_hint(mrow + (long long) r * ldn, r <= lane ? a : b, pol_out);
                 }
             }

@@ -33,6 +33,7 @@ struct StepDev {
     int32_t Kpad_prev;
     int32_t np;               // panels / tiles of the new cut (global)
     const int32_t *pF, *pM;   // Kpad: parent rows of every new class in the previous matrix (-1 none)
+    const int32_t *prow, *pcnt, *slots;   // per panel: its distinct parent rows (64 slots), their count; per class: father / mother slot
     const double *zero_row;   // >= 256 zeros (the parent row of a class with an unknown parent)
     double *ring;             // ring_n x ring_stride doubles: N^T panels, [Kpad_prev][32]
     int64_t ring_stride;

@@ -46,6 +46,7 @@ constexpr int kPanel = 32;          // classes per panel / tile
 constexpr int kFlagSingleton = 1;   // class has exactly one member: its diagonal holds the self kinship
 constexpr int kFlagKept = 2;        // member kept from the previous cut (both "parents" = its own old row)
 constexpr int kFlagBoth = 4;        // new class with both parents known
+constexpr int kZeroSlot = 2 * kPanel;   // staged row 64 = zeros
 
 struct StepPlan {
     int64_t K = 0, Kpad = 0, K_prev = 0, Kpad_prev = 0;
@@ -57,6 +58,10 @@ struct StepPlan {
     int64_t kept_cls = 0;      // singleton classes of kept individuals
     int64_t panel_rows = 0;    // sum over panels of the distinct parent rows the panel reads
     std::vector<int32_t> pF, pM;       // Kpad: parent class rows in matrix g-1, -1 = none (padding: -1, -1)
+    // de-duplicated parent rows per panel: prow[64 p + s] = s-th distinct parent row of panel p (-1 past the
+    // end), pcnt[p] = how many; slots[i] = slot of class i's father row | slot of its mother row << 8
+    // (kZeroSlot = unknown parent: an all-zero staged row)
+    std::vector<int32_t> prow, pcnt, slots;
     std::vector<int32_t> flags;        // Kpad
     std::vector<int32_t> cls_ind;      // K: lowest-ranked member (= the individual, uncompressed)
     std::vector<int32_t> cls_size;     // K: members
@@ -349,15 +354,26 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
             // ---- traffic statistics: distinct parent rows overall and per panel ----------------
             prow_stamp.assign((size_t) S.K_prev, -1);
             prow_panel.assign((size_t) S.K_prev, -1);
+            std::vector<int32_t> slot_of((size_t) S.K_prev, 0);
+            S.prow.assign((size_t) S.np * 2 * kPanel, -1);
+            S.pcnt.assign((size_t) S.np, 0);
+            S.slots.assign((size_t) S.Kpad, kZeroSlot | (kZeroSlot << 8));
             int64_t pcls = 0, prow = 0;
             for (int64_t pos = 0; pos < K; pos++) {
                 const int32_t panel = (int32_t) (pos / kPanel);
+                int32_t sl[2] = { kZeroSlot, kZeroSlot };
                 for (int q = 0; q < 2; q++) {
                     const int32_t pc = q ? S.pM[pos] : S.pF[pos];
                     if (pc < 0) continue;
                     if (prow_stamp[pc] != g) { prow_stamp[pc] = g; pcls++; }
-                    if (prow_panel[pc] != panel) { prow_panel[pc] = panel; prow++; }
+                    if (prow_panel[pc] != panel) {
+                        prow_panel[pc] = panel; prow++;
+                        slot_of[pc] = S.pcnt[panel]++;
+                        S.prow[(size_t) panel * 2 * kPanel + slot_of[pc]] = pc;
+                    }
+                    sl[q] = slot_of[pc];
                 }
+                S.slots[pos] = sl[0] | (sl[1] << 8);
             }
             S.P_cls = pcls; S.panel_rows = prow;
 
