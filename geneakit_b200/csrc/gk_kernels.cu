@@ -51,7 +51,7 @@ constexpr int kThreadsTma = (NW2 + NC1 + 1) * 32;   // + the phase-1 producer wa
 constexpr int S1 = kP1Classes;            // phase 1: classes per item (8)
 constexpr int C1 = kP1Cols;               // phase 1: columns per item (256): 2 KB row segments, the size the TMA engine needs
 constexpr int P1PITCH = C1 * 8 + 16;      // bytes between staged rows: 516 words = 4 mod 32 -> conflict-free (class, column) reads
-constexpr int P1STAGE = 2 * S1 * P1PITCH; // 16 rows: slot i = father row of class i, slot 8 + i = mother row
+constexpr int P1STAGE = (2 * S1 + 1) * P1PITCH; // up to 16 distinct parent rows of the 8 classes + one all-zero row (slot 16)
 constexpr size_t kStepSmemTma = (size_t) NW2 * kStageDoubles * sizeof(double) + (size_t) NS1 * P1STAGE + 2 * NS1 * sizeof(unsigned long long);
 
 __device__ __forceinline__ int ld_relaxed(const int *p) {
@@ -301,6 +301,10 @@ __global__ void __launch_bounds__(kThreadsTma, 1) phi_step_tma_kernel(const Step
         for (int i = 0; i < NS1; i++) { mbar_init(smem_u32(bars + i), 1); mbar_init(smem_u32(bars + NS1 + i), NC1 / NS1); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    // the all-zero rows (unknown parent) of every stage are never overwritten
+    for (int i = threadIdx.x; i < NS1 * (P1PITCH / 8); i += blockDim.x)
+        reinterpret_cast<double *>(smem1 + (size_t) (i / (P1PITCH / 8)) * P1STAGE + (size_t) kZeroSlot8 * P1PITCH)[i % (P1PITCH / 8)] = 0.0;
+    for (int i = threadIdx.x; i < NW2 * PS; i += blockDim.x) smem2[(size_t) (i / PS) * kStageDoubles + kZeroSlot * PS + i % PS] = 0.0;
     __syncthreads();
     const RowLookup prev{ sprev, s.prev.base[0], s.prev.n > 1 ? s.prev.row0[1] : 1, s.prev.n, s.ld_prev };
     const unsigned long long pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
@@ -315,19 +319,17 @@ __global__ void __launch_bounds__(kThreadsTma, 1) phi_step_tma_kernel(const Step
             const int w = min(C1, s.Kpad_prev - cb * C1);                 // columns of this block (multiple of 32)
             const int stage = (int) (k % NS1);
             const unsigned full = smem_u32(bars + stage), empty = smem_u32(bars + NS1 + stage);
-            const double *src = s.zero_row;
-            if (lane < 2 * S1) {
-                const int cls = panel * T + sg * S1 + (lane & (S1 - 1));
-                const int row = lane < S1 ? s.pF[cls] : s.pM[cls];
-                if (row >= 0) src = prev(row) + (long long) cb * C1;
-            }
+            const int sub = panel * (T / S1) + sg;
+            const int n = s.pcnt8[sub];                                   // distinct parent rows of the 8 classes
+            const int row = lane < 2 * S1 ? s.prow8[sub * 2 * S1 + lane] : -1;
             if (lane == 0) {
-                mbar_wait(empty, (unsigned) (((k / NS1) & 1) ^ 1));        // the consumer is done with this stage
-                mbar_arrive_expect_tx(full, (unsigned) (2 * S1 * w * sizeof(double)));
+                mbar_wait(empty, (unsigned) (((k / NS1) & 1) ^ 1));        // the consumers are done with this stage
+                mbar_arrive_expect_tx(full, (unsigned) (n * w * sizeof(double)));
             }
             __syncwarp();
-            if (lane < 2 * S1)
-                bulk_copy(smem_u32(smem1 + (size_t) stage * P1STAGE + (size_t) lane * P1PITCH), src, (unsigned) (w * sizeof(double)), full, pol_stream);
+            if (lane < n)
+                bulk_copy(smem_u32(smem1 + (size_t) stage * P1STAGE + (size_t) lane * P1PITCH), prev(row) + (long long) cb * C1,
+                          (unsigned) (w * sizeof(double)), full, pol_stream);
         }
     } else if (warp >= NW2) {
         // ============================ phase-1 consumers =========================================
@@ -351,8 +353,9 @@ __global__ void __launch_bounds__(kThreadsTma, 1) phi_step_tma_kernel(const Step
                 __syncwarp();
             }
             mbar_wait(full, (unsigned) ((k / NS1) & 1));
-            const double *rf = reinterpret_cast<const double *>(smem1 + (size_t) stage * P1STAGE + (size_t) i * P1PITCH) + cc;
-            const double *rm = reinterpret_cast<const double *>(smem1 + (size_t) stage * P1STAGE + (size_t) (S1 + i) * P1PITCH) + cc;
+            const int sl = s.slots8[panel * T + sg * S1 + i];
+            const double *rf = reinterpret_cast<const double *>(smem1 + (size_t) stage * P1STAGE + (size_t) (sl & 0xFF) * P1PITCH) + cc;
+            const double *rm = reinterpret_cast<const double *>(smem1 + (size_t) stage * P1STAGE + (size_t) ((sl >> 8) & 0xFF) * P1PITCH) + cc;
             double *dst = s.ring + (long long) ((panel - s.panel_begin) % s.ring_n) * s.ring_stride +
                           ((long long) cb * C1 + cc) * T + sg * S1 + i;
             const int cbeg = part * (w / kPer), cend = cbeg + w / kPer;      // w is a multiple of 32
@@ -365,9 +368,8 @@ __global__ void __launch_bounds__(kThreadsTma, 1) phi_step_tma_kernel(const Step
         // ============================ phase-2 warps (LDGSTS) ====================================
         double *const S = smem2 + (size_t) warp * kStageDoubles;
         const int half = lane >> 4, l16 = lane & 15;
-        // copy r < 16: father rows of classes r (lanes 0-15) and r + 16 (lanes 16-31); r >= 16: mother rows
-        const unsigned sdst = smem_u32(S) + (unsigned) ((half * 16 * PS + l16 * 2) * sizeof(double));
-        const double2 *sf = reinterpret_cast<const double2 *>(S + lane * PS), *sm = reinterpret_cast<const double2 *>(S + (T + lane) * PS);
+        // copy r: distinct rows 2r (lanes 0-15) and 2r + 1 (lanes 16-31) of the tile -> slots 2r, 2r + 1
+        const unsigned sdst = smem_u32(S) + (unsigned) ((half * PS + l16 * 2) * sizeof(double));
         double *const out = s.out_base;              // own rows of the new matrix: global row r at out + (r - out_row0) * ld_new
         const long long ldn = s.ld_new;
         const unsigned long long pol_out = s.out_policy == 0 ? pol_stream : (s.out_policy == 2 ? pol_keep : policy_evict_normal());
@@ -376,31 +378,35 @@ __global__ void __launch_bounds__(kThreadsTma, 1) phi_step_tma_kernel(const Step
         for (long long q = (long long) blockIdx.x * NW2 + warp; q < s.total2; q += nw2) {
             while (q >= s.grp_off2[g + 1]) ++g;
             const int I = s.panel_begin + g, J = (int) (q - s.grp_off2[g]);
-            const int myF = s.pF[J * T + lane], myM = s.pM[J * T + lane];
+            const int r0 = s.prow[J * 2 * T + lane], r1 = s.prow[J * 2 * T + T + lane], n = s.pcnt[J];
+            const int slots = s.slots[J * T + lane];
             const double *buf = s.ring + (long long) ((I - s.panel_begin) % s.ring_n) * s.ring_stride;
             if (I != ready_panel) {              // phase 1 of panel I must be complete before its rows are read
                 if (lane == 0 && !s.debug_nowait) wait_count(s.done1 + I, s.n1pp * (NC1 / NS1));
                 ready_panel = I;
                 __syncwarp();
             }
-#pragma unroll 8
-            for (int r = 0; r < T; r++) {
-                const int row = __shfl_sync(0xffffffffu, r < 16 ? myF : myM, (r & 15) + 16 * half);
+            const int nops = (n + 1) >> 1;
+#pragma unroll 4
+            for (int r = 0; r < nops; r++) {
+                const int row = __shfl_sync(0xffffffffu, r < 16 ? r0 : r1, (2 * r + half) & 31);
                 const double *src = row < 0 ? s.zero_row : buf + (long long) row * T + l16 * 2;
-                cp_async16(sdst + (unsigned) (((r & 15) + (r >> 4) * T) * PS * sizeof(double)), src, row >= 0 ? 16u : 0u, pol_keep);
+                cp_async16(sdst + (unsigned) (2 * r * PS * sizeof(double)), src, row >= 0 ? 16u : 0u, pol_keep);
             }
+            const double2 *sf = reinterpret_cast<const double2 *>(S + (slots & 0xFF) * PS);
+            const double2 *sm = reinterpret_cast<const double2 *>(S + ((slots >> 8) & 0xFF) * PS);
             double *drow = out + ((long long) J * T - s.out_row0) * ldn + I * T + lane;    // row j of tile J, columns of panel I
             double *mrow = out + ((long long) I * T - s.out_row0) * ldn + J * T + lane;    // row i of panel I, columns of tile J
             cp_async_wait_all();
             __syncwarp();
             if (J != I || s.full_rows) {
                 if (!s.full_rows) {
-                    // direct: lane = class i of the panel, row j: B[j][i] = 1/2 (N^T[F_j][i] + N^T[M_j][i])
 #pragma unroll 8
-                    for (int j = 0; j < T; j++)
-                        st_hint(drow + (long long) j * ldn, 0.5 * (S[j * PS + lane] + S[(T + j) * PS + lane]), pol_out);
+                    for (int j = 0; j < T; j++) {
+                        const int sl = __shfl_sync(0xffffffffu, slots, j);
+                        st_hint(drow + (long long) j * ldn, 0.5 * (S[(sl & 0xFF) * PS + lane] + S[((sl >> 8) & 0xFF) * PS + lane]), pol_out);
+                    }
                 }
-                // mirror: lane = class j of the tile, rows i, i + 1: B[i][j] = the same value
 #pragma unroll 8
                 for (int i2 = 0; i2 < T / 2; i2++) {
                     const double2 x = sf[i2], y = sm[i2];
@@ -408,12 +414,12 @@ __global__ void __launch_bounds__(kThreadsTma, 1) phi_step_tma_kernel(const Step
                     st_hint(mrow + (long long) (2 * i2 + 1) * ldn, 0.5 * (x.y + y.y), pol_out);
                 }
             } else {
-                // diagonal tile: V[j][i] is valid where j <= i (in RANKED mode that is the reference's
-                // grouping); the other triangle is its mirror.  out[r][lane] = r <= lane ? V[r][lane] : V[lane][r]
+                const double *sfl = reinterpret_cast<const double *>(sf), *sml = reinterpret_cast<const double *>(sm);
 #pragma unroll 4
                 for (int r = 0; r < T; r++) {
-                    const double a = 0.5 * (S[r * PS + lane] + S[(T + r) * PS + lane]);          // V[r][lane]
-                    const double b = 0.5 * (S[lane * PS + r] + S[(T + lane) * PS + r]);          // V[lane][r]
+                    const int sl = __shfl_sync(0xffffffffu, slots, r);
+                    const double a = 0.5 * (S[(sl & 0xFF) * PS + lane] + S[((sl >> 8) & 0xFF) * PS + lane]);   // V[r][lane]
+                    const double b = 0.5 * (sfl[r] + sml[r]);                                                    // V[lane][r]
                     st_hint(mrow + (long long) r * ldn, r <= lane ? a : b, pol_out);
                 }
             }

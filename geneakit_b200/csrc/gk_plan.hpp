@@ -47,6 +47,8 @@ constexpr int kFlagSingleton = 1;   // class has exactly one member: its diagona
 constexpr int kFlagKept = 2;        // member kept from the previous cut (both "parents" = its own old row)
 constexpr int kFlagBoth = 4;        // new class with both parents known
 constexpr int kZeroSlot = 2 * kPanel;   // staged row 64 = zeros
+constexpr int kSub = 8;                 // classes per sub-panel
+constexpr int kZeroSlot8 = 2 * kSub;    // staged row 16 = zeros
 
 struct StepPlan {
     int64_t K = 0, Kpad = 0, K_prev = 0, Kpad_prev = 0;
@@ -62,6 +64,10 @@ struct StepPlan {
     // end), pcnt[p] = how many; slots[i] = slot of class i's father row | slot of its mother row << 8
     // (kZeroSlot = unknown parent: an all-zero staged row)
     std::vector<int32_t> prow, pcnt, slots;
+    // the same per SUB-PANEL of 8 classes (the TMA phase-1 items of the multi-GPU kernel): 16 slots each,
+    // kZeroSlot8 = unknown parent
+    std::vector<int32_t> prow8, pcnt8, slots8;
+    int64_t sub_rows = 0;      // sum over sub-panels of their distinct parent rows
     std::vector<int32_t> flags;        // Kpad
     std::vector<int32_t> cls_ind;      // K: lowest-ranked member (= the individual, uncompressed)
     std::vector<int32_t> cls_size;     // K: members
@@ -376,6 +382,28 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
                 S.slots[pos] = sl[0] | (sl[1] << 8);
             }
             S.P_cls = pcls; S.panel_rows = prow;
+            {   // sub-panels of 8 classes
+                const int64_t nsub = S.Kpad / kSub;
+                S.prow8.assign((size_t) nsub * 2 * kSub, -1);
+                S.pcnt8.assign((size_t) nsub, 0);
+                S.slots8.assign((size_t) S.Kpad, kZeroSlot8 | (kZeroSlot8 << 8));
+                std::fill(prow_panel.begin(), prow_panel.end(), -1);
+                for (int64_t pos = 0; pos < K; pos++) {
+                    const int32_t sub = (int32_t) (pos / kSub);
+                    int32_t sl[2] = { kZeroSlot8, kZeroSlot8 };
+                    for (int q = 0; q < 2; q++) {
+                        const int32_t pc = q ? S.pM[pos] : S.pF[pos];
+                        if (pc < 0) continue;
+                        if (prow_panel[pc] != sub) {
+                            prow_panel[pc] = sub; S.sub_rows++;
+                            slot_of[pc] = S.pcnt8[sub]++;
+                            S.prow8[(size_t) sub * 2 * kSub + slot_of[pc]] = pc;
+                        }
+                        sl[q] = slot_of[pc];
+                    }
+                    S.slots8[pos] = sl[0] | (sl[1] << 8);
+                }
+            }
 
             // ---- corrections: class pairs that share a parent INDIVIDUAL whose class has several members
             uses.clear(); terms.clear();
