@@ -180,3 +180,19 @@ class VirtualShardedPhi:
     def close(self):
         for j in self.jobs:
             j.close()
+
+
+def shard_ancestors(n_anc, rank, world):
+    """gen.gc shards by ANCESTOR COLUMN with no exchange at all (every ancestor's propagation is
+    independent): columns [a0, a1) of the m x a matrix for `rank`."""
+    return n_anc * rank // world, n_anc * (rank + 1) // world
+
+
+def sharded_gc(pedigree, proband_ids, ancestor_ids, rank, world, **gk):
+    """This rank's column block of gen.gc (rows = probands, columns = its slice of the ancestors),
+    computed by the same C-ABI call on the sliced ancestor list."""
+    a0, a1 = shard_ancestors(len(ancestor_ids), rank, world)
+    if a1 <= a0:
+        return np.zeros((len(proband_ids), 0), dtype=np.float64), (a0, a1)
+    block = cgeneakit.compute_genetic_contributions(pedigree, proband_ids, list(ancestor_ids[a0:a1]), **gk)
+    return block, (a0, a1)

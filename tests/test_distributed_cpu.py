@@ -28,7 +28,10 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     try:
         import geneakit_b200 as gk
-        from geneakit_b200.distributed import shard_rows, combine_mean
+        from geneakit_b200.distributed import shard_rows, combine_mean, shard_ancestors
+        cols = [None] * world
+        dist.all_gather_object(cols, shard_ancestors(7399, rank, world))
+        assert cols[0][0] == 0 and cols[-1][1] == 7399 and all(cols[i][1] == cols[i + 1][0] for i in range(world - 1))
         from conftest import load_golden
         from oracle.api import phi_mean
         from plan_emulator import step_view, emulate_step_rows, SINGLETON

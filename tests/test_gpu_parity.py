@@ -168,3 +168,15 @@ def test_sharded_ranks_on_one_gpu_genea140_and_synthetic(oracle):
         v = VirtualShardedPhi(ped, pro, world=world, compress=compress).upload().run()
         assert v.to_host().tobytes() == want.tobytes()
         v.close()
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_gc_sharded_by_ancestor_columns(world):
+    """gen.gc shards by ancestor column with zero exchange: the column blocks of `world` ranks
+    concatenate to the reference fixture."""
+    from geneakit_b200.distributed import sharded_gc
+    g = load_golden("genea140")
+    ped = _ped(g)
+    pro, anc = [int(x) for x in g["pro"]], [int(x) for x in g["anc"]]
+    blocks = [sharded_gc(ped, pro, anc, r, world)[0] for r in range(world)]
+    assert np.concatenate(blocks, axis=1).tobytes() == g["gc"].tobytes()
