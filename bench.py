@@ -240,7 +240,15 @@ def main():
                 "ms_per_launch_avg": step_ms / max(nstep, 1), "share_of_step": step_ms / ms,
                 "expand_ms": t_ms[nstep] if len(t_ms) > nstep else None,
                 "expand_gbs": (b[nstep] / world / (t_ms[nstep] * 1e-3) / 1e9) if len(t_ms) > nstep and t_ms[nstep] > 0 else None}
+    rank_ms = None
+    if dist is not None:
+        # every rank's step-kernel and expansion time of the last pass (imbalance shows up here)
+        mine = torch.tensor([step_ms, t_ms[nstep] if len(t_ms) > nstep else 0.0], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_ms = [[round(float(x[0]), 3), round(float(x[1]), 3)] for x in allr]
     if world > 1:
+        roofline["rank_step_expand_ms"] = rank_ms
         roofline["note"] = "per GPU (rank 0): 1/%d of every cut's algorithmic bytes over this rank's launch time" % world
         roofline["nvlink_bytes_per_pass_rank0"] = int(st["rank_remote_row_bytes"])
         roofline["nvlink_gbs_rank0"] = st["rank_remote_row_bytes"] / (step_ms * 1e-3) / 1e9 if step_ms > 0 else None

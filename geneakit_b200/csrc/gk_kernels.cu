@@ -504,15 +504,23 @@ __global__ void __launch_bounds__(256) fetch_rows_kernel(const RowTable t, long 
 // the row stays in L2) and then streams it, coalesced, to every local result row of that class,
 // patching the "same individual" entries with the self kinship.  Each CTA also emits one
 // (sum, diagonal sum) partial for the mean.
+constexpr int kExpCPT = kExpandCols / 256;     // result columns per thread
+constexpr int kExpMembers = 64;                // result rows of a class whose (row, individual) are staged in shared memory
 __global__ void __launch_bounds__(256) expand_kernel(const ExpandDev e) {
+    __shared__ int mem_i[kExpMembers], mem_u[kExpMembers];
     const int a = blockIdx.x / e.nchunks, chunk = blockIdx.x - a * e.nchunks;
     const int c = e.cact[a];
     const long long j0 = (long long) chunk * kExpandCols + threadIdx.x;
-    double v[4];
-    int uj[4];
+    const int q0 = e.coff[a], nm = e.coff[a + 1] - q0;
+    if (threadIdx.x < nm && threadIdx.x < kExpMembers) {      // independent of the gathers below: both chains overlap
+        const int i = e.cmem[q0 + threadIdx.x];
+        mem_i[threadIdx.x] = i; mem_u[threadIdx.x] = e.ind[i];
+    }
+    double v[kExpCPT];
+    int uj[kExpCPT];
     const double *row = e.G + (long long) (e.compact ? a : c) * e.ld;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < kExpCPT; k++) {
         const long long j = j0 + 256 * k;
         const bool ok = j < e.m;
         uj[k] = ok ? e.ind[j] : -2;
@@ -520,16 +528,17 @@ __global__ void __launch_bounds__(256) expand_kernel(const ExpandDev e) {
     }
     const double dc = e.d[c];
     double sum = 0.0, dsum = 0.0;
-    for (int q = e.coff[a]; q < e.coff[a + 1]; q++) {
-        const long long i = e.cmem[q];
-        const int ui = e.ind[i];
+    __syncthreads();
+    for (int q = 0; q < nm; q++) {
+        long long i; int ui;
+        if (q < kExpMembers) { i = mem_i[q]; ui = mem_u[q]; } else { i = e.cmem[q0 + q]; ui = e.ind[i]; }
         double *orow = e.out + (i - e.row0) * e.m;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < kExpCPT; k++) {
             const long long j = j0 + 256 * k;
             if (j < e.m) {
                 const double val = (uj[k] == ui) ? dc : v[k];
-                orow[j] = val;
+                __stcs(orow + j, val);
                 sum += val;
                 if (i == j) dsum += val;
             }

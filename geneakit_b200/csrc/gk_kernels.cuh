@@ -91,7 +91,7 @@ cudaError_t launch_init(double *G0, double *d0, const int32_t *flags, int64_t K0
 cudaError_t launch_init_rows(double *G0, double *d0, const int32_t *flags, int64_t K0, int64_t Kpad0,
                              int64_t row_begin, int64_t rows, int64_t dlen, cudaStream_t st);
 cudaError_t launch_fetch_rows(const RowTable &t, int64_t ld, const int32_t *rows, int32_t nrows, double *dst, cudaStream_t st);
-constexpr int kExpandCols = 1024;     // result columns per CTA of the expansion kernel
+constexpr int kExpandCols = 2048;     // result columns per CTA of the expansion kernel
 cudaError_t launch_expand(const ExpandDev &e, cudaStream_t st);
 cudaError_t launch_eye(double *out, int64_t m, int64_t row0, int64_t row1, double *partials, cudaStream_t st);
 // two-stage deterministic reduction of the per-CTA partials: scratch holds 2*256 doubles
