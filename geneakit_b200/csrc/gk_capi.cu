@@ -272,13 +272,12 @@ int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, c
         delete j;
         return fail(code, msg);
     }
-    if (j->world > 1 && j->plan.ranked) {
-        delete j;
-        return fail(GK_ERR_ARG, "pedigrees deeper than 26 generations (ranked rounding) run on one GPU per job");
-    }
-    j->full_rows = j->world > 1 ? 1 : 0;
+    // a rank of a multi-GPU job evaluates every tile J and stores only its own rows; RANKED jobs (rounding order
+    // fixed by rank) must keep J <= I and store the mirror tile into the rows of J's owner instead
+    j->full_rows = (j->world > 1 && !j->plan.ranked) ? 1 : 0;
     j->use_tma = j->world > 1 ? 1 : 0;
     if (const char *e = std::getenv("GK_STEP_KERNEL")) j->use_tma = (e[0] == 't') ? 1 : 0;
+    if (j->world > 1 && j->plan.ranked) j->use_tma = 1;      // only that kernel stores mirror tiles into a peer's rows
     if (const char *e = std::getenv("GK_FULL_ROWS")) if (e[0] == '1' && !j->plan.ranked) j->full_rows = 1;
     if (const char *e = std::getenv("GK_LAG")) j->lag_env = std::atoi(e);
     if (const char *e = std::getenv("GK_RING")) j->ring_env = std::atoi(e);
@@ -560,6 +559,7 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     if (j->opts.verbose && j->rank == 0) std::printf("Cut %d out of %d\n", g, P.G);
     gk::StepDev d{};
     d.prev = row_table(j, g - 1);
+    d.outt = row_table(j, g);
     d.out_base = j->buf[g & 1]; d.out_row0 = (int64_t) o.pb * gk::kPanel;
     d.ld_prev = S.Kpad_prev; d.ld_new = S.Kpad;
     d.Kpad_prev = (int32_t) S.Kpad_prev; d.np = S.np;

@@ -291,12 +291,12 @@ __global__ void __launch_bounds__(kThreads, 1) phi_step_kernel(const StepDev s) 
 // persistent grid cannot deadlock.  No CTA-wide barrier in the loops.
 __global__ void __launch_bounds__(kThreadsTma, 1) phi_step_tma_kernel(const StepDev s) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ double *sprev[kMaxShards];
+    __shared__ double *sprev[kMaxShards], *sout[kMaxShards];
     double *smem2 = reinterpret_cast<double *>(smem_raw);                                   // NW2 phase-2 stages
     unsigned char *smem1 = smem_raw + (size_t) NW2 * kStageDoubles * sizeof(double);        // NS1 phase-1 stages
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem1 + (size_t) NS1 * P1STAGE);   // full[NS1], empty[NS1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < kMaxShards) sprev[threadIdx.x] = s.prev.base[threadIdx.x];
+    if (threadIdx.x < kMaxShards) { sprev[threadIdx.x] = s.prev.base[threadIdx.x]; sout[threadIdx.x] = s.outt.base[threadIdx.x]; }
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS1; i++) { mbar_init(smem_u32(bars + i), 1); mbar_init(smem_u32(bars + NS1 + i), NC1 / NS1); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -395,7 +395,10 @@ __global__ void __launch_bounds__(kThreadsTma, 1) phi_step_tma_kernel(const Step
             }
             const double2 *sf = reinterpret_cast<const double2 *>(S + (slots & 0xFF) * PS);
             const double2 *sm = reinterpret_cast<const double2 *>(S + ((slots >> 8) & 0xFF) * PS);
-            double *drow = out + ((long long) J * T - s.out_row0) * ldn + I * T + lane;    // row j of tile J, columns of panel I
+            // row j of tile J, columns of panel I: tile J may belong to another rank (ranked multi-GPU jobs evaluate
+            // J <= I and store the mirror into the owner's rows: peer stores over NVLink)
+            const RowLookup outl{ sout, s.outt.base[0], s.outt.n > 1 ? s.outt.row0[1] : 1, s.outt.n, ldn };
+            double *drow = const_cast<double *>(outl(J * T)) + I * T + lane;
             double *mrow = out + ((long long) I * T - s.out_row0) * ldn + J * T + lane;    // row i of panel I, columns of tile J
             cp_async_wait_all();
             __syncwarp();

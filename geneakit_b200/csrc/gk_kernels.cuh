@@ -27,6 +27,7 @@ struct RowTable {
 // Everything one recurrence step needs, by value.
 struct StepDev {
     RowTable prev;            // class matrix of cut g-1: Kpad_prev rows x ld_prev
+    RowTable outt;            // every rank's rows of the class matrix of cut g (mirror stores of a ranked multi-GPU job)
     double *out_base;         // own rows of the class matrix of cut g (Kpad columns): global row r at out_base + (r - out_row0) * ld_new
     int64_t out_row0;
     int64_t ld_prev, ld_new;

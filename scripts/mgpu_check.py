@@ -19,8 +19,10 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ok = True
-    for (n, gens, m, seed) in ((3000, 6, 200, 1), (60000, 12, 3000, 5), (200000, 12, 10000, 3)):
-        ped, pro = gk.synthetic_pedigree(n, gens, m, seed=seed)
+    # the last case is a 30-generation bottleneck population: RANKED mode (mirror tiles stored into peer rows)
+    for (n, gens, m, seed, founders) in ((3000, 6, 200, 1, None), (60000, 12, 3000, 5, None), (200000, 12, 10000, 3, None),
+                                         (40000, 30, 1500, 5, 40)):
+        ped, pro = gk.synthetic_pedigree(n, gens, m, seed=seed, founders=founders)
         sp = ShardedPhi(ped, pro, rank=rank, world=world, device=local, stream=stream.cuda_stream).upload()
         for _ in range(2):
             sp.run()

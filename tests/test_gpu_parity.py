@@ -136,11 +136,13 @@ def test_properties_at_scale():
 
 
 @pytest.mark.parametrize("world", [2, 3, 8])
-@pytest.mark.parametrize("name", ["overlap400_s1", "geneaJi_dup_anc", "overlap25_s3", "founders_only"])
+@pytest.mark.parametrize("name", ["overlap400_s1", "geneaJi_dup_anc", "overlap25_s3", "founders_only",
+                                  "deep45_sorted", "deep45_shuffled", "deep30_w40"])
 def test_sharded_ranks_on_one_gpu_match_reference_fixture(name, world):
     """The multi-GPU algorithm (rows of every cut's matrix sharded over `world` ranks, parent rows
     read from the owners' buffers, only the self-kinship vector exchanged) with the ranks emulated
-    on one GPU: bit-exact against the reference fixture, and the same mean."""
+    on one GPU: bit-exact against the reference fixture, and the same mean.  The deep fixtures run in
+    RANKED mode: tiles J <= I only, mirror tiles stored into the owner's rows."""
     from geneakit_b200.distributed import VirtualShardedPhi
     g = load_golden(name)
     ped = _ped(g)
