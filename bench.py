@@ -31,6 +31,8 @@ WORKLOADS = {
                desc="synthetic 2M-individual, 20-generation pedigree, 100k probands (BASELINE configs[3])"),
     "c3": dict(n=200_000, gens=12, m=10_000, seed=3, founders=None,
                desc="synthetic 200k-individual, 12-generation pedigree, 10k probands (BASELINE configs[2])"),
+    "c5": dict(n=5_000_000, gens=30, m=50_000, seed=5, founders=2000,
+               desc="synthetic 5M-individual, 30-generation founder-population pedigree, 50k probands (BASELINE configs[4]; needs 8 GPUs)"),
     "c5s": dict(n=1_250_000, gens=30, m=12_500, seed=5, founders=500,
                 desc="1/4-scale founder-population pedigree, 30 generations (BASELINE configs[4] shape)"),
     "tiny": dict(n=20_000, gens=8, m=1_500, seed=3, founders=None, desc="tiny synthetic (debug)"),
