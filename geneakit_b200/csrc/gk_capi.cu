@@ -32,7 +32,7 @@ int cuda_fail(cudaError_t e, const char *what) {
     } while (0)
 
 struct StepOffsets {
-    size_t prow = 0, pcnt = 0, slots = 0, prow8 = 0, pcnt8 = 0, slots8 = 0;
+    size_t prow = 0, pcnt = 0, slots = 0, prow8 = 0, pcnt8 = 0, slots8 = 0, first_use = 0;
     size_t pF = 0, pM = 0, flags = 0, pg_i = 0, pg_j = 0, pg_off = 0, pt_cls = 0, pt_mult = 0, grp_off = 0, grp_info = 0;
     size_t done = 0;              // offset into the counter arena: done1 at +0, done2 at +np
     int32_t ngroups = 0, npatch = 0;
@@ -336,6 +336,7 @@ int gk_phi_upload(gk_phi_job *j) {
         o.pF = push(S.pF); o.pM = push(S.pM); o.flags = push(S.flags);
         o.prow = push(S.prow); o.pcnt = push(S.pcnt); o.slots = push(S.slots);
         o.prow8 = push(S.prow8); o.pcnt8 = push(S.pcnt8); o.slots8 = push(S.slots8);
+        o.first_use = push(S.first_use);
         o.pg_i = push(S.pg_i); o.pg_j = push(S.pg_j); o.pg_off = push(S.pg_off);
         o.pt_cls = push(S.pt_cls); o.pt_mult = push(S.pt_mult);
         o.npatch = (int32_t) S.pg_i.size();
@@ -565,6 +566,7 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     d.Kpad_prev = (int32_t) S.Kpad_prev; d.np = S.np;
     d.pF = j->ints + o.pF; d.pM = j->ints + o.pM;
     d.prow = j->ints + o.prow; d.pcnt = j->ints + o.pcnt; d.slots = j->ints + o.slots;
+    d.first_use = j->ints + o.first_use;
     d.prow8 = j->ints + o.prow8; d.pcnt8 = j->ints + o.pcnt8; d.slots8 = j->ints + o.slots8;
     d.zero_row = j->zero_row;
     d.ring = j->ring; d.ring_stride = S.Kpad_prev * gk::kPanel; d.ring_n = o.ring_n;

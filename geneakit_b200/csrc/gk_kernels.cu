@@ -218,11 +218,13 @@ __global__ void __launch_bounds__(kThreads, 1) phi_step_kernel(const StepDev s) 
             cp_async_wait_all();
             __syncwarp();
             double *dst = buf + (long long) local * T * T + lane;
+            // rows of the panel that no tile J <= I will read are not written (half of them on average)
+            const unsigned need = s.full_rows ? 0xffffffffu : __ballot_sync(0xffffffffu, s.first_use[local * T + lane] <= I);
 #pragma unroll 8
             for (int c2 = 0; c2 < T / 2; c2++) {
                 const double2 x = sf[c2], y = sm[c2];
-                st_hint(dst + (2 * c2) * T, 0.5 * (x.x + y.x), pol_keep);
-                st_hint(dst + (2 * c2 + 1) * T, 0.5 * (x.y + y.y), pol_keep);
+                if (need >> (2 * c2) & 1u) st_hint(dst + (2 * c2) * T, 0.5 * (x.x + y.x), pol_keep);
+                if (need >> (2 * c2 + 1) & 1u) st_hint(dst + (2 * c2 + 1) * T, 0.5 * (x.y + y.y), pol_keep);
             }
             done = s.done1 + I;
         } else {

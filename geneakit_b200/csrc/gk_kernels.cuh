@@ -34,6 +34,7 @@ struct StepDev {
     int32_t Kpad_prev;
     int32_t np;               // panels / tiles of the new cut (global)
     const int32_t *pF, *pM;   // Kpad: parent rows of every new class in the previous matrix (-1 none)
+    const int32_t *first_use; // Kpad_prev: lowest tile of this cut that reads row c of a transposed panel (np: none)
     const int32_t *prow, *pcnt, *slots;   // per panel: its distinct parent rows (64 slots), their count; per class: father / mother slot
     const int32_t *prow8, *pcnt8, *slots8; // the same per sub-panel of 8 classes (16 slots): phase-1 items of phi_step_tma_kernel
     const double *zero_row;   // >= 256 zeros (the parent row of a class with an unknown parent)

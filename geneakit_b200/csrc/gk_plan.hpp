@@ -63,6 +63,7 @@ struct StepPlan {
     // de-duplicated parent rows per panel: prow[64 p + s] = s-th distinct parent row of panel p (-1 past the
     // end), pcnt[p] = how many; slots[i] = slot of class i's father row | slot of its mother row << 8
     // (kZeroSlot = unknown parent: an all-zero staged row)
+    std::vector<int32_t> first_use;    // Kpad_prev: lowest tile (panel index) of this cut holding a child of previous class c; np if none
     std::vector<int32_t> prow, pcnt, slots;
     // the same per SUB-PANEL of 8 classes (the TMA phase-1 items of the multi-GPU kernel): 16 slots each,
     // kZeroSlot8 = unknown parent
@@ -382,6 +383,13 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
                 S.slots[pos] = sl[0] | (sl[1] << 8);
             }
             S.P_cls = pcls; S.panel_rows = prow;
+            // a row N^T[c] of panel I's transposed panel is only ever read by the tiles J <= I that hold a child of c
+            S.first_use.assign((size_t) S.Kpad_prev, S.np);
+            for (int64_t pos = K - 1; pos >= 0; pos--)
+                for (int q = 0; q < 2; q++) {
+                    const int32_t pc = q ? S.pM[pos] : S.pF[pos];
+                    if (pc >= 0) S.first_use[pc] = (int32_t) (pos / kPanel);
+                }
             {   // sub-panels of 8 classes
                 const int64_t nsub = S.Kpad / kSub;
                 S.prow8.assign((size_t) nsub * 2 * kSub, -1);
