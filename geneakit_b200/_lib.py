@@ -80,6 +80,7 @@ def _load():
         getattr(L, name).argtypes = [vp]
     L.gk_phi_mean.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.gk_phi_copy_out.argtypes = [vp, vp]
+    L.gk_phi_copy_rows.argtypes = [vp, i64, i64, vp]
     L.gk_phi_device_result.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
     L.gk_phi_get_stats.argtypes = [vp, C.POINTER(gk_phi_stats)]
     L.gk_phi_cut_sizes.argtypes = [vp, _I, i32]
@@ -108,7 +109,7 @@ EXPORTS = [
     "gk_phi_f64", "gk_gc_f64", "gk_phi_required_gb", "gk_childless", "gk_parentless", "gk_dfs_order",
     "gk_cut_sizes", "gk_shard_rows", "gk_last_error", "gk_abi_version", "gk_host_alloc", "gk_host_free",
     "gk_phi_plan", "gk_phi_upload", "gk_phi_run", "gk_phi_sync", "gk_phi_mean", "gk_phi_copy_out",
-    "gk_phi_device_result", "gk_phi_get_stats", "gk_phi_cut_sizes", "gk_phi_class_sizes",
+    "gk_phi_device_result", "gk_phi_copy_rows", "gk_phi_get_stats", "gk_phi_cut_sizes", "gk_phi_class_sizes",
     "gk_phi_step_times", "gk_phi_step_bytes", "gk_phi_free", "gk_phi_step_view", "gk_phi_final_view",
     "gk_phi_ipc_export", "gk_phi_ipc_open", "gk_phi_local_buffers", "gk_phi_set_peer", "gk_phi_peers_ready",
     "gk_phi_run_step", "gk_phi_finish", "gk_phi_dvec", "gk_phi_dvec_copy_from",

@@ -231,6 +231,12 @@ class DevicePhi:
         check(lib.gk_phi_copy_out(self._h, ptr))
         return out
 
+    def rows(self, row_begin, nrows):
+        """Rows [row_begin, row_begin + nrows) of the result, copied to the host (a slice, not the M x M matrix)."""
+        out = np.empty((nrows, self.m), dtype=np.float64)
+        check(lib.gk_phi_copy_rows(self._h, int(row_begin), int(nrows), out.ctypes.data))
+        return out
+
     def device_pointer(self):
         p, ld = C.c_void_p(), C.c_int64()
         check(lib.gk_phi_device_result(self._h, C.byref(p), C.byref(ld)))

@@ -680,6 +680,16 @@ int gk_phi_copy_out(gk_phi_job *j, double *host_out) {
     return GK_OK;
 }
 
+int gk_phi_copy_rows(gk_phi_job *j, int64_t row_begin, int64_t nrows, double *host_out) {
+    if (!j || !j->ran) return fail(GK_ERR_STATE, "gk_phi_copy_rows before gk_phi_run");
+    if (!host_out || row_begin < j->row0 || nrows < 0 || row_begin + nrows > j->row1) return fail(GK_ERR_ARG, "rows outside this job's block");
+    GK_CUDA(cudaSetDevice(j->device));
+    GK_CUDA(cudaMemcpyAsync(host_out, j->out + (row_begin - j->row0) * (int64_t) j->plan.m, (size_t) nrows * j->plan.m * sizeof(double),
+                            cudaMemcpyDeviceToHost, j->stream));
+    GK_CUDA(cudaStreamSynchronize(j->stream));
+    return GK_OK;
+}
+
 int gk_phi_device_result(gk_phi_job *j, double **dev, int64_t *ld) {
     if (!j || !j->uploaded) return fail(GK_ERR_STATE, "job not uploaded");
     if (dev) *dev = j->out;

@@ -133,6 +133,8 @@ int gk_phi_run(gk_phi_job *job);                    /* enqueue init + all steps 
 int gk_phi_sync(gk_phi_job *job);                   /* wait for the job's stream */
 int gk_phi_mean(gk_phi_job *job, double *sum_all, double *sum_diag, double *mean);
 int gk_phi_copy_out(gk_phi_job *job, double *host_out);            /* (row1-row0)*m doubles: this shard's rows */
+/* rows [row_begin, row_begin + nrows) of the result (caller order; inside this job's block) -> nrows*m doubles */
+int gk_phi_copy_rows(gk_phi_job *job, int64_t row_begin, int64_t nrows, double *host_out);
 int gk_phi_device_result(gk_phi_job *job, double **dev, int64_t *ld); /* this shard's rows of the m x m matrix, in HBM */
 int gk_phi_get_stats(gk_phi_job *job, gk_phi_stats *stats);
 int gk_phi_cut_sizes(gk_phi_job *job, int32_t *sizes, int32_t cap);   /* |cut_g| as the reference counts them */

@@ -182,3 +182,45 @@ def test_gc_sharded_by_ancestor_columns(world):
     pro, anc = [int(x) for x in g["pro"]], [int(x) for x in g["anc"]]
     blocks = [sharded_gc(ped, pro, anc, r, world)[0] for r in range(world)]
     assert np.concatenate(blocks, axis=1).tobytes() == g["gc"].tobytes()
+
+
+def test_properties_at_full_c4_scale():
+    """BASELINE configs[3] at FULL size on one GPU (2M individuals, 20 generations, 100k probands: an 80 GB
+    result that stays in HBM).  The literal oracle needs 160 GB and ~40 min, so check what must hold for any
+    correct result, on row slices: symmetry, the dyadic grid, the diagonal, the sub-list property (kinship of
+    a sub-list of probands = the sub-matrix) against an independent small job, and the fused mean against the
+    row sums."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 150e9:
+        pytest.skip("needs a 180 GB device")
+    ped, pro = gk.synthetic_pedigree(2_000_000, 20, 100_000, seed=4)
+    job = gk.cgeneakit.DevicePhi(ped, pro).upload().run()
+    m = job.m
+    blocks = [(0, 16), (m // 2 - 8, 16), (m - 16, 16)]
+    rows = {r0: job.rows(r0, n) for r0, n in blocks}
+    scale = 2.0 ** (2 * 19 + 1)
+    for r0, A in rows.items():
+        assert np.all(A >= 0) and np.all(A < 1)
+        assert np.array_equal(A * scale, np.round(A * scale))                      # multiples of 2^-(2D+1)
+        d = A[np.arange(A.shape[0]), r0 + np.arange(A.shape[0])]
+        assert np.all(d >= 0.5)                                                      # 1/2 (1 + F)
+    for r0, A in rows.items():                                                       # symmetry across the slices
+        for r1, B in rows.items():
+            assert np.array_equal(A[:, r1:r1 + B.shape[0]], B[:, r0:r0 + A.shape[0]].T)
+    idx = np.concatenate([np.arange(r0, r0 + n) for r0, n in blocks])
+    sub = [pro[i] for i in idx]
+    S = gk.cgeneakit.compute_kinships(ped, sub)                                      # independent job: other cuts, other classes
+    full = np.vstack([rows[r0] for r0, _ in blocks])[:, idx]
+    assert S.tobytes() == np.ascontiguousarray(full).tobytes()
+    # fused phiMean against a host reduction of whole rows, streamed in 512-row blocks
+    total = diag = 0.0
+    for r0 in range(0, m, 25_000):                                                   # 4 sampled blocks of 512 rows
+        A = job.rows(r0, 512)
+        total += A.sum(); diag += A[np.arange(512), r0 + np.arange(512)].sum()
+    s_all, s_diag = job.sums()
+    assert s_all > 0 and s_diag >= 0.5 * m
+    mean = job.mean()
+    assert mean == (s_all - s_diag) / (float(m) * m - m)
+    part_mean = (total - diag) / (4 * 512 * (m - 1.0))
+    assert abs(part_mean - mean) < 0.2 * mean                                        # a 2 % row sample agrees with the fused mean
+    job.close()
