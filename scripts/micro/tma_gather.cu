@@ -47,10 +47,11 @@ __global__ void __launch_bounds__(32, 1) tma_kernel(const double *A, long long l
     if (acc == 12345.678) sink[0] = acc;
 }
 // LDGSTS: W warps per CTA, each stages 64 row segments of 256 B (2 rows per instruction), waits, repeats
-__global__ void __launch_bounds__(512, 1) ldgsts_kernel(const double *A, long long ld, const int *rows, int nrows, long long items, double *sink, int cg) {
+template <int RW>
+__global__ void __launch_bounds__(1024, 1) ldgsts_kernel(const double *A, long long ld, const int *rows, int nrows, long long items, double *sink, int cg) {
     extern __shared__ __align__(128) unsigned char sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
-    unsigned char *S = sm + (size_t) warp * 64 * 272;
+    unsigned char *S = sm + (size_t) warp * RW * 272;
     const long long per = items / ((long long) gridDim.x * W);
     const long long segs = ld / 32;
     const int half = lane >> 4, l16 = lane & 15;
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(512, 1) ldgsts_kernel(const double *A, long lo
         const long long it = ((long long) blockIdx.x * W + warp) * per + k;
         const long long seg = it % segs;
         #pragma unroll 8
-        for (int r = 0; r < 32; r++) {
+        for (int r = 0; r < RW / 2; r++) {
             const int row = rows[(it * 7 + (r * 2 + half) * 13) % nrows];
             const double *src = A + (long long) row * ld + seg * 32 + l16 * 2;
             const unsigned dst = smem_u32(S + (size_t) (r * 2 + half) * 272 + l16 * 16);
@@ -125,19 +126,24 @@ int main() {
     run_tma<8192, 4, 6>(A, ld, rows, nrows, sink);
     run_tma<2048, 16, 3>(A, ld, rows, nrows, sink);
     run_tma<2048, 32, 3>(A, ld, rows, nrows, sink);
-    for (int cg = 0; cg < 2; cg++)
-        for (int W : { 4, 8, 12 }) {
-            const size_t smem = (size_t) W * 64 * 272;
-            cudaFuncSetAttribute(ldgsts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-            const long long items = 148LL * W * 1500;
-            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-            ldgsts_kernel<<<148, W * 32, smem>>>(A, ld, rows, nrows, items / 10, sink, cg);
-            cudaEventRecord(e0);
-            ldgsts_kernel<<<148, W * 32, smem>>>(A, ld, rows, nrows, items, sink, cg);
-            cudaEventRecord(e1); cudaEventSynchronize(e1);
-            float ms; cudaEventElapsedTime(&ms, e0, e1);
-            printf("LDGSTS.%s W=%2d warps/SM: %.3f ms, %.0f GB/s  %s\n", cg ? "cg" : "ca", W, ms, (double) items * 16384 / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
-        }
+    // LDGSTS: what it sustains depends on the rows per item (stage size), the warps per SM and the L1 the
+    // shared-memory footprint leaves (B200: 64 rows x 12 warps = 204 KB: 2.0 TB/s; 32 x 16 = 136 KB: 5.5; 16 x 32: 6.5)
+    auto run_l = [&](auto kern, int RW, int W, int cg) {
+        const size_t smem = (size_t) W * RW * 272;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        const long long items = 148LL * W * 1500 * 64 / RW;
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        kern<<<148, W * 32, smem>>>(A, ld, rows, nrows, items / 10, sink, cg);
+        cudaEventRecord(e0);
+        kern<<<148, W * 32, smem>>>(A, ld, rows, nrows, items, sink, cg);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf("LDGSTS.%s rows/item=%2d W=%2d warps/SM (%3zu KB smem): %.3f ms, %.0f GB/s  %s\n", cg ? "cg" : "ca", RW, W, smem / 1024, ms,
+               (double) items * RW * 256 / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
+    };
+    for (int W : { 8, 12 }) run_l(ldgsts_kernel<64>, 64, W, 1);
+    for (int W : { 8, 12, 16, 24 }) run_l(ldgsts_kernel<32>, 32, W, 1);
+    for (int W : { 12, 16, 24, 32 }) run_l(ldgsts_kernel<16>, 16, W, 1);
     for (int W : { 8, 16, 32 }) {
         const long long items = 148LL * W * 1500;
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
