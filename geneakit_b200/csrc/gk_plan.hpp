@@ -35,7 +35,10 @@
 // higher-ranked one" -- the grouping lib/compute.cpp:529-548 rounds with.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <cstdlib>
+#include <thread>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -190,6 +193,43 @@ inline void locality_order(const std::vector<ClassRec> &cls, const std::vector<i
     }
 }
 
+// Run fn(g) for g in [g0, g1) on up to `threads` host threads (the cuts are planned independently).
+template <class F>
+inline void parallel_steps(int g0, int g1, int threads, F fn) {
+    if (threads <= 1 || g1 - g0 <= 1) { for (int g = g0; g < g1; g++) fn(g); return; }
+    std::atomic<int> next(g0);
+    std::vector<std::thread> pool;
+    const int nt = std::min(threads, g1 - g0);
+    for (int t = 0; t < nt; t++)
+        pool.emplace_back([&]() { for (int g = next.fetch_add(1); g < g1; g = next.fetch_add(1)) fn(g); });
+    for (auto &th : pool) th.join();
+}
+
+// Per-cut scratch of the planner.  Stage A fills members / classes (in NATURAL order: sorted by key), stage
+// B the order of the classes, stage C the arrays the kernels read.
+struct CutWork {
+    std::vector<int32_t> members;                  // individuals of the cut, ascending
+    std::vector<int32_t> nat_of;                   // natural class id of members[k]
+    std::vector<ClassRec> cls;                     // natural order; pc0 / pc1 = NATURAL ids in the previous cut (stage B)
+    std::vector<int32_t> pos;                      // natural id -> position in the class matrix
+    int64_t n_kept = 0, P_ref = 0;
+    int32_t base = 0;
+    std::vector<int32_t> table;                    // table[ind - base] = natural id (built when the cut's rank range is compact)
+    void build_table() {
+        if (members.empty()) return;
+        base = members.front();
+        const int64_t range = (int64_t) members.back() - base + 1;
+        if (range > 8 * (int64_t) members.size() + 1024) return;     // sparse cut: keep the binary search
+        table.assign((size_t) range, -1);
+        for (size_t k = 0; k < members.size(); k++) table[members[k] - base] = nat_of[k];
+    }
+    int32_t nat(int32_t ind) const {               // natural class id of an individual of this cut
+        if (!table.empty()) return table[ind - base];
+        const auto it = std::lower_bound(members.begin(), members.end(), ind);
+        return nat_of[it - members.begin()];
+    }
+};
+
 inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m,
                            const int32_t *pro, int compress_opt, int order_opt, int world, PhiPlan &P) {
     auto t0 = std::chrono::steady_clock::now();
@@ -224,253 +264,262 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
     P.ranked = (G - 1 > 26);
     P.compressed = P.ranked ? false : (compress_opt != 0);
     P.steps.resize(G);
+    int threads = (int) std::thread::hardware_concurrency();
+    threads = std::max(1, std::min(threads, 8));
+    if (const char *e = std::getenv("GK_PLAN_THREADS")) threads = std::max(1, std::atoi(e));
 
-    // members entering each cut: enter(x) = G-1-maxp, last cut containing x = G-1-minp
-    std::vector<int64_t> new_off(G + 1, 0);
-    for (int32_t x = 0; x < n; x++) if (maxp[x] >= 0) new_off[G - 1 - maxp[x] + 1]++;
-    for (int g = 0; g < G; g++) new_off[g + 1] += new_off[g];
-    std::vector<int32_t> new_mem(new_off[G]);
+    // ---- members of every cut (x belongs to cuts enter(x) = G-1-maxp .. leave(x) = G-1-minp), ascending ----
+    std::vector<CutWork> W(G);
     {
-        std::vector<int64_t> w(new_off.begin(), new_off.end() - 1);
-        for (int32_t x = 0; x < n; x++) if (maxp[x] >= 0) new_mem[w[G - 1 - maxp[x]]++] = x;
+        std::vector<int64_t> cnt(G + 1, 0);
+        for (int32_t x = 0; x < n; x++) if (maxp[x] >= 0) { cnt[G - 1 - maxp[x]]++; cnt[G - minp[x]]--; }
+        int64_t run = 0;
+        for (int g = 0; g < G; g++) { run += cnt[g]; W[g].members.reserve((size_t) run); }
+        for (int32_t x = 0; x < n; x++) if (maxp[x] >= 0)
+            for (int g = G - 1 - maxp[x]; g <= G - 1 - minp[x]; g++) W[g].members.push_back(x);
     }
-    auto leave = [&](int32_t x) { return G - 1 - minp[x]; };
+    auto enter = [&](int32_t x) { return G - 1 - maxp[x]; };
+    std::atomic<bool> failed(false);
 
-    std::vector<int32_t> cls_prev(n, -1), cls_cur(n, -1);
-    std::vector<int32_t> par_stamp(n, -1);            // distinct-parent counting
-    std::vector<int32_t> prow_stamp, prow_panel;      // distinct parent rows of the previous matrix / per panel
-    std::vector<int32_t> cur;                         // members of the current cut (individuals)
-    std::vector<MemberRec> mem;
-    std::vector<ClassRec> cls;
-    std::vector<int32_t> order;
-    struct Use { int32_t ind, cls, mult; };
-    std::vector<Use> uses;
-    struct Term { int32_t i, j, c, mult; };
-    std::vector<Term> terms;
-
-    for (int g = 0; g < G; g++) {
-        StepPlan &S = P.steps[g];
-        const StepPlan *Sp = g > 0 ? &P.steps[g - 1] : nullptr;
-        // ---- members of cut g ------------------------------------------------------------
-        std::vector<int32_t> nxt;
-        nxt.reserve(cur.size() + (new_off[g + 1] - new_off[g]));
-        mem.clear();
-        for (int32_t x : cur) if (leave(x) >= g) {
-            MemberRec r; r.ind = x; r.kept = 1; r.pi0 = r.pi1 = x; r.pc0 = r.pc1 = cls_prev[x];
-            mem.push_back(r); nxt.push_back(x);
+    // ---- stage A (parallel): classes of every cut, in natural order --------------------------------
+    parallel_steps(0, G, threads, [&](int g) {
+        CutWork &C = W[g];
+        const size_t nm = C.members.size();
+        // new members with equal (father, mother) share a class; kept members and uncompressed jobs: singletons
+        std::vector<std::pair<uint64_t, uint32_t>> keys(nm);
+        for (size_t k = 0; k < nm; k++) {
+            const int32_t x = C.members[k];
+            const bool kept = enter(x) < g;
+            uint64_t key;
+            if (kept || !P.compressed) key = (uint64_t(1) << 63) | uint64_t(uint32_t(x));
+            else key = (uint64_t(uint32_t(sire[x] + 1)) << 31) | uint64_t(uint32_t(dam[x] + 1));
+            keys[k] = { key, (uint32_t) k };
+            if (kept) C.n_kept++;
         }
-        S.n_kept = (int64_t) mem.size();
-        int64_t pref = 0;
-        for (int64_t e = new_off[g]; e < new_off[g + 1]; e++) {
-            int32_t x = new_mem[e];
-            MemberRec r; r.ind = x; r.kept = 0;
-            r.pi0 = sire[x]; r.pi1 = dam[x];
-            r.pc0 = r.pi0 >= 0 ? cls_prev[r.pi0] : -1;
-            r.pc1 = r.pi1 >= 0 ? cls_prev[r.pi1] : -1;
-            if ((r.pi0 >= 0 && r.pc0 < 0) || (r.pi1 >= 0 && r.pc1 < 0)) {
-                P.error = "internal: parent of a new cut member is not in the previous cut"; P.error_code = 1; return false;
-            }
-            for (int q = 0; q < 2; q++) {
-                int32_t p = q ? r.pi1 : r.pi0;
-                if (p >= 0 && par_stamp[p] != g) { par_stamp[p] = g; pref++; }
-            }
-            mem.push_back(r); nxt.push_back(x);
-        }
-        S.P_ref = pref;
-        S.cut_size = (g == G - 1) ? (int64_t) m : (int64_t) mem.size();
-        S.K_prev = Sp ? Sp->K : 0;
-        S.Kpad_prev = Sp ? Sp->Kpad : 0;
-
-        // ---- classes: new members with equal (pi0, pi1) share a row; kept are singletons ----
-        auto key_of = [&](const MemberRec &r) -> uint64_t {
-            if (r.kept || !P.compressed)           // unique per individual
-                return (uint64_t(1) << 63) | uint64_t(uint32_t(r.ind));
-            return (uint64_t(uint32_t(r.pi0 + 1)) << 31) | uint64_t(uint32_t(r.pi1 + 1));
-        };
-        std::sort(mem.begin(), mem.end(), [&](const MemberRec &a, const MemberRec &b) {
-            uint64_t ka = key_of(a), kb = key_of(b);
-            if (ka != kb) return ka < kb;
-            return a.ind < b.ind;
-        });
-        cls.clear();
-        for (int32_t i = 0; i < (int32_t) mem.size();) {
-            int32_t j = i + 1;
-            uint64_t k = key_of(mem[i]);
-            while (j < (int32_t) mem.size() && key_of(mem[j]) == k) j++;
+        std::sort(keys.begin(), keys.end());          // ties: position = individual order
+        C.nat_of.assign(nm, 0);
+        std::vector<int32_t> parents;
+        for (size_t i = 0; i < nm;) {
+            size_t j = i + 1;
+            while (j < nm && keys[j].first == keys[i].first) j++;
+            const int32_t x = C.members[keys[i].second];
             ClassRec c;
-            c.pi0 = mem[i].pi0; c.pi1 = mem[i].pi1; c.pc0 = mem[i].pc0; c.pc1 = mem[i].pc1;
-            c.first_member = mem[i].ind; c.kept = mem[i].kept; c.member_begin = i; c.member_end = j;
-            c.size = j - i;
-            cls.push_back(c);
+            c.kept = enter(x) < g;
+            c.pi0 = c.kept ? x : sire[x]; c.pi1 = c.kept ? x : dam[x];
+            c.pc0 = c.pc1 = -1;
+            c.first_member = x; c.size = (int32_t) (j - i);
+            c.member_begin = (int32_t) i; c.member_end = (int32_t) j;
+            for (size_t q = i; q < j; q++) C.nat_of[keys[q].second] = (int32_t) C.cls.size();
+            if (!c.kept) { if (c.pi0 >= 0) parents.push_back(c.pi0); if (c.pi1 >= 0) parents.push_back(c.pi1); }
+            C.cls.push_back(c);
             i = j;
         }
-        const int64_t K = (int64_t) cls.size();
-        // ---- order ---------------------------------------------------------------------------
+        std::sort(parents.begin(), parents.end());
+        C.P_ref = (int64_t) (std::unique(parents.begin(), parents.end()) - parents.begin());
+        C.build_table();
+    });
+
+    // ---- stage B: parent classes (natural ids in the previous cut) and the order of the classes --------
+    // The order only needs to know WHICH classes share a parent row, so the cuts are independent of one
+    // another -- except for multi-GPU jobs, which group the classes by the rank that owns the first parent's
+    // row (a POSITION in the previous matrix): those are ordered cut after cut.
+    auto order_cut = [&](int g) {
+        CutWork &C = W[g];
+        const int64_t K = (int64_t) C.cls.size();
+        const int64_t K_prev = g > 0 ? (int64_t) W[g - 1].cls.size() : 0;
+        if (g > 0)
+            for (ClassRec &c : C.cls) {
+                c.pc0 = c.pi0 >= 0 ? W[g - 1].nat(c.pi0) : -1;
+                c.pc1 = c.pi1 >= 0 ? W[g - 1].nat(c.pi1) : -1;
+            }
+        std::vector<int32_t> order;
+        order.reserve(K);
         if (P.ranked) {
             order.resize(K);
             for (int64_t i = 0; i < K; i++) order[i] = (int32_t) i;
-            std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cls[a].first_member > cls[b].first_member; });
+            std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return C.cls[a].first_member > C.cls[b].first_member; });
         } else if (order_opt == 0 || g == 0) {
             order.resize(K);
             for (int64_t i = 0; i < K; i++) order[i] = (int32_t) i;
             std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-                const ClassRec &x = cls[a], &y = cls[b];
+                const ClassRec &x = C.cls[a], &y = C.cls[b];
                 if (x.pc0 != y.pc0) return x.pc0 < y.pc0;
                 if (x.pc1 != y.pc1) return x.pc1 < y.pc1;
                 return x.first_member < y.first_member;
             });
         } else {
-            // Multi-GPU: the rows of every matrix are sharded in equal blocks of panels.  Group the new
-            // classes by the rank that owns their first known parent's row (so that row is a LOCAL read
-            // for the rank that will own the class -- up to the spill at the block boundaries), then
-            // order each group for locality.
-            order.clear();
-            order.reserve(K);
             std::vector<int32_t> subset;
-            if (world <= 1 || S.K_prev <= 0) {
+            if (world <= 1) {
                 subset.resize(K);
                 for (int64_t i = 0; i < K; i++) subset[i] = (int32_t) i;
-                locality_order(cls, subset, S.K_prev, order);
+                locality_order(C.cls, subset, K_prev, order);
             } else {
-                const int64_t rps = (int64_t) ((Sp->np + world - 1) / world) * kPanel;     // rows per shard of the previous matrix
+                // Multi-GPU: the rows of every matrix are sharded in equal blocks of panels.  Group the new
+                // classes by the rank that owns their first known parent's row (so that row is a LOCAL read
+                // for the rank that will own the class -- up to the spill at the block boundaries), then
+                // order each group for locality.
+                const int64_t np_prev = round_up(std::max<int64_t>(K_prev, 1), kPanel) / kPanel;
+                const int64_t rps = ((np_prev + world - 1) / world) * kPanel;       // rows per shard of the previous matrix
                 std::vector<std::vector<int32_t>> groups(world);
                 for (int64_t i = 0; i < K; i++) {
-                    const int32_t pc = cls[i].pc0 >= 0 ? cls[i].pc0 : cls[i].pc1;
-                    const int q = pc < 0 ? (int) (i % world) : (int) std::min<int64_t>(world - 1, pc / rps);
+                    const int32_t pcn = C.cls[i].pc0 >= 0 ? C.cls[i].pc0 : C.cls[i].pc1;
+                    const int q = pcn < 0 ? (int) (i % world) : (int) std::min<int64_t>(world - 1, W[g - 1].pos[pcn] / rps);
                     groups[q].push_back((int32_t) i);
                 }
-                for (int q = 0; q < world; q++) locality_order(cls, groups[q], S.K_prev, order);
+                for (int q = 0; q < world; q++) locality_order(C.cls, groups[q], K_prev, order);
             }
         }
+        C.pos.assign(K, 0);
+        for (int64_t p = 0; p < K; p++) C.pos[order[p]] = (int32_t) p;
+    };
+    if (world > 1 && !P.ranked && order_opt != 0) for (int g = 0; g < G; g++) order_cut(g);
+    else parallel_steps(0, G, threads, order_cut);
+
+    // ---- stage C (parallel): the arrays the kernels read -------------------------------------------
+    parallel_steps(0, G, threads, [&](int g) {
+        StepPlan &S = P.steps[g];
+        const CutWork &C = W[g];
+        const CutWork *Cp = g > 0 ? &W[g - 1] : nullptr;
+        const int64_t K = (int64_t) C.cls.size();
+        S.n_kept = C.n_kept; S.P_ref = C.P_ref;
+        S.cut_size = (g == G - 1) ? (int64_t) m : (int64_t) C.members.size();
+        S.K_prev = Cp ? (int64_t) Cp->cls.size() : 0;
+        S.Kpad_prev = Cp ? round_up(std::max<int64_t>(S.K_prev, 1), kPanel) : 0;
         S.K = K;
         S.Kpad = round_up(std::max<int64_t>(K, 1), kPanel);
         S.np = (int) (S.Kpad / kPanel);
         S.pF.assign((size_t) S.Kpad, -1); S.pM.assign((size_t) S.Kpad, -1); S.flags.assign((size_t) S.Kpad, 0);
         S.cls_ind.resize(K); S.cls_size.resize(K);
-        for (int64_t pos = 0; pos < K; pos++) {
-            const ClassRec &c = cls[order[pos]];
-            for (int32_t q = c.member_begin; q < c.member_end; q++) cls_cur[mem[q].ind] = (int32_t) pos;
-            S.pF[pos] = c.pc0; S.pM[pos] = c.pc1;
-            S.flags[pos] = (c.size == 1 ? kFlagSingleton : 0) | (c.kept ? kFlagKept : 0) |
-                           ((!c.kept && c.pc0 >= 0 && c.pc1 >= 0) ? kFlagBoth : 0);
-            S.cls_ind[pos] = c.first_member; S.cls_size[pos] = c.size;
+        std::vector<int32_t> nat_at(K);                    // position -> natural id
+        for (int64_t i = 0; i < K; i++) nat_at[C.pos[i]] = (int32_t) i;
+        for (int64_t p = 0; p < K; p++) {
+            const ClassRec &c = C.cls[nat_at[p]];
+            if ((c.pi0 >= 0 && g > 0 && c.pc0 < 0) || (c.pi1 >= 0 && g > 0 && c.pc1 < 0)) failed = true;
+            S.pF[p] = c.pc0 >= 0 ? Cp->pos[c.pc0] : -1;
+            S.pM[p] = c.pc1 >= 0 ? Cp->pos[c.pc1] : -1;
+            S.flags[p] = (c.size == 1 ? kFlagSingleton : 0) | (c.kept ? kFlagKept : 0) |
+                         ((!c.kept && c.pc0 >= 0 && c.pc1 >= 0) ? kFlagBoth : 0);
+            S.cls_ind[p] = c.first_member; S.cls_size[p] = c.size;
             if (c.kept) S.kept_cls++;
         }
+        if (g == 0) return;
 
-        if (g > 0) {
-            // ---- traffic statistics: distinct parent rows overall and per panel ----------------
-            prow_stamp.assign((size_t) S.K_prev, -1);
-            prow_panel.assign((size_t) S.K_prev, -1);
-            std::vector<int32_t> slot_of((size_t) S.K_prev, 0);
-            S.prow.assign((size_t) S.np * 2 * kPanel, -1);
-            S.pcnt.assign((size_t) S.np, 0);
-            S.slots.assign((size_t) S.Kpad, kZeroSlot | (kZeroSlot << 8));
-            int64_t pcls = 0, prow = 0;
+        // ---- distinct parent rows: overall, per panel (64 slots), per sub-panel of 8 classes (16 slots) ----
+        std::vector<int32_t> stamp((size_t) S.K_prev, -1), unit_stamp((size_t) S.K_prev, -1), slot_of((size_t) S.K_prev, 0);
+        S.prow.assign((size_t) S.np * 2 * kPanel, -1);
+        S.pcnt.assign((size_t) S.np, 0);
+        S.slots.assign((size_t) S.Kpad, kZeroSlot | (kZeroSlot << 8));
+        int64_t pcls = 0, prow = 0;
+        for (int64_t pos = 0; pos < K; pos++) {
+            const int32_t panel = (int32_t) (pos / kPanel);
+            int32_t sl[2] = { kZeroSlot, kZeroSlot };
+            for (int q = 0; q < 2; q++) {
+                const int32_t pc = q ? S.pM[pos] : S.pF[pos];
+                if (pc < 0) continue;
+                if (stamp[pc] != g) { stamp[pc] = g; pcls++; }
+                if (unit_stamp[pc] != panel) {
+                    unit_stamp[pc] = panel; prow++;
+                    slot_of[pc] = S.pcnt[panel]++;
+                    S.prow[(size_t) panel * 2 * kPanel + slot_of[pc]] = pc;
+                }
+                sl[q] = slot_of[pc];
+            }
+            S.slots[pos] = sl[0] | (sl[1] << 8);
+        }
+        S.P_cls = pcls; S.panel_rows = prow;
+        // a row N^T[c] of panel I's transposed panel is only ever read by the tiles J <= I that hold a child of c
+        S.first_use.assign((size_t) S.Kpad_prev, S.np);
+        for (int64_t pos = K - 1; pos >= 0; pos--)
+            for (int q = 0; q < 2; q++) {
+                const int32_t pc = q ? S.pM[pos] : S.pF[pos];
+                if (pc >= 0) S.first_use[pc] = (int32_t) (pos / kPanel);
+            }
+        {
+            const int64_t nsub = S.Kpad / kSub;
+            S.prow8.assign((size_t) nsub * 2 * kSub, -1);
+            S.pcnt8.assign((size_t) nsub, 0);
+            S.slots8.assign((size_t) S.Kpad, kZeroSlot8 | (kZeroSlot8 << 8));
+            std::fill(unit_stamp.begin(), unit_stamp.end(), -1);
             for (int64_t pos = 0; pos < K; pos++) {
-                const int32_t panel = (int32_t) (pos / kPanel);
-                int32_t sl[2] = { kZeroSlot, kZeroSlot };
+                const int32_t sub = (int32_t) (pos / kSub);
+                int32_t sl[2] = { kZeroSlot8, kZeroSlot8 };
                 for (int q = 0; q < 2; q++) {
                     const int32_t pc = q ? S.pM[pos] : S.pF[pos];
                     if (pc < 0) continue;
-                    if (prow_stamp[pc] != g) { prow_stamp[pc] = g; pcls++; }
-                    if (prow_panel[pc] != panel) {
-                        prow_panel[pc] = panel; prow++;
-                        slot_of[pc] = S.pcnt[panel]++;
-                        S.prow[(size_t) panel * 2 * kPanel + slot_of[pc]] = pc;
+                    if (unit_stamp[pc] != sub) {
+                        unit_stamp[pc] = sub; S.sub_rows++;
+                        slot_of[pc] = S.pcnt8[sub]++;
+                        S.prow8[(size_t) sub * 2 * kSub + slot_of[pc]] = pc;
                     }
                     sl[q] = slot_of[pc];
                 }
-                S.slots[pos] = sl[0] | (sl[1] << 8);
-            }
-            S.P_cls = pcls; S.panel_rows = prow;
-            // a row N^T[c] of panel I's transposed panel is only ever read by the tiles J <= I that hold a child of c
-            S.first_use.assign((size_t) S.Kpad_prev, S.np);
-            for (int64_t pos = K - 1; pos >= 0; pos--)
-                for (int q = 0; q < 2; q++) {
-                    const int32_t pc = q ? S.pM[pos] : S.pF[pos];
-                    if (pc >= 0) S.first_use[pc] = (int32_t) (pos / kPanel);
-                }
-            {   // sub-panels of 8 classes
-                const int64_t nsub = S.Kpad / kSub;
-                S.prow8.assign((size_t) nsub * 2 * kSub, -1);
-                S.pcnt8.assign((size_t) nsub, 0);
-                S.slots8.assign((size_t) S.Kpad, kZeroSlot8 | (kZeroSlot8 << 8));
-                std::fill(prow_panel.begin(), prow_panel.end(), -1);
-                for (int64_t pos = 0; pos < K; pos++) {
-                    const int32_t sub = (int32_t) (pos / kSub);
-                    int32_t sl[2] = { kZeroSlot8, kZeroSlot8 };
-                    for (int q = 0; q < 2; q++) {
-                        const int32_t pc = q ? S.pM[pos] : S.pF[pos];
-                        if (pc < 0) continue;
-                        if (prow_panel[pc] != sub) {
-                            prow_panel[pc] = sub; S.sub_rows++;
-                            slot_of[pc] = S.pcnt8[sub]++;
-                            S.prow8[(size_t) sub * 2 * kSub + slot_of[pc]] = pc;
-                        }
-                        sl[q] = slot_of[pc];
-                    }
-                    S.slots8[pos] = sl[0] | (sl[1] << 8);
-                }
-            }
-
-            // ---- corrections: class pairs that share a parent INDIVIDUAL whose class has several members
-            uses.clear(); terms.clear();
-            for (int64_t pos = 0; pos < K; pos++) {
-                const ClassRec &c = cls[order[pos]];
-                bool pushed0 = false;
-                for (int q = 0; q < 2; q++) {
-                    const int32_t pi = q ? c.pi1 : c.pi0, pc = q ? c.pc1 : c.pc0;
-                    if (pi < 0 || Sp->cls_size[pc] <= 1) continue;     // singleton parent class: diagonal already = self kinship
-                    if (q == 1 && pushed0 && pi == c.pi0) { uses.back().mult++; continue; }   // kept: the same individual twice
-                    uses.push_back({ pi, (int32_t) pos, 1 });
-                    if (q == 0) pushed0 = true;
-                }
-            }
-            std::sort(uses.begin(), uses.end(), [](const Use &a, const Use &b) { return a.ind != b.ind ? a.ind < b.ind : a.cls < b.cls; });
-            int64_t budget = (int64_t) 1 << 27;
-            for (size_t a = 0; a < uses.size();) {
-                size_t b = a + 1;
-                while (b < uses.size() && uses[b].ind == uses[a].ind) b++;
-                const int64_t k = (int64_t) (b - a);
-                budget -= k * (k + 1) / 2;
-                if (budget < 0) {
-                    P.error = "an individual of a multi-member sibship has too many mates for the correction list (compress=0 avoids it)";
-                    P.error_code = 1; return false;
-                }
-                const int32_t pc = cls_prev[uses[a].ind];
-                for (size_t x = a; x < b; x++)
-                    for (size_t y = a; y <= x; y++) {
-                        if (x == y && (S.flags[uses[x].cls] & kFlagSingleton)) continue;   // diagonal of a singleton := d_new
-                        terms.push_back({ uses[x].cls, uses[y].cls, pc, uses[x].mult * uses[y].mult });
-                    }
-                a = b;
-            }
-            std::sort(terms.begin(), terms.end(), [](const Term &a, const Term &b) {
-                if (a.i != b.i) return a.i < b.i;
-                if (a.j != b.j) return a.j < b.j;
-                return a.c < b.c;
-            });
-            S.pg_off.push_back(0);
-            for (size_t a = 0; a < terms.size();) {
-                size_t b = a;
-                while (b < terms.size() && terms[b].i == terms[a].i && terms[b].j == terms[a].j) {
-                    if (!S.pt_cls.empty() && (size_t) S.pg_off.back() < S.pt_cls.size() && S.pt_cls.back() == terms[b].c)
-                        S.pt_mult.back() += terms[b].mult;                          // same class twice (two shared siblings... same individual listed once per class)
-                    else { S.pt_cls.push_back(terms[b].c); S.pt_mult.push_back(terms[b].mult); }
-                    b++;
-                }
-                S.pg_i.push_back(terms[a].i); S.pg_j.push_back(terms[a].j);
-                S.pg_off.push_back((int32_t) S.pt_cls.size());
-                a = b;
+                S.slots8[pos] = sl[0] | (sl[1] << 8);
             }
         }
-        cur.swap(nxt);
-        cls_prev.swap(cls_cur);   // cls_cur now holds stale entries; every member is rewritten before use
+
+        // ---- corrections: class pairs that share a parent INDIVIDUAL whose class has several members ----
+        struct Use { int32_t ind, cls, mult; };
+        struct Term { int32_t i, j, c, mult; };
+        std::vector<Use> uses;
+        std::vector<Term> terms;
+        for (int64_t pos = 0; pos < K; pos++) {
+            const ClassRec &c = C.cls[nat_at[pos]];
+            bool pushed0 = false;
+            for (int q = 0; q < 2; q++) {
+                const int32_t pi = q ? c.pi1 : c.pi0, pcn = q ? c.pc1 : c.pc0;
+                if (pi < 0 || Cp->cls[pcn].size <= 1) continue;       // singleton parent class: diagonal already = self kinship
+                if (q == 1 && pushed0 && pi == c.pi0) { uses.back().mult++; continue; }   // kept: the same individual twice
+                uses.push_back({ pi, (int32_t) pos, 1 });
+                if (q == 0) pushed0 = true;
+            }
+        }
+        std::sort(uses.begin(), uses.end(), [](const Use &a, const Use &b) {
+            return ((uint64_t) (uint32_t) a.ind << 32 | (uint32_t) a.cls) < ((uint64_t) (uint32_t) b.ind << 32 | (uint32_t) b.cls);
+        });
+        int64_t budget = (int64_t) 1 << 27;
+        for (size_t a = 0; a < uses.size();) {
+            size_t b = a + 1;
+            while (b < uses.size() && uses[b].ind == uses[a].ind) b++;
+            const int64_t k = (int64_t) (b - a);
+            budget -= k * (k + 1) / 2;
+            if (budget < 0) { failed = true; return; }
+            const int32_t pc = Cp->pos[Cp->nat(uses[a].ind)];
+            for (size_t x = a; x < b; x++)
+                for (size_t y = a; y <= x; y++) {
+                    if (x == y && (S.flags[uses[x].cls] & kFlagSingleton)) continue;   // diagonal of a singleton := d_new
+                    terms.push_back({ uses[x].cls, uses[y].cls, pc, uses[x].mult * uses[y].mult });
+                }
+            a = b;
+        }
+        std::sort(terms.begin(), terms.end(), [](const Term &a, const Term &b) {
+            if (a.i != b.i) return a.i < b.i;
+            if (a.j != b.j) return a.j < b.j;
+            return a.c < b.c;
+        });
+        S.pg_off.push_back(0);
+        for (size_t a = 0; a < terms.size();) {
+            size_t b = a;
+            while (b < terms.size() && terms[b].i == terms[a].i && terms[b].j == terms[a].j) {
+                if (!S.pt_cls.empty() && (size_t) S.pg_off.back() < S.pt_cls.size() && S.pt_cls.back() == terms[b].c)
+                    S.pt_mult.back() += terms[b].mult;
+                else { S.pt_cls.push_back(terms[b].c); S.pt_mult.push_back(terms[b].mult); }
+                b++;
+            }
+            S.pg_i.push_back(terms[a].i); S.pg_j.push_back(terms[a].j);
+            S.pg_off.push_back((int32_t) S.pt_cls.size());
+            a = b;
+        }
+    });
+    if (failed) {
+        P.error = "internal: a parent is missing from the previous cut, or an individual of a multi-member sibship has too many "
+                  "mates for the correction list (compress=0 avoids the latter)";
+        P.error_code = 1; return false;
     }
 
     // ---- final expansion map (caller order, duplicates expand to the same row) --------------
     P.final_cls.resize(m); P.final_ind.resize(m);
-    for (int32_t i = 0; i < m; i++) { P.final_ind[i] = pro[i]; P.final_cls[i] = cls_prev[pro[i]]; }
+    const CutWork &L = W[G - 1];
+    for (int32_t i = 0; i < m; i++) { P.final_ind[i] = pro[i]; P.final_cls[i] = L.pos[L.nat(pro[i])]; }
     P.plan_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return true;
 }
