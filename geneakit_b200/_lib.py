@@ -46,6 +46,12 @@ class gk_step_view(C.Structure):
                 ("pg_i", _P), ("pg_j", _P), ("pg_off", _P), ("pt_cls", _P), ("pt_mult", _P)]
 
 
+class gk_gc_stats(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("total_seconds", C.c_double), ("algorithmic_bytes", C.c_int64),
+                ("member_rows", C.c_int64), ("column_blocks", C.c_int64), ("block_columns", C.c_int64),
+                ("kernel_launches", C.c_int64), ("n_cuts", C.c_int32), ("reserved", C.c_int32)]
+
+
 def make_opts(device=-1, verbose=False, compress=-1, order=-1, rank=0, world=1, stream=None):
     o = gk_opts()
     o.struct_size = C.sizeof(gk_opts)
@@ -100,6 +106,9 @@ def _load():
     L.gk_phi_dvec.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
     L.gk_phi_dvec_copy_from.argtypes = [vp, vp, i32]
     L.gk_phi_free.argtypes = [vp]; L.gk_phi_free.restype = None
+    L.gk_phi_debug_prof.argtypes = [vp, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")]
+    L.gk_cache_release.argtypes = []; L.gk_cache_release.restype = None
+    L.gk_gc_last_stats.argtypes = [C.POINTER(gk_gc_stats)]
     return L
 
 
@@ -113,6 +122,7 @@ EXPORTS = [
     "gk_phi_step_times", "gk_phi_step_bytes", "gk_phi_free", "gk_phi_step_view", "gk_phi_final_view",
     "gk_phi_ipc_export", "gk_phi_ipc_open", "gk_phi_local_buffers", "gk_phi_set_peer", "gk_phi_peers_ready",
     "gk_phi_run_step", "gk_phi_finish", "gk_phi_dvec", "gk_phi_dvec_copy_from",
+    "gk_phi_debug_prof", "gk_cache_release", "gk_gc_last_stats",
 ]
 
 

@@ -1,12 +1,17 @@
 // C ABI of libgeneakit_b200.so (see include/geneakit_b200.h).  Host orchestration only:
 // plan on the host (gk_plan.hpp), keep matrices in HBM, enqueue the sm_100a kernels
 // (gk_kernels.cu) on one stream.  There is no CPU compute path in this file.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <cuda.h>     // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked
 
 #include "../../include/geneakit_b200.h"
 #include "gk_gcplan.hpp"
@@ -16,6 +21,8 @@
 namespace {
 
 thread_local std::string g_err;
+std::mutex g_call_mu;              // the one-shot entry points run one call at a time (SURVEY 8b "internal mutex")
+gk_gc_stats g_gc_stats{};
 
 int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -31,6 +38,65 @@ int cuda_fail(cudaError_t e, const char *what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #call);      \
     } while (0)
 
+// ---- device memory cache (SURVEY 8b "lazily creates CUDA contexts/streams once per process and caches them") -------
+// cudaMalloc / cudaFree of the ~110 GB a c4 job needs cost more than the kernels.  Freed blocks are kept per device and
+// handed out again to the next job that asks for a similar size (best fit within 25 %); on an allocation failure the
+// cache of that device is dropped and the request retried.  gk_cache_release() / GENEAKIT_CACHE=0 switch it off.
+struct PoolBlock { void *p; size_t bytes; int dev; };
+std::mutex g_pool_mu;
+std::vector<PoolBlock> g_pool_free, g_pool_live;
+bool pool_enabled() {
+    static const bool on = [] { const char *e = std::getenv("GENEAKIT_CACHE"); return !(e && e[0] == '0'); }();
+    return on;
+}
+void pool_drop(int dev) {       // caller holds the lock
+    for (size_t i = 0; i < g_pool_free.size();)
+        if (dev < 0 || g_pool_free[i].dev == dev) {
+            cudaSetDevice(g_pool_free[i].dev);
+            cudaFree(g_pool_free[i].p);
+            g_pool_free[i] = g_pool_free.back(); g_pool_free.pop_back();
+        } else i++;
+}
+cudaError_t pool_alloc(void **out, size_t bytes, int dev) {
+    bytes = std::max<size_t>(bytes, 256);
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    int best = -1;
+    for (size_t i = 0; i < g_pool_free.size(); i++) {
+        const PoolBlock &b = g_pool_free[i];
+        if (b.dev != dev || b.bytes < bytes || b.bytes > bytes + bytes / 4 + (1 << 20)) continue;
+        if (best < 0 || b.bytes < g_pool_free[best].bytes) best = (int) i;
+    }
+    if (best >= 0) {
+        *out = g_pool_free[best].p;
+        g_pool_live.push_back(g_pool_free[best]);
+        g_pool_free[best] = g_pool_free.back(); g_pool_free.pop_back();
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        pool_drop(dev);
+        cudaSetDevice(dev);
+        e = cudaMalloc(out, bytes);
+    }
+    if (e == cudaSuccess) g_pool_live.push_back({ *out, bytes, dev });
+    return e;
+}
+void pool_free(void *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (size_t i = 0; i < g_pool_live.size(); i++)
+        if (g_pool_live[i].p == p) {
+            PoolBlock b = g_pool_live[i];
+            g_pool_live[i] = g_pool_live.back(); g_pool_live.pop_back();
+            if (pool_enabled()) g_pool_free.push_back(b);
+            else { cudaSetDevice(b.dev); cudaFree(p); }
+            return;
+        }
+    cudaFree(p);
+}
+template <class T> cudaError_t pool_alloc_t(T **out, size_t bytes, int dev) { void *p = nullptr; cudaError_t e = pool_alloc(&p, bytes, dev); *out = static_cast<T *>(p); return e; }
+
 struct StepOffsets {
     size_t prow = 0, pcnt = 0, slots = 0, prow8 = 0, pcnt8 = 0, slots8 = 0, first_use = 0;
     size_t pF = 0, pM = 0, flags = 0, pg_i = 0, pg_j = 0, pg_off = 0, pt_cls = 0, pt_mult = 0, grp_off = 0, grp_info = 0;
@@ -40,12 +106,45 @@ struct StepOffsets {
     int32_t pb = 0, pe = 0, cpp = 0;      // own panels [pb, pe), panels per rank
     size_t grp_off2 = 0; int64_t total1 = 0, total2 = 0; int32_t n1pp = 0, ring_tma = 4;   // multi-GPU kernel: two item streams
     int32_t lag = 1, ring_n = 3;          // phase 2 trails phase 1 by `lag` panels; panel buffers in the ring
+    // one-GPU TMA gather4 kernel (phi_step_g4_kernel): padded row lists per panel, item prefix, its own ring depth
+    size_t prow4 = 0, pcnt4 = 0, slots4 = 0, item_off = 0;
+    int64_t total_g4 = 0;
+    int32_t use_g4 = 0, ring_g4 = 4;
 };
+
+typedef CUresult (*gk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                       const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+gk_encode_tiled_fn tensor_map_encoder() {
+    static gk_encode_tiled_fn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
+        return (gk_encode_tiled_fn) p;
+    }();
+    return fn;
+}
+// 2-D FP64 tensor map over a row-major matrix of `rows` x `cols` doubles (pitch ld doubles), box = {W, 1}: the shape
+// cp.async.bulk.tensor ... tile::gather4 wants (four row coordinates per instruction)
+bool make_row_gather_map(CUtensorMap *m, double *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t W) {
+    gk_encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc) return false;
+    cuuint64_t dims[2] = { cols, rows }, strides[1] = { ld * sizeof(double) };
+    cuuint32_t box[2] = { W, 1 }, es[2] = { 1, 1 };
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 }  // namespace
 
+struct gk_plan_inputs {             // what the plan was built from (kept for gk_phi_replan)
+    int32_t n = 0, m = 0;
+    std::vector<int32_t> sire, dam, pro;
+};
+
 struct gk_phi_job {
-    gk::PhiPlan plan;
+    std::shared_ptr<gk::PhiPlan> planp = std::make_shared<gk::PhiPlan>();   // shared by the ranks of a one-process multi-GPU job
+    std::shared_ptr<gk_plan_inputs> inputs;
     gk_opts opts{};
     int device = 0;
     int rank = 0, world = 1;
@@ -58,10 +157,14 @@ struct gk_phi_job {
     bool peer_ipc[gk::kMaxShards][2] = {};
     bool peers_set = false;
     double *dvec[2] = { nullptr, nullptr };           // self kinship per class (full length, replicated)
+    double *dvec_peer[gk::kMaxShards][2] = {};        // one-process multi-GPU: the other ranks' replicas (written by the diagonal kernel)
+    int n_dvec_peer = 0;
     int64_t dvec_len = 0;
     double *ring = nullptr;
     double *zero_row = nullptr;
     int use_tma = 0;                  // step kernel: 0 = warp-autonomous LDGSTS (one GPU), 1 = TMA phase 1 (multi-GPU; GK_STEP_KERNEL=tma|ldgsts)
+    int g4_min_k = 0;                 // GK_G4_MIN_K: smallest previous-cut matrix the gather kernel is used for (tests force 32)
+    int use_g4 = 0;                   // one GPU: TMA gather4 phase 1 + L2-direct phase 2 (default; GK_STEP_KERNEL=g4|ldgsts|tma)
     int full_rows = 0;                // phase 2 evaluates every tile J and stores only the own rows (multi-GPU; GK_FULL_ROWS=1 forces it)
     int lag_env = 0, ring_env = 0, lag_scale_pct = 100;   // tuning overrides (GK_LAG, GK_RING, GK_LAG_PCT)
     double *out = nullptr;            // result rows; single GPU: aliases the buffer the last step does not use
@@ -79,6 +182,7 @@ struct gk_phi_job {
     int32_t nact = 0, nchunks = 0;
     int64_t nblocks_expand = 0;
     double *scratch = nullptr;
+    unsigned long long *prof = nullptr;   // GK_PROF=1: role cycle counters of the gather4 step kernel, summed over the steps
     std::vector<cudaEvent_t> ev;      // start / end events of every step (2g, 2g+1); 0, 1: the final expansion
     int64_t device_bytes = 0;
     int64_t launches = 0;
@@ -93,17 +197,19 @@ void destroy(gk_phi_job *j) {
     for (int q = 0; q < gk::kMaxShards; q++)
         for (int p = 0; p < 2; p++)
             if (j->peer_ipc[q][p] && j->peer[q][p]) cudaIpcCloseMemHandle(j->peer[q][p]);
-    for (int p = 0; p < 2; p++) { if (j->buf[p]) cudaFree(j->buf[p]); if (j->dvec[p]) cudaFree(j->dvec[p]); }
-    if (j->ring) cudaFree(j->ring);
-    if (j->zero_row) cudaFree(j->zero_row);
-    if (j->out_own) cudaFree(j->out_own);
-    if (j->gloc) cudaFree(j->gloc);
-    if (j->partials) cudaFree(j->partials);
-    if (j->scratch) cudaFree(j->scratch);
-    if (j->sums_dev) cudaFree(j->sums_dev);
+    if (j->stream) cudaStreamSynchronize(j->stream);     // nothing of this job may still run when its blocks go back to the cache
+    for (int p = 0; p < 2; p++) { pool_free(j->buf[p]); pool_free(j->dvec[p]); }
+    pool_free(j->ring);
+    pool_free(j->zero_row);
+    pool_free(j->out_own);
+    pool_free(j->gloc);
+    pool_free(j->partials);
+    pool_free(j->scratch);
+    pool_free(j->prof);
+    pool_free(j->sums_dev);
     if (j->sums_host) cudaFreeHost(j->sums_host);
-    if (j->ints) cudaFree(j->ints);
-    if (j->counters) cudaFree(j->counters);
+    pool_free(j->ints);
+    pool_free(j->counters);
     for (cudaEvent_t e : j->ev) cudaEventDestroy(e);
     if (j->own_stream && j->stream) cudaStreamDestroy(j->stream);
     delete j;
@@ -139,7 +245,7 @@ void panel_range(int np, int rank, int world, int32_t *pb, int32_t *pe, int32_t 
 
 gk::RowTable row_table(const gk_phi_job *j, int g) {
     gk::RowTable t{};
-    const gk::StepPlan &S = j->plan.steps[g];
+    const gk::StepPlan &S = j->planp->steps[g];
     const int cpp = j->off[g].cpp;
     t.n = j->world;
     for (int q = 0; q < gk::kMaxShards; q++) {
@@ -153,6 +259,204 @@ gk::RowTable row_table(const gk_phi_job *j, int g) {
 
 }  // namespace
 
+// The plan arrays of a job (this rank's view), flattened into one int32 arena (every array 16-byte aligned); fills the
+// offsets in j->off / j->off_*.  Returns the number of completion counters the step kernels need.
+static size_t build_arena(gk_phi_job *j, std::vector<int32_t> &arena) {
+    gk::PhiPlan &P = *j->planp;
+    const int G = P.G;
+    arena.clear();
+    // ---- plan arrays: one int32 arena (every array 16-byte aligned) -------------------------
+    auto push = [&](const std::vector<int32_t> &v) {
+        size_t o = arena.size();
+        arena.insert(arena.end(), v.begin(), v.end());
+        while (arena.size() % 4) arena.push_back(0);
+        return o;
+    };
+    size_t ncount = 0;
+    j->off_flags0 = push(P.steps[0].flags);
+    for (int g = 1; g < G; g++) {
+        gk::StepPlan &S = P.steps[g];
+        StepOffsets &o = j->off[g];
+        o.pF = push(S.pF); o.pM = push(S.pM); o.flags = push(S.flags);
+        o.prow = push(S.prow); o.pcnt = push(S.pcnt); o.slots = push(S.slots);
+        o.prow8 = push(S.prow8); o.pcnt8 = push(S.pcnt8); o.slots8 = push(S.slots8);
+        o.first_use = push(S.first_use);
+        o.pg_i = push(S.pg_i); o.pg_j = push(S.pg_j); o.pg_off = push(S.pg_off);
+        o.pt_cls = push(S.pt_cls); o.pt_mult = push(S.pt_mult);
+        o.npatch = (int32_t) S.pg_i.size();
+        // work queue of the own panels: phase 2 trails phase 1 by `lag` panels: P1(s), P2(s - lag), ...
+        const int ncb = (int) ((S.Kpad_prev + gk::kCB - 1) / gk::kCB);
+        std::vector<int64_t> goff(1, 0);
+        std::vector<int32_t> ginfo;
+        auto add = [&](int phase, int panel) {
+            const int64_t items = phase == 1 ? ncb : (j->full_rows ? S.np : panel + 1);
+            ginfo.push_back(panel | ((phase - 1) << 30));
+            goff.push_back(goff.back() + items);
+        };
+        // The resident warps work on a window of ~nwarps consecutive queue items: phase 2 of a panel
+        // should start only after that many items have been dealt since its phase 1 ended.
+        {
+            const int64_t nwarps = (int64_t) gk::step_grid() * gk::kStepWarps;
+            int lag = (int) ((nwarps * j->lag_scale_pct / 100 + ncb - 1) / ncb);
+            lag = std::max(1, std::min(lag, (int) gk::kRingMax - 2));
+            if (j->lag_env > 0) lag = std::min(j->lag_env, (int) gk::kRingMax - 1);
+            o.lag = lag;
+            o.ring_n = j->ring_env > 0 ? std::max(lag + 1, std::min(j->ring_env, (int) gk::kRingMax)) : lag + 2;
+        }
+        for (int s = o.pb; s < o.pe + o.lag; s++) {
+            if (s < o.pe) add(1, s);
+            if (s - o.lag >= o.pb) add(2, s - o.lag);
+        }
+        o.ngroups = (int32_t) ginfo.size();
+        o.total_items = goff.back();
+        std::vector<int32_t> g32(goff.size() * 2);
+        std::memcpy(g32.data(), goff.data(), goff.size() * 8);
+        o.grp_off = push(g32); o.grp_info = push(ginfo);
+        {   // multi-GPU kernel (phi_step_tma_kernel): phase-1 items = 8 classes x 256 columns, phase-2 items = one tile
+            const int ncb256 = (int) ((S.Kpad_prev + gk::kP1Cols - 1) / gk::kP1Cols);
+            o.n1pp = (gk::kPanel / gk::kP1Classes) * ncb256;
+            o.total1 = (int64_t) (o.pe - o.pb) * o.n1pp;
+            std::vector<int64_t> goff2(1, 0);
+            for (int s = o.pb; s < o.pe; s++) goff2.push_back(goff2.back() + (j->full_rows ? S.np : s + 1));
+            o.total2 = goff2.back();
+            std::vector<int32_t> g32b(goff2.size() * 2);
+            std::memcpy(g32b.data(), goff2.data(), goff2.size() * 8);
+            o.grp_off2 = push(g32b);
+            o.ring_tma = j->ring_env > 0 ? std::max(2, std::min(j->ring_env, (int) gk::kRingMax)) : 4;
+            if (j->use_tma) o.ring_n = o.ring_tma;
+        }
+        // ---- one-GPU TMA gather4 kernel: per panel the distinct parent rows padded to a multiple of four with the
+        //      matrix's all-zero row (index Kpad_prev), which also is the staged row of an unknown parent ----------
+        o.use_g4 = (j->use_g4 && tensor_map_encoder() && S.Kpad_prev >= (j->g4_min_k > 0 ? j->g4_min_k : 8192)) ? 1 : 0;   // small cuts: the warp-autonomous kernel has less fixed cost
+        if (o.use_g4) {
+            const int zero_row = (int) S.Kpad_prev;
+            const int nu = 2 * S.np;                                   // units of 16 classes
+            std::vector<int32_t> prow4((size_t) nu * gk::kG4RowsMax, -1), pcnt4((size_t) nu, 0), slots4((size_t) S.Kpad, 0);
+            std::vector<int64_t> ioff((size_t) nu + 1, 0);
+            std::vector<int32_t> stamp((size_t) S.Kpad_prev + 1, -1), slot_of((size_t) S.Kpad_prev + 1, 0);
+            for (int u = 0; u < nu; u++) {
+                // distinct parent rows of the unit's 16 classes (an unknown parent = the matrix's all-zero row)
+                int n = 0;
+                int32_t rows[34], rf[16], rm[16];
+                for (int i = 0; i < 16; i++)
+                    for (int q = 0; q < 2; q++) {
+                        int32_t r = q ? S.pM[u * 16 + i] : S.pF[u * 16 + i];
+                        if (r < 0) r = zero_row;
+                        if (stamp[r] != u) { stamp[r] = u; slot_of[r] = n; rows[n++] = r; }
+                        (q ? rm : rf)[i] = slot_of[r];          // index into rows[]
+                    }
+                // Staged position of every row.  The consumer reads, per 128-bit shared load, the father (or mother) rows of
+                // 8 consecutive classes at the same column: conflict-free when those 8 staged positions are distinct mod 8
+                // (rows are an odd number of 16-byte units apart).  Greedy colouring with 8 colours over the four groups
+                // (classes 0-7 / 8-15, father / mother), colours balanced so that position = colour + 8 * k fits the stage.
+                const int W = n * (512 + 2) * 8 <= gk::kG4StageBytes ? 512 : 256;
+                const int cap = gk::kG4StageBytes / ((W + 2) * 8);
+                int load[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, colour[34], pos[34];
+                for (int r = 0; r < n; r++) {
+                    unsigned forbidden = 0;
+                    for (int g4 = 0; g4 < 4; g4++) {
+                        const int32_t *par = (g4 & 1) ? rm : rf;
+                        const int i0 = (g4 >> 1) * 8;
+                        bool member = false;
+                        for (int i = i0; i < i0 + 8; i++) if (par[i] == r) member = true;
+                        if (!member) continue;
+                        for (int i = i0; i < i0 + 8; i++) if (par[i] < r) forbidden |= 1u << colour[par[i]];
+                    }
+                    int best = -1;
+                    for (int pass = 0; pass < 2 && best < 0; pass++)
+                        for (int c = 0; c < 8; c++) {
+                            if (c + 8 * load[c] >= cap) continue;                  // no free position of this colour
+                            if (pass == 0 && (forbidden >> c & 1u)) continue;
+                            if (best < 0 || load[c] < load[best]) best = c;
+                        }
+                    colour[r] = best; pos[r] = best + 8 * load[best]; load[best]++;
+                }
+                int npos = 0;
+                for (int r = 0; r < n; r++) { prow4[(size_t) u * gk::kG4RowsMax + pos[r]] = rows[r]; npos = std::max(npos, pos[r] + 1); }
+                for (int q = 0; q < npos; q++) {                                     // unused positions: -1 (not copied)
+                    bool used = false;
+                    for (int r = 0; r < n; r++) if (pos[r] == q) used = true;
+                    if (!used) prow4[(size_t) u * gk::kG4RowsMax + q] = -1;
+                }
+                for (int i = 0; i < 16; i++) slots4[u * 16 + i] = pos[rf[i]] | (pos[rm[i]] << 8);
+                pcnt4[u] = npos | (n << 8) | ((W == 512 ? 1 : 0) << 16);
+                const int p = u >> 1;
+                ioff[u + 1] = ioff[u] + (p >= o.pb && p < o.pe ? (S.Kpad_prev + W - 1) / W : 0);
+            }
+            o.total_g4 = ioff[nu];
+            std::vector<int32_t> i32(ioff.size() * 2);
+            std::memcpy(i32.data(), ioff.data(), ioff.size() * 8);
+            o.prow4 = push(prow4); o.pcnt4 = push(pcnt4); o.slots4 = push(slots4); o.item_off = push(i32);
+            const int64_t panel_bytes = S.Kpad_prev * gk::kPanel * 8;
+            int rn = (int) std::max<int64_t>(2, std::min<int64_t>(12, ((int64_t) 104 << 20) / panel_bytes));   // half of a slot is written on average (rows some tile J <= I reads)
+            if (j->ring_env > 0) rn = std::max(2, std::min(j->ring_env, (int) gk::kRingMax));
+            o.ring_g4 = rn;
+            o.ring_n = rn;
+        }
+        o.done = ncount; ncount += 2 * (size_t) S.np + 4;      // + the 8-byte aligned phase-2 queue counter
+        ncount = (ncount + 1) / 2 * 2;
+    }
+    j->off_final_cls = push(P.final_cls);
+    j->off_final_ind = push(P.final_ind);
+    // result rows of this shard and, for the expansion kernel, its caller entries grouped by class
+    {
+        const int64_t Kl = P.steps[G - 1].K;
+        std::vector<int32_t> cnt((size_t) Kl + 1, 0), cact, coff(1, 0), cmem;
+        if (!P.single_cut) {
+            for (int64_t i = j->row0; i < j->row1; i++) cnt[P.final_cls[i] + 1]++;
+            for (int64_t c = 0; c < Kl; c++) if (cnt[c + 1] > 0) { cact.push_back((int32_t) c); coff.push_back(coff.back() + cnt[c + 1]); }
+            std::vector<int32_t> slot((size_t) Kl, -1), w(coff.begin(), coff.end() - 1);
+            for (size_t a = 0; a < cact.size(); a++) slot[cact[a]] = (int32_t) a;
+            cmem.assign((size_t) (j->row1 - j->row0), 0);
+            for (int64_t i = j->row0; i < j->row1; i++) cmem[w[slot[P.final_cls[i]]]++] = (int32_t) i;
+        }
+        j->nact = (int32_t) cact.size();
+        j->nchunks = (int32_t) ((P.m + gk::kExpandCols - 1) / gk::kExpandCols);
+        j->off_cact = push(cact); j->off_coff = push(coff); j->off_cmem = push(cmem);
+        j->nblocks_expand = P.single_cut ? 1 : (int64_t) j->nact * j->nchunks;
+    }
+    return ncount;
+}
+
+// Everything of a job that follows from (plan, rank, world): kernel choice, panel ranges, result rows, NVLink statistics.
+static void configure_job(gk_phi_job *j) {
+    j->row_bytes = j->remote_row_bytes = 0;
+    // a rank of a multi-GPU job evaluates every tile J and stores only its own rows; RANKED jobs (rounding order
+    // fixed by rank) must keep J <= I and store the mirror tile into the rows of J's owner instead
+    j->full_rows = (j->world > 1 && !j->planp->ranked) ? 1 : 0;
+    j->use_tma = j->world > 1 ? 1 : 0;
+    j->use_g4 = j->world > 1 ? 0 : 1;
+    if (const char *e = std::getenv("GK_STEP_KERNEL")) { j->use_tma = (e[0] == 't') ? 1 : 0; j->use_g4 = (e[0] == 'g' && j->world == 1) ? 1 : 0; }
+    if (j->world > 1 && j->planp->ranked) j->use_tma = 1;      // only that kernel stores mirror tiles into a peer's rows
+    if (const char *e = std::getenv("GK_FULL_ROWS")) if (e[0] == '1' && !j->planp->ranked) j->full_rows = 1;
+    if (const char *e = std::getenv("GK_G4_MIN_K")) j->g4_min_k = std::atoi(e);
+    if (const char *e = std::getenv("GK_LAG")) j->lag_env = std::atoi(e);
+    if (const char *e = std::getenv("GK_RING")) j->ring_env = std::atoi(e);
+    if (const char *e = std::getenv("GK_LAG_PCT")) j->lag_scale_pct = std::max(1, std::atoi(e));
+    const int G = j->planp->G;
+    j->off.assign(G, StepOffsets{});
+    for (int g = 0; g < G; g++)
+        panel_range(j->planp->steps[g].np, j->rank, j->world, &j->off[g].pb, &j->off[g].pe, &j->off[g].cpp);
+    gk_shard_rows(j->planp->m, j->rank, j->world, &j->row0, &j->row1);
+    // rows of the previous matrix this rank's panels read, and how many of them live on a peer (NVLink)
+    for (int g = 1; g < G; g++) {
+        const gk::StepPlan &S = j->planp->steps[g];
+        const StepOffsets &o = j->off[g];
+        const int64_t rps = (int64_t) j->off[g - 1].cpp * gk::kPanel;
+        std::vector<int32_t> stamp((size_t) std::max<int64_t>(S.K_prev, 1), -1);
+        const int unit = j->use_tma ? gk::kSub : gk::kPanel;          // classes whose parent rows are staged together
+        for (int p = o.pb * gk::kPanel / unit; p < o.pe * gk::kPanel / unit; p++)
+            for (int i = p * unit; i < (p + 1) * unit; i++)
+                for (int q = 0; q < 2; q++) {
+                    const int32_t r = q ? S.pM[i] : S.pF[i];
+                    if (r < 0 || stamp[r] == p) continue;
+                    stamp[r] = p;
+                    j->row_bytes += 8 * S.Kpad_prev;
+                    if (r / rps != j->rank) j->remote_row_bytes += 8 * S.Kpad_prev;
+                }
+    }
+}
+
 extern "C" {
 
 const char *gk_last_error(void) { return g_err.c_str(); }
@@ -160,7 +464,7 @@ int32_t gk_abi_version(void) { return GK_ABI_VERSION; }
 
 void *gk_host_alloc(uint64_t bytes) {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
         cudaGetLastError();
         g_err = "cudaHostAlloc failed";
         return nullptr;
@@ -168,6 +472,11 @@ void *gk_host_alloc(uint64_t bytes) {
     return p;
 }
 void gk_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+void gk_cache_release(void) {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    pool_drop(-1);
+}
 
 int32_t gk_childless(int32_t n, const int32_t *sire, const int32_t *dam, int32_t *out) {
     if (n < 0 || (n > 0 && (!sire || !dam))) { g_err = "bad argument"; return -GK_ERR_ARG; }
@@ -266,44 +575,18 @@ int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, c
     if (j->opts.world > gk::kMaxShards) { delete j; return fail(GK_ERR_ARG, "world > 8 shards"); }
     if (j->opts.rank < 0 || j->opts.rank >= j->opts.world) { delete j; return fail(GK_ERR_ARG, "rank outside [0, world)"); }
     j->rank = j->opts.rank; j->world = j->opts.world;
-    if (!gk::build_phi_plan(n, sire, dam, m, pro, j->opts.compress, j->opts.order, j->world, j->plan)) {
-        int code = j->plan.error_code == 2 ? GK_ERR_INDEX : GK_ERR_ARG;
-        std::string msg = j->plan.error;
+    if (n > 0 && m > 0 && sire && dam && pro) {
+        j->inputs = std::make_shared<gk_plan_inputs>();
+        j->inputs->n = n; j->inputs->m = m;
+        j->inputs->sire.assign(sire, sire + n); j->inputs->dam.assign(dam, dam + n); j->inputs->pro.assign(pro, pro + m);
+    }
+    if (!gk::build_phi_plan(n, sire, dam, m, pro, j->opts.compress, j->opts.order, j->world, *j->planp)) {
+        int code = j->planp->error_code == 2 ? GK_ERR_INDEX : GK_ERR_ARG;
+        std::string msg = j->planp->error;
         delete j;
         return fail(code, msg);
     }
-    // a rank of a multi-GPU job evaluates every tile J and stores only its own rows; RANKED jobs (rounding order
-    // fixed by rank) must keep J <= I and store the mirror tile into the rows of J's owner instead
-    j->full_rows = (j->world > 1 && !j->plan.ranked) ? 1 : 0;
-    j->use_tma = j->world > 1 ? 1 : 0;
-    if (const char *e = std::getenv("GK_STEP_KERNEL")) j->use_tma = (e[0] == 't') ? 1 : 0;
-    if (j->world > 1 && j->plan.ranked) j->use_tma = 1;      // only that kernel stores mirror tiles into a peer's rows
-    if (const char *e = std::getenv("GK_FULL_ROWS")) if (e[0] == '1' && !j->plan.ranked) j->full_rows = 1;
-    if (const char *e = std::getenv("GK_LAG")) j->lag_env = std::atoi(e);
-    if (const char *e = std::getenv("GK_RING")) j->ring_env = std::atoi(e);
-    if (const char *e = std::getenv("GK_LAG_PCT")) j->lag_scale_pct = std::max(1, std::atoi(e));
-    const int G = j->plan.G;
-    j->off.assign(G, StepOffsets{});
-    for (int g = 0; g < G; g++)
-        panel_range(j->plan.steps[g].np, j->rank, j->world, &j->off[g].pb, &j->off[g].pe, &j->off[g].cpp);
-    gk_shard_rows(j->plan.m, j->rank, j->world, &j->row0, &j->row1);
-    // rows of the previous matrix this rank's panels read, and how many of them live on a peer (NVLink)
-    for (int g = 1; g < G; g++) {
-        const gk::StepPlan &S = j->plan.steps[g];
-        const StepOffsets &o = j->off[g];
-        const int64_t rps = (int64_t) j->off[g - 1].cpp * gk::kPanel;
-        std::vector<int32_t> stamp((size_t) std::max<int64_t>(S.K_prev, 1), -1);
-        const int unit = j->use_tma ? gk::kSub : gk::kPanel;          // classes whose parent rows are staged together
-        for (int p = o.pb * gk::kPanel / unit; p < o.pe * gk::kPanel / unit; p++)
-            for (int i = p * unit; i < (p + 1) * unit; i++)
-                for (int q = 0; q < 2; q++) {
-                    const int32_t r = q ? S.pM[i] : S.pF[i];
-                    if (r < 0 || stamp[r] == p) continue;
-                    stamp[r] = p;
-                    j->row_bytes += 8 * S.Kpad_prev;
-                    if (r / rps != j->rank) j->remote_row_bytes += 8 * S.Kpad_prev;
-                }
-    }
+    configure_job(j);
     *job = j;
     return GK_OK;
 }
@@ -315,100 +598,20 @@ int gk_phi_upload(gk_phi_job *j) {
     if (rc) return rc;
     std::call_once(g_cfg_once, [] { g_cfg_err = gk::configure_kernels(); });
     if (g_cfg_err != cudaSuccess) return cuda_fail(g_cfg_err, "kernel configuration (is this an sm_100 device?)");
-    gk::PhiPlan &P = j->plan;
+    gk::PhiPlan &P = *j->planp;
     const int G = P.G;
     if (j->opts.stream) j->stream = (cudaStream_t) j->opts.stream;
     else { GK_CUDA(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking)); j->own_stream = true; }
 
-    // ---- plan arrays: one int32 arena (every array 16-byte aligned) -------------------------
     std::vector<int32_t> arena;
-    auto push = [&](const std::vector<int32_t> &v) {
-        size_t o = arena.size();
-        arena.insert(arena.end(), v.begin(), v.end());
-        while (arena.size() % 4) arena.push_back(0);
-        return o;
-    };
-    size_t ncount = 0;
-    j->off_flags0 = push(P.steps[0].flags);
-    for (int g = 1; g < G; g++) {
-        gk::StepPlan &S = P.steps[g];
-        StepOffsets &o = j->off[g];
-        o.pF = push(S.pF); o.pM = push(S.pM); o.flags = push(S.flags);
-        o.prow = push(S.prow); o.pcnt = push(S.pcnt); o.slots = push(S.slots);
-        o.prow8 = push(S.prow8); o.pcnt8 = push(S.pcnt8); o.slots8 = push(S.slots8);
-        o.first_use = push(S.first_use);
-        o.pg_i = push(S.pg_i); o.pg_j = push(S.pg_j); o.pg_off = push(S.pg_off);
-        o.pt_cls = push(S.pt_cls); o.pt_mult = push(S.pt_mult);
-        o.npatch = (int32_t) S.pg_i.size();
-        // work queue of the own panels: phase 2 trails phase 1 by `lag` panels: P1(s), P2(s - lag), ...
-        const int ncb = (int) ((S.Kpad_prev + gk::kCB - 1) / gk::kCB);
-        std::vector<int64_t> goff(1, 0);
-        std::vector<int32_t> ginfo;
-        auto add = [&](int phase, int panel) {
-            const int64_t items = phase == 1 ? ncb : (j->full_rows ? S.np : panel + 1);
-            ginfo.push_back(panel | ((phase - 1) << 30));
-            goff.push_back(goff.back() + items);
-        };
-        // The resident warps work on a window of ~nwarps consecutive queue items: phase 2 of a panel
-        // should start only after that many items have been dealt since its phase 1 ended.
-        {
-            const int64_t nwarps = (int64_t) gk::step_grid() * gk::kStepWarps;
-            int lag = (int) ((nwarps * j->lag_scale_pct / 100 + ncb - 1) / ncb);
-            lag = std::max(1, std::min(lag, (int) gk::kRingMax - 2));
-            if (j->lag_env > 0) lag = std::min(j->lag_env, (int) gk::kRingMax - 1);
-            o.lag = lag;
-            o.ring_n = j->ring_env > 0 ? std::max(lag + 1, std::min(j->ring_env, (int) gk::kRingMax)) : lag + 2;
-        }
-        for (int s = o.pb; s < o.pe + o.lag; s++) {
-            if (s < o.pe) add(1, s);
-            if (s - o.lag >= o.pb) add(2, s - o.lag);
-        }
-        o.ngroups = (int32_t) ginfo.size();
-        o.total_items = goff.back();
-        std::vector<int32_t> g32(goff.size() * 2);
-        std::memcpy(g32.data(), goff.data(), goff.size() * 8);
-        o.grp_off = push(g32); o.grp_info = push(ginfo);
-        {   // multi-GPU kernel (phi_step_tma_kernel): phase-1 items = 8 classes x 256 columns, phase-2 items = one tile
-            const int ncb256 = (int) ((S.Kpad_prev + gk::kP1Cols - 1) / gk::kP1Cols);
-            o.n1pp = (gk::kPanel / gk::kP1Classes) * ncb256;
-            o.total1 = (int64_t) (o.pe - o.pb) * o.n1pp;
-            std::vector<int64_t> goff2(1, 0);
-            for (int s = o.pb; s < o.pe; s++) goff2.push_back(goff2.back() + (j->full_rows ? S.np : s + 1));
-            o.total2 = goff2.back();
-            std::vector<int32_t> g32b(goff2.size() * 2);
-            std::memcpy(g32b.data(), goff2.data(), goff2.size() * 8);
-            o.grp_off2 = push(g32b);
-            o.ring_tma = j->ring_env > 0 ? std::max(2, std::min(j->ring_env, (int) gk::kRingMax)) : 4;
-            if (j->use_tma) o.ring_n = o.ring_tma;
-        }
-        o.done = ncount; ncount += 2 * (size_t) S.np;
-    }
-    j->off_final_cls = push(P.final_cls);
-    j->off_final_ind = push(P.final_ind);
-    // result rows of this shard and, for the expansion kernel, its caller entries grouped by class
-    {
-        const int64_t Kl = P.steps[G - 1].K;
-        std::vector<int32_t> cnt((size_t) Kl + 1, 0), cact, coff(1, 0), cmem;
-        if (!P.single_cut) {
-            for (int64_t i = j->row0; i < j->row1; i++) cnt[P.final_cls[i] + 1]++;
-            for (int64_t c = 0; c < Kl; c++) if (cnt[c + 1] > 0) { cact.push_back((int32_t) c); coff.push_back(coff.back() + cnt[c + 1]); }
-            std::vector<int32_t> slot((size_t) Kl, -1), w(coff.begin(), coff.end() - 1);
-            for (size_t a = 0; a < cact.size(); a++) slot[cact[a]] = (int32_t) a;
-            cmem.assign((size_t) (j->row1 - j->row0), 0);
-            for (int64_t i = j->row0; i < j->row1; i++) cmem[w[slot[P.final_cls[i]]]++] = (int32_t) i;
-        }
-        j->nact = (int32_t) cact.size();
-        j->nchunks = (int32_t) ((P.m + gk::kExpandCols - 1) / gk::kExpandCols);
-        j->off_cact = push(cact); j->off_coff = push(coff); j->off_cmem = push(cmem);
-        j->nblocks_expand = P.single_cut ? 1 : (int64_t) j->nact * j->nchunks;
-    }
+    const size_t ncount = build_arena(j, arena);
     j->ints_count = arena.size();
-    GK_CUDA(cudaMalloc(&j->ints, std::max<size_t>(arena.size(), 4) * sizeof(int32_t)));
+    GK_CUDA(pool_alloc_t(&j->ints, std::max<size_t>(arena.size(), 4) * sizeof(int32_t), j->device));
     GK_CUDA(cudaMemcpyAsync(j->ints, arena.data(), arena.size() * sizeof(int32_t), cudaMemcpyHostToDevice, j->stream));
     GK_CUDA(cudaStreamSynchronize(j->stream));
     j->device_bytes += (int64_t) arena.size() * 4;
     j->counters_count = std::max<size_t>(ncount, 1);
-    GK_CUDA(cudaMalloc(&j->counters, j->counters_count * sizeof(int32_t)));
+    GK_CUDA(pool_alloc_t(&j->counters, j->counters_count * sizeof(int32_t), j->device));
 
     // ---- matrices: two ping-pong buffers holding the own rows of each cut's class matrix --------
     int64_t need[2] = { 0, 0 };
@@ -416,7 +619,7 @@ int gk_phi_upload(gk_phi_job *j) {
     for (int g = 0; g < G; g++) {
         const gk::StepPlan &S = P.steps[g];
         const int64_t rows = (int64_t) (j->off[g].pe - j->off[g].pb) * gk::kPanel;
-        need[g & 1] = std::max(need[g & 1], rows * S.Kpad);
+        need[g & 1] = std::max(need[g & 1], rows * S.Kpad + S.Kpad);       // + the all-zero row the gather4 kernel addresses as row Kpad
         if (g + 1 < G) max_prev = std::max(max_prev, S.Kpad);
         dlen = std::max(dlen, (int64_t) j->off[g].cpp * gk::kPanel * j->world);
     }
@@ -425,7 +628,7 @@ int gk_phi_upload(gk_phi_job *j) {
     if (j->world == 1) need[out_buf] = std::max(need[out_buf], mm);
     for (int p = 0; p < 2; p++) {
         need[p] = std::max<int64_t>(need[p], 32);
-        cudaError_t e = cudaMalloc(&j->buf[p], (size_t) need[p] * sizeof(double));
+        cudaError_t e = pool_alloc_t(&j->buf[p], (size_t) need[p] * sizeof(double), j->device);
         if (e != cudaSuccess) {
             cudaGetLastError();
             char msg[256];
@@ -438,24 +641,25 @@ int gk_phi_upload(gk_phi_job *j) {
     }
     if (j->world == 1) { j->out = j->buf[out_buf]; j->peers_set = true; }
     else {
-        GK_CUDA(cudaMalloc(&j->out_own, (size_t) std::max<int64_t>(mm, 1) * sizeof(double)));
+        GK_CUDA(pool_alloc_t(&j->out_own, (size_t) std::max<int64_t>(mm, 1) * sizeof(double), j->device));
         j->out = j->out_own;
         const int64_t gl = (int64_t) std::max(j->nact, 1) * P.steps[G - 1].Kpad;
-        GK_CUDA(cudaMalloc(&j->gloc, (size_t) gl * sizeof(double)));
+        GK_CUDA(pool_alloc_t(&j->gloc, (size_t) gl * sizeof(double), j->device));
         j->device_bytes += (mm + gl) * 8;
     }
     j->dvec_len = dlen;
-    for (int p = 0; p < 2; p++) { GK_CUDA(cudaMalloc(&j->dvec[p], (size_t) dlen * sizeof(double))); j->device_bytes += dlen * 8; }
+    for (int p = 0; p < 2; p++) { GK_CUDA(pool_alloc_t(&j->dvec[p], (size_t) dlen * sizeof(double), j->device)); j->device_bytes += dlen * 8; }
     int64_t ring_doubles = 32;
     for (int g = 1; g < G; g++) ring_doubles = std::max(ring_doubles, (int64_t) j->off[g].ring_n * P.steps[g].Kpad_prev * gk::kPanel);
-    GK_CUDA(cudaMalloc(&j->ring, (size_t) ring_doubles * sizeof(double)));
-    GK_CUDA(cudaMalloc(&j->zero_row, gk::kP1Cols * sizeof(double)));
+    GK_CUDA(pool_alloc_t(&j->ring, (size_t) ring_doubles * sizeof(double), j->device));
+    GK_CUDA(pool_alloc_t(&j->zero_row, gk::kP1Cols * sizeof(double), j->device));
     GK_CUDA(cudaMemsetAsync(j->zero_row, 0, gk::kP1Cols * sizeof(double), j->stream));
     j->device_bytes += ring_doubles * 8;
-    GK_CUDA(cudaMalloc(&j->partials, (size_t) std::max<int64_t>(j->nblocks_expand, 1) * 2 * sizeof(double)));
-    GK_CUDA(cudaMalloc(&j->scratch, 2 * 256 * sizeof(double)));
+    GK_CUDA(pool_alloc_t(&j->partials, (size_t) std::max<int64_t>(j->nblocks_expand, 1) * 2 * sizeof(double), j->device));
+    GK_CUDA(pool_alloc_t(&j->scratch, 2 * 256 * sizeof(double), j->device));
     j->device_bytes += j->nblocks_expand * 16;
-    GK_CUDA(cudaMalloc(&j->sums_dev, 2 * sizeof(double)));
+    GK_CUDA(pool_alloc_t(&j->sums_dev, 2 * sizeof(double), j->device));
+    if (const char *e = std::getenv("GK_PROF")) if (e[0] == '1') GK_CUDA(pool_alloc_t(&j->prof, 16 * sizeof(unsigned long long), j->device));
     GK_CUDA(cudaHostAlloc(&j->sums_host, 2 * sizeof(double), cudaHostAllocDefault));
     j->ev.resize(2 * (G + 1));
     for (auto &e : j->ev) GK_CUDA(cudaEventCreate(&e));
@@ -507,7 +711,7 @@ int gk_phi_peers_ready(gk_phi_job *j) {
     return GK_OK;
 }
 int gk_phi_dvec(gk_phi_job *j, int32_t step, void **dev, int64_t *chunk_doubles, int64_t *total_doubles) {
-    if (!j || !j->uploaded || step < 0 || step >= j->plan.G) return fail(GK_ERR_ARG, "bad step");
+    if (!j || !j->uploaded || step < 0 || step >= j->planp->G) return fail(GK_ERR_ARG, "bad step");
     if (dev) *dev = j->dvec[step & 1];
     if (chunk_doubles) *chunk_doubles = (int64_t) j->off[step].cpp * gk::kPanel;
     if (total_doubles) *total_doubles = (int64_t) j->off[step].cpp * gk::kPanel * j->world;
@@ -517,7 +721,7 @@ int gk_phi_dvec(gk_phi_job *j, int32_t step, void **dev, int64_t *chunk_doubles,
 // Same-process emulation of the all-gather (several ranks' jobs on ONE GPU, one stream): copy the
 // chunk rank `src` owns of the self-kinship vector of cut `step` into this job's replica.
 int gk_phi_dvec_copy_from(gk_phi_job *j, gk_phi_job *src, int32_t step) {
-    if (!j || !src || !j->uploaded || !src->uploaded || step < 0 || step >= j->plan.G) return fail(GK_ERR_ARG, "bad argument");
+    if (!j || !src || !j->uploaded || !src->uploaded || step < 0 || step >= j->planp->G) return fail(GK_ERR_ARG, "bad argument");
     if (j == src) return GK_OK;
     const int64_t chunk = (int64_t) j->off[step].cpp * gk::kPanel;
     GK_CUDA(cudaMemcpyAsync(j->dvec[step & 1] + src->rank * chunk, src->dvec[step & 1] + src->rank * chunk,
@@ -533,7 +737,7 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     if (!j) return fail(GK_ERR_ARG, "null job");
     if (!j->uploaded) return fail(GK_ERR_STATE, "gk_phi_run_step before gk_phi_upload");
     if (!j->peers_set) return fail(GK_ERR_STATE, "peer buffers are not set (gk_phi_ipc_open / gk_phi_set_peer, gk_phi_peers_ready)");
-    gk::PhiPlan &P = j->plan;
+    gk::PhiPlan &P = *j->planp;
     if (g < 0 || g >= P.G) return fail(GK_ERR_ARG, "bad step");
     GK_CUDA(cudaSetDevice(j->device));
     cudaStream_t st = j->stream;
@@ -541,6 +745,7 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     const StepOffsets &o = j->off[g];
     if (g == 0) {
         GK_CUDA(cudaMemsetAsync(j->counters, 0, j->counters_count * sizeof(int32_t), st));
+        if (j->prof) GK_CUDA(cudaMemsetAsync(j->prof, 0, 16 * sizeof(unsigned long long), st));
         j->launches = 0;
         if (P.single_cut) { j->steps_done = 1; return GK_OK; }
         // own rows of the founders' matrix
@@ -577,16 +782,32 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     d.panel_begin = o.pb; d.panel_end = o.pe;
     d.full_rows = j->full_rows;
     { const char *e = std::getenv("GK_OUT_POLICY"); d.out_policy = e ? std::atoi(e) : 0; }
-    { const char *e = std::getenv("GK_DEBUG_NOWAIT"); d.debug_nowait = (e && e[0] == '1') ? 1 : 0; }
+    { const char *e = std::getenv("GK_DEBUG_NOWAIT"); d.debug_nowait = e ? std::atoi(e) : 0; }
     GK_CUDA(cudaEventRecord(j->ev[2 * g], st));
     d.grp_off2 = reinterpret_cast<const int64_t *>(j->ints + o.grp_off2);
     d.total1 = o.total1; d.total2 = o.total2; d.n1pp = o.n1pp;
     d.ncb256 = (int32_t) ((S.Kpad_prev + gk::kP1Cols - 1) / gk::kP1Cols);
-    if (j->use_tma) GK_CUDA(gk::launch_step_tma(d, st));
+    if (o.use_g4) {
+        double *prev = j->buf[(g - 1) & 1];
+        GK_CUDA(cudaMemsetAsync(prev + S.Kpad_prev * S.Kpad_prev, 0, (size_t) S.Kpad_prev * sizeof(double), st));   // row Kpad_prev := 0
+        CUtensorMap m128, m64;
+        if (!make_row_gather_map(&m128, prev, (uint64_t) S.Kpad_prev + 1, (uint64_t) S.Kpad_prev, (uint64_t) S.Kpad_prev, 130) ||
+            !make_row_gather_map(&m64, prev, (uint64_t) S.Kpad_prev + 1, (uint64_t) S.Kpad_prev, (uint64_t) S.Kpad_prev, 66))
+            return fail(GK_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+        d.prow4 = j->ints + o.prow4; d.pcnt4 = j->ints + o.pcnt4; d.slots4 = j->ints + o.slots4;
+        d.item_off = reinterpret_cast<const int64_t *>(j->ints + o.item_off);
+        d.total_g4 = o.total_g4;
+        d.prof = j->prof;
+        { const char *e = std::getenv("GK_CHUNK2"); d.chunk2 = e ? std::atoi(e) : 0; }
+        d.queue2 = reinterpret_cast<unsigned long long *>(j->counters + ((o.done + 2 * (size_t) S.np + 1) / 2 * 2));
+        GK_CUDA(gk::launch_step_g4(d, &m128, &m64, st));
+    } else if (j->use_tma) GK_CUDA(gk::launch_step_tma(d, st));
     else GK_CUDA(gk::launch_step(d, st));
     gk::DiagDev q{};
     q.prev = d.prev; q.out = row_table(j, g); q.ld_prev = d.ld_prev; q.ld_new = d.ld_new;
     q.dprev = j->dvec[(g - 1) & 1]; q.dnew = j->dvec[g & 1];
+    q.n_peer = j->n_dvec_peer;
+    for (int r = 0; r < j->n_dvec_peer; r++) q.dnew_peer[r] = j->dvec_peer[r][g & 1];
     q.pF = d.pF; q.pM = d.pM; q.flags = j->ints + o.flags;
     q.c_begin = (int32_t) std::min<int64_t>(S.K, (int64_t) o.pb * gk::kPanel);
     q.c_end = (int32_t) std::min<int64_t>(S.K, (int64_t) o.pe * gk::kPanel);
@@ -602,7 +823,7 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
 // Final expansion to the caller's proband order + the fused phiMean partial sums of the own rows.
 int gk_phi_finish(gk_phi_job *j) {
     if (!j || !j->uploaded) return fail(GK_ERR_STATE, "job not uploaded");
-    gk::PhiPlan &P = j->plan;
+    gk::PhiPlan &P = *j->planp;
     const int G = P.G;
     if (j->steps_done < G) return fail(GK_ERR_STATE, "gk_phi_finish before the last gk_phi_run_step");
     GK_CUDA(cudaSetDevice(j->device));
@@ -639,7 +860,7 @@ int gk_phi_run(gk_phi_job *j) {
     if (!j) return fail(GK_ERR_ARG, "null job");
     if (!j->uploaded) return fail(GK_ERR_STATE, "gk_phi_run before gk_phi_upload");
     if (j->world > 1) return fail(GK_ERR_STATE, "a sharded job is driven step by step (gk_phi_run_step + the all-gather of gk_phi_dvec)");
-    gk::PhiPlan &P = j->plan;
+    gk::PhiPlan &P = *j->planp;
     if (j->opts.verbose) {
         // same text as lib/compute.cpp:662-676
         for (int g = 0; g < P.G; g++) std::printf("Cut size %d/%d: %d\n", g + 1, P.G, (int) P.steps[g].cut_size);
@@ -663,7 +884,7 @@ int gk_phi_mean(gk_phi_job *j, double *sum_all, double *sum_diag, double *mean) 
     const double total = j->sums_host[0], diag = j->sums_host[1];
     if (sum_all) *sum_all = total;
     if (sum_diag) *sum_diag = diag;
-    const double n = (double) j->plan.m;
+    const double n = (double) j->planp->m;
     // geneakit/compute.py:131-132 (with world > 1 these are this shard's partial sums: the driver
     // all-reduces sum_all / sum_diag across ranks and applies the same formula)
     if (mean) *mean = (total - diag) / (n * n - n);
@@ -674,7 +895,7 @@ int gk_phi_copy_out(gk_phi_job *j, double *host_out) {
     if (!j || !j->ran) return fail(GK_ERR_STATE, "gk_phi_copy_out before gk_phi_run");
     if (!host_out) return fail(GK_ERR_ARG, "null output");
     GK_CUDA(cudaSetDevice(j->device));
-    const size_t bytes = (size_t) (j->row1 - j->row0) * j->plan.m * sizeof(double);
+    const size_t bytes = (size_t) (j->row1 - j->row0) * j->planp->m * sizeof(double);
     GK_CUDA(cudaMemcpyAsync(host_out, j->out, bytes, cudaMemcpyDeviceToHost, j->stream));
     GK_CUDA(cudaStreamSynchronize(j->stream));
     return GK_OK;
@@ -684,7 +905,7 @@ int gk_phi_copy_rows(gk_phi_job *j, int64_t row_begin, int64_t nrows, double *ho
     if (!j || !j->ran) return fail(GK_ERR_STATE, "gk_phi_copy_rows before gk_phi_run");
     if (!host_out || row_begin < j->row0 || nrows < 0 || row_begin + nrows > j->row1) return fail(GK_ERR_ARG, "rows outside this job's block");
     GK_CUDA(cudaSetDevice(j->device));
-    GK_CUDA(cudaMemcpyAsync(host_out, j->out + (row_begin - j->row0) * (int64_t) j->plan.m, (size_t) nrows * j->plan.m * sizeof(double),
+    GK_CUDA(cudaMemcpyAsync(host_out, j->out + (row_begin - j->row0) * (int64_t) j->planp->m, (size_t) nrows * j->planp->m * sizeof(double),
                             cudaMemcpyDeviceToHost, j->stream));
     GK_CUDA(cudaStreamSynchronize(j->stream));
     return GK_OK;
@@ -693,13 +914,13 @@ int gk_phi_copy_rows(gk_phi_job *j, int64_t row_begin, int64_t nrows, double *ho
 int gk_phi_device_result(gk_phi_job *j, double **dev, int64_t *ld) {
     if (!j || !j->uploaded) return fail(GK_ERR_STATE, "job not uploaded");
     if (dev) *dev = j->out;
-    if (ld) *ld = j->plan.m;
+    if (ld) *ld = j->planp->m;
     return GK_OK;
 }
 
 int gk_phi_get_stats(gk_phi_job *j, gk_phi_stats *s) {
     if (!j || !s) return fail(GK_ERR_ARG, "null argument");
-    const gk::PhiPlan &P = j->plan;
+    const gk::PhiPlan &P = *j->planp;
     std::memset(s, 0, sizeof *s);
     s->n_cuts = P.G; s->n_steps = P.G - 1; s->compressed = P.compressed; s->ranked = P.ranked;
     s->tile = gk::kPanel; s->m = P.m;
@@ -730,12 +951,12 @@ int gk_phi_get_stats(gk_phi_job *j, gk_phi_stats *s) {
 
 int gk_phi_cut_sizes(gk_phi_job *j, int32_t *sizes, int32_t cap) {
     if (!j) return fail(GK_ERR_ARG, "null job");
-    for (int g = 0; g < j->plan.G && g < cap; g++) sizes[g] = (int32_t) j->plan.steps[g].cut_size;
+    for (int g = 0; g < j->planp->G && g < cap; g++) sizes[g] = (int32_t) j->planp->steps[g].cut_size;
     return GK_OK;
 }
 int gk_phi_class_sizes(gk_phi_job *j, int32_t *sizes, int32_t cap) {
     if (!j) return fail(GK_ERR_ARG, "null job");
-    for (int g = 0; g < j->plan.G && g < cap; g++) sizes[g] = (int32_t) j->plan.steps[g].K;
+    for (int g = 0; g < j->planp->G && g < cap; g++) sizes[g] = (int32_t) j->planp->steps[g].K;
     return GK_OK;
 }
 
@@ -743,8 +964,8 @@ int gk_phi_step_times(gk_phi_job *j, float *ms, int32_t cap) {
     if (!j || !j->ran) return fail(GK_ERR_STATE, "no run recorded");
     int rc = gk_phi_sync(j);
     if (rc) return rc;
-    const int G = j->plan.G;
-    if (j->plan.single_cut) return GK_OK;
+    const int G = j->planp->G;
+    if (j->planp->single_cut) return GK_OK;
     for (int g = 1; g < G && g - 1 < cap; g++) GK_CUDA(cudaEventElapsedTime(&ms[g - 1], j->ev[2 * g], j->ev[2 * g + 1]));
     if (G - 1 < cap) GK_CUDA(cudaEventElapsedTime(&ms[G - 1], j->ev[0], j->ev[1]));   // expansion + mean
     return GK_OK;
@@ -752,7 +973,7 @@ int gk_phi_step_times(gk_phi_job *j, float *ms, int32_t cap) {
 
 int gk_phi_step_bytes(gk_phi_job *j, int64_t *bytes, int32_t cap) {
     if (!j || !bytes) return fail(GK_ERR_ARG, "null argument");
-    const gk::PhiPlan &P = j->plan;
+    const gk::PhiPlan &P = *j->planp;
     for (int g = 1; g < P.G && g - 1 < cap; g++) {
         const gk::StepPlan &S = P.steps[g], &Sp = P.steps[g - 1];
         bytes[g - 1] = 8 * (S.P_cls * Sp.K + S.K * S.K - S.kept_cls * S.kept_cls);
@@ -763,8 +984,8 @@ int gk_phi_step_bytes(gk_phi_job *j, int64_t *bytes, int32_t cap) {
 }
 
 int gk_phi_step_view(gk_phi_job *j, int32_t step, gk_step_view *v) {
-    if (!j || !v || step < 0 || step >= j->plan.G) return fail(GK_ERR_ARG, "bad step");
-    const gk::PhiPlan &P = j->plan;
+    if (!j || !v || step < 0 || step >= j->planp->G) return fail(GK_ERR_ARG, "bad step");
+    const gk::PhiPlan &P = *j->planp;
     const gk::StepPlan &S = P.steps[step];
     std::memset(v, 0, sizeof *v);
     v->K = S.K; v->Kpad = S.Kpad; v->K_prev = S.K_prev; v->Kpad_prev = S.Kpad_prev;
@@ -779,19 +1000,212 @@ int gk_phi_step_view(gk_phi_job *j, int32_t step, gk_step_view *v) {
 }
 int gk_phi_final_view(gk_phi_job *j, const int32_t **cls, const int32_t **ind, int64_t *K_last) {
     if (!j) return fail(GK_ERR_ARG, "null job");
-    if (cls) *cls = j->plan.final_cls.data();
-    if (ind) *ind = j->plan.final_ind.data();
-    if (K_last) *K_last = j->plan.steps[j->plan.G - 1].K;
+    if (cls) *cls = j->planp->final_cls.data();
+    if (ind) *ind = j->planp->final_ind.data();
+    if (K_last) *K_last = j->planp->steps[j->planp->G - 1].K;
+    return GK_OK;
+}
+
+int gk_phi_debug_prof(gk_phi_job *j, uint64_t *out16) {
+    if (!j || !j->uploaded || !out16) return fail(GK_ERR_ARG, "bad argument");
+    std::memset(out16, 0, 16 * sizeof(uint64_t));
+    if (!j->prof) return GK_OK;
+    GK_CUDA(cudaSetDevice(j->device));
+    GK_CUDA(cudaStreamSynchronize(j->stream));
+    GK_CUDA(cudaMemcpy(out16, j->prof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return GK_OK;
 }
 
 void gk_phi_free(gk_phi_job *j) { destroy(j); }
 
+// Plan again from the inputs the job was created with and copy the plan arrays to the device once more (same sizes:
+// the planner is deterministic).  With gk_phi_run it is one "flattened arrays on the host -> matrix resident in HBM"
+// pass (SURVEY 8d's t_phi) on buffers that are already allocated.
+int gk_phi_replan(gk_phi_job *j) {
+    if (!j || !j->uploaded) return fail(GK_ERR_STATE, "gk_phi_replan before gk_phi_upload");
+    if (!j->inputs) return fail(GK_ERR_STATE, "the job does not hold its inputs");
+    auto fresh = std::make_shared<gk::PhiPlan>();
+    const gk_plan_inputs &in = *j->inputs;
+    if (!gk::build_phi_plan(in.n, in.sire.data(), in.dam.data(), in.m, in.pro.data(), j->opts.compress, j->opts.order, j->world, *fresh))
+        return fail(GK_ERR_ARG, fresh->error);
+    j->planp = fresh;
+    return gk_phi_reupload(j);
+}
+
+// (multi-GPU jobs of one process share the plan: rank 0 replans, the others take its plan and upload their own view)
+int gk_phi_reupload(gk_phi_job *j) {
+    if (!j || !j->uploaded) return fail(GK_ERR_STATE, "gk_phi_reupload before gk_phi_upload");
+    GK_CUDA(cudaSetDevice(j->device));
+    configure_job(j);
+    std::vector<int32_t> arena;
+    build_arena(j, arena);
+    if (arena.size() != j->ints_count) return fail(GK_ERR_STATE, "internal: the plan changed size between two plans of the same inputs");
+    GK_CUDA(cudaMemcpyAsync(j->ints, arena.data(), arena.size() * sizeof(int32_t), cudaMemcpyHostToDevice, j->stream));
+    GK_CUDA(cudaStreamSynchronize(j->stream));       // the arena is a local
+    j->ran = false; j->steps_done = 0;
+    return GK_OK;
+}
+
+// Another rank of the same job in THIS process: shares the plan (planned once for `world` ranks) and the inputs.
+int gk_phi_clone_rank(gk_phi_job *src, int32_t rank, int32_t device, gk_phi_job **out) {
+    if (!src || !out) return fail(GK_ERR_ARG, "null argument");
+    if (rank < 0 || rank >= src->world) return fail(GK_ERR_ARG, "rank outside [0, world)");
+    gk_phi_job *j = new gk_phi_job();
+    j->planp = src->planp; j->inputs = src->inputs; j->opts = src->opts;
+    j->opts.rank = rank; j->opts.device = device; j->opts.stream = nullptr;
+    j->rank = rank; j->world = src->world;
+    configure_job(j);
+    *out = j;
+    return GK_OK;
+}
+
+// ---- one process, several GPUs (SURVEY 8b "Threading", 5 "distributed backend"): what gen.phi() itself uses ----------
+// The ranks of the sharded algorithm (DESIGN.md "Multi-GPU") as jobs of THIS process, one per device, one plan shared by
+// all of them.  Peers are plain pointers (cudaDeviceEnablePeerAccess), the self-kinship vector is written into every
+// rank's replica by the diagonal kernel, and the barrier between cuts is an event every stream waits on -- no host
+// thread per GPU, no NCCL.  The result rows go from every GPU straight into the caller's one m x m host matrix, in parallel.
+namespace {
+
+struct MultiPhi {
+    std::vector<gk_phi_job *> jobs;
+    std::vector<cudaEvent_t> cut_done;       // one per rank
+    bool virtual_devices = false;             // tests on a one-GPU box: every rank on the current device, ONE stream
+    ~MultiPhi() {
+        for (size_t q = 0; q < cut_done.size(); q++) if (cut_done[q]) { cudaSetDevice(jobs[q]->device); cudaEventDestroy(cut_done[q]); }
+        for (gk_phi_job *j : jobs) destroy(j);
+    }
+};
+
+int multi_devices(const gk_opts *o, int *ndev, bool *virt) {
+    int want = (o && o->world > 1 && o->rank < 0) ? o->world : 0;
+    if (!want) if (const char *e = std::getenv("GENEAKIT_GPUS")) want = std::atoi(e);
+    *virt = false;
+    if (const char *e = std::getenv("GENEAKIT_VIRTUAL_DEVICES")) *virt = e[0] == '1';
+    if (want <= 1) { *ndev = 1; return GK_OK; }
+    if (want > gk::kMaxShards) return fail(GK_ERR_ARG, "at most 8 GPUs");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return fail(GK_ERR_CUDA, "no usable CUDA device; geneakit_b200 has no CPU fallback"); }
+    if (!*virt && want > count) want = count;         // use the GPUs the box has
+    *ndev = want;
+    return GK_OK;
+}
+
+int multi_phi(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, const int32_t *pro, double *out,
+              double *mean_or_null, const gk_opts *opts, int ndev, bool virt) {
+    MultiPhi M;
+    M.virtual_devices = virt;
+    gk_opts o{};
+    if (opts) std::memcpy(&o, opts, std::min<size_t>(sizeof(gk_opts), (size_t) std::max(0, opts->struct_size)));
+    else { o.compress = -1; o.order = -1; }
+    int base = 0;
+    if (virt) GK_CUDA(cudaGetDevice(&base));
+    o.struct_size = sizeof(gk_opts); o.world = ndev; o.rank = 0; o.device = virt ? base : 0; o.stream = nullptr;
+    gk_phi_job *j0 = nullptr;
+    int rc = gk_phi_plan(n, sire, dam, m, pro, &o, &j0);
+    if (rc) return rc;
+    M.jobs.push_back(j0);
+    for (int q = 1; q < ndev; q++) {
+        gk_phi_job *jq = nullptr;
+        rc = gk_phi_clone_rank(j0, q, virt ? base : q, &jq);
+        if (rc) return rc;
+        M.jobs.push_back(jq);
+    }
+    if (virt) {          // one stream for every rank: persistent kernels of different ranks must never be co-scheduled on one GPU
+        rc = gk_phi_upload(j0);
+        if (rc) return rc;
+        for (int q = 1; q < ndev; q++) { M.jobs[q]->opts.stream = j0->stream; rc = gk_phi_upload(M.jobs[q]); if (rc) return rc; }
+    } else {
+        // allocation + H2D of the plan on every device at once
+        std::vector<int> rcs(ndev, 0);
+        std::vector<std::string> errs(ndev);
+        std::vector<std::thread> th;
+        for (int q = 0; q < ndev; q++)
+            th.emplace_back([&, q] { rcs[q] = gk_phi_upload(M.jobs[q]); if (rcs[q]) errs[q] = g_err; });
+        for (auto &t : th) t.join();
+        for (int q = 0; q < ndev; q++) if (rcs[q]) return fail(rcs[q], errs[q]);
+        for (int q = 0; q < ndev; q++) {
+            GK_CUDA(cudaSetDevice(M.jobs[q]->device));
+            for (int p = 0; p < ndev; p++) {
+                if (p == q) continue;
+                cudaError_t e = cudaDeviceEnablePeerAccess(M.jobs[p]->device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess (the GPUs of a multi-GPU job must be NVLink / P2P peers)");
+            }
+        }
+    }
+    for (int q = 0; q < ndev; q++) {
+        gk_phi_job *j = M.jobs[q];
+        int k = 0;
+        for (int p = 0; p < ndev; p++) {
+            if (p == q) continue;
+            j->peer[p][0] = M.jobs[p]->buf[0]; j->peer[p][1] = M.jobs[p]->buf[1];
+            j->dvec_peer[k][0] = M.jobs[p]->dvec[0]; j->dvec_peer[k][1] = M.jobs[p]->dvec[1];
+            k++;
+        }
+        j->n_dvec_peer = k;
+        j->peers_set = true;
+    }
+    M.cut_done.assign(ndev, nullptr);
+    for (int q = 0; q < ndev; q++) {
+        GK_CUDA(cudaSetDevice(M.jobs[q]->device));
+        GK_CUDA(cudaEventCreateWithFlags(&M.cut_done[q], cudaEventDisableTiming));
+    }
+    const int G = j0->planp->G;
+    if (o.verbose) {
+        for (int g = 0; g < G; g++) std::printf("Cut size %d/%d: %d\n", g + 1, G, (int) j0->planp->steps[g].cut_size);
+        std::printf("Computing the kinship matrix:\n");
+    }
+    for (int g = 0; g < G; g++) {
+        for (int q = 0; q < ndev; q++) { rc = gk_phi_run_step(M.jobs[q], g); if (rc) return rc; }
+        if (!virt) {
+            // the barrier between cuts: every rank's step g (rows + self kinships written to every replica) before any step g + 1
+            for (int q = 0; q < ndev; q++) { GK_CUDA(cudaSetDevice(M.jobs[q]->device)); GK_CUDA(cudaEventRecord(M.cut_done[q], M.jobs[q]->stream)); }
+            for (int q = 0; q < ndev; q++) {
+                GK_CUDA(cudaSetDevice(M.jobs[q]->device));
+                for (int p = 0; p < ndev; p++) if (p != q) GK_CUDA(cudaStreamWaitEvent(M.jobs[q]->stream, M.cut_done[p], 0));
+            }
+        }
+    }
+    for (int q = 0; q < ndev; q++) { rc = gk_phi_finish(M.jobs[q]); if (rc) return rc; }
+    // result rows: every GPU copies its block into the caller's matrix (its own PCIe link), all at once
+    for (int q = 0; q < ndev; q++) {
+        gk_phi_job *j = M.jobs[q];
+        GK_CUDA(cudaSetDevice(j->device));
+        const size_t bytes = (size_t) (j->row1 - j->row0) * m * sizeof(double);
+        if (bytes) GK_CUDA(cudaMemcpyAsync(out + (size_t) j->row0 * m, j->out, bytes, cudaMemcpyDeviceToHost, j->stream));
+    }
+    double total = 0.0, diag = 0.0;
+    for (int q = 0; q < ndev; q++) {
+        gk_phi_job *j = M.jobs[q];
+        GK_CUDA(cudaSetDevice(j->device));
+        GK_CUDA(cudaStreamSynchronize(j->stream));
+        total += j->sums_host[0]; diag += j->sums_host[1];
+    }
+    if (!virt) {
+        // a peer may still be reading this rank's rows in its expansion: every stream is drained above before anything is freed
+    }
+    if (mean_or_null) *mean_or_null = (total - diag) / ((double) m * (double) m - (double) m);
+    if (virt) GK_CUDA(cudaSetDevice(base));
+    return GK_OK;
+}
+
+}  // namespace
+
 int gk_phi_f64(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, const int32_t *pro,
                double *out, double *mean_or_null, const gk_opts *opts) {
     if (!out) return fail(GK_ERR_ARG, "null output");
+    std::lock_guard<std::mutex> call_lock(g_call_mu);         // one call at a time
+    int ndev = 1;
+    bool virt = false;
+    int rc = multi_devices(opts, &ndev, &virt);
+    if (rc) return rc;
+    if (ndev > 1) return multi_phi(n, sire, dam, m, pro, out, mean_or_null, opts, ndev, virt);
     gk_phi_job *j = nullptr;
-    int rc = gk_phi_plan(n, sire, dam, m, pro, opts, &j);
+    gk_opts o{};
+    if (opts) std::memcpy(&o, opts, std::min<size_t>(sizeof(gk_opts), (size_t) std::max(0, opts->struct_size)));
+    else { o.device = -1; o.compress = -1; o.order = -1; }
+    o.struct_size = sizeof(gk_opts); o.rank = 0; o.world = 1;
+    rc = gk_phi_plan(n, sire, dam, m, pro, &o, &j);
     if (rc) return rc;
     rc = gk_phi_upload(j);
     if (!rc) rc = gk_phi_run(j);
@@ -806,6 +1220,8 @@ int gk_phi_f64(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, co
 int gk_gc_f64(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, const int32_t *pro,
               int32_t a, const int32_t *anc, double *out, const gk_opts *opts) {
     if (!out) return fail(GK_ERR_ARG, "null output");
+    std::lock_guard<std::mutex> call_lock(g_call_mu);         // one call at a time
+    const auto t_begin = std::chrono::steady_clock::now();
     gk::GcPlan P;
     if (!gk::build_gc_plan(n, sire, dam, m, pro, a, anc, P))
         return fail(P.error_code == 2 ? GK_ERR_INDEX : GK_ERR_ARG, P.error);
@@ -817,37 +1233,87 @@ int gk_gc_f64(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, con
     if (!st) { GK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); own = true; }
     double *V[2] = { nullptr, nullptr }, *dout = nullptr;
     int32_t *ints = nullptr;
+    cudaEvent_t ev[2] = { nullptr, nullptr };
     std::vector<int32_t> arena;
     struct Off { size_t p0, p1, so, sc; };
     std::vector<Off> off(P.G);
     auto push = [&](const std::vector<int32_t> &v) { size_t o = arena.size(); arena.insert(arena.end(), v.begin(), v.end()); return o; };
+    int64_t member_rows = 0;
     for (int g = 0; g < P.G; g++) {
         off[g].p0 = push(P.steps[g].p0); off[g].p1 = push(P.steps[g].p1);
         off[g].so = push(P.steps[g].seed_off); off[g].sc = push(P.steps[g].seed_col);
+        member_rows += P.steps[g].rows;
     }
     const size_t orow = push(P.row_of);
     auto cleanup = [&]() {
-        if (V[0]) cudaFree(V[0]); if (V[1]) cudaFree(V[1]); if (dout) cudaFree(dout); if (ints) cudaFree(ints);
+        cudaStreamSynchronize(st);
+        pool_free(V[0]); pool_free(V[1]); pool_free(dout); pool_free(ints);
+        if (ev[0]) cudaEventDestroy(ev[0]);
+        if (ev[1]) cudaEventDestroy(ev[1]);
         if (own) cudaStreamDestroy(st);
     };
 #define GK_CUDA_C(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int c_ = cuda_fail(e_, #call); cleanup(); return c_; } } while (0)
-    const size_t vbytes = (size_t) std::max<int64_t>(P.max_rows, 1) * P.ld * sizeof(double);
-    GK_CUDA_C(cudaMalloc(&V[0], vbytes));
-    GK_CUDA_C(cudaMalloc(&V[1], vbytes));
-    GK_CUDA_C(cudaMalloc(&dout, (size_t) m * a * sizeof(double)));
-    GK_CUDA_C(cudaMalloc(&ints, std::max<size_t>(arena.size(), 1) * sizeof(int32_t)));
-    GK_CUDA_C(cudaMemcpyAsync(ints, arena.data(), arena.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    for (int g = 0; g < P.G; g++) {
-        gk::GcStepDev d{};
-        d.Vprev = V[(g + 1) & 1]; d.Vnew = V[g & 1]; d.ld = P.ld; d.rows = P.steps[g].rows;
-        d.p0 = ints + off[g].p0; d.p1 = ints + off[g].p1; d.seed_off = ints + off[g].so; d.seed_col = ints + off[g].sc;
-        GK_CUDA_C(gk::launch_gc_step(d, st));
+    // The ancestor columns are independent, so a wide ancestor list is propagated block of columns by block
+    // of columns: the two live matrices (largest cut x block) plus the m x block result must fit the HBM that is free.
+    size_t free_b = 0, total_b = 0;
+    GK_CUDA_C(cudaMemGetInfo(&free_b, &total_b));
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        for (const PoolBlock &b : g_pool_free) if (b.dev == dev) free_b += b.bytes;      // cached blocks are dropped on demand
     }
-    GK_CUDA_C(gk::launch_gc_gather(V[(P.G - 1) & 1], P.ld, ints + orow, dout, m, a, st));
-    GK_CUDA_C(cudaMemcpyAsync(out, dout, (size_t) m * a * sizeof(double), cudaMemcpyDeviceToHost, st));
-    GK_CUDA_C(cudaStreamSynchronize(st));
+    const int64_t rows_live = 2 * std::max<int64_t>(P.max_rows, 1) + m;
+    int64_t budget = (int64_t) (0.85 * (double) free_b) - (int64_t) arena.size() * 4;
+    if (const char *e = std::getenv("GK_GC_BUDGET_MB")) budget = (int64_t) std::atoll(e) << 20;   // tests: force several blocks
+    int64_t blk = budget / (rows_live * 8) / 16 * 16;
+    if (blk < 16) { cleanup(); return fail(GK_ERR_OOM, "out of device memory: gen.gc needs 16 ancestor columns x (2 x largest cut + probands) doubles of HBM"); }
+    blk = std::min<int64_t>(blk, P.ld);
+    const size_t vbytes = (size_t) std::max<int64_t>(P.max_rows, 1) * blk * sizeof(double);
+    GK_CUDA_C(pool_alloc_t(&V[0], vbytes, dev));
+    GK_CUDA_C(pool_alloc_t(&V[1], vbytes, dev));
+    GK_CUDA_C(pool_alloc_t(&dout, (size_t) m * blk * sizeof(double), dev));
+    GK_CUDA_C(pool_alloc_t(&ints, std::max<size_t>(arena.size(), 1) * sizeof(int32_t), dev));
+    GK_CUDA_C(cudaEventCreate(&ev[0]));
+    GK_CUDA_C(cudaEventCreate(&ev[1]));
+    GK_CUDA_C(cudaMemcpyAsync(ints, arena.data(), arena.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    double kernel_ms = 0.0;
+    int64_t nblocks = 0, launches = 0;
+    for (int64_t c0 = 0; c0 < a; c0 += blk, nblocks++) {
+        const int64_t w = std::min<int64_t>(blk, a - c0);            // ancestor columns [c0, c0 + w) of this block
+        const int64_t ldb = (w + 15) / 16 * 16;
+        GK_CUDA_C(cudaEventRecord(ev[0], st));
+        for (int g = 0; g < P.G; g++) {
+            gk::GcStepDev d{};
+            d.Vprev = V[(g + 1) & 1]; d.Vnew = V[g & 1]; d.ld = ldb; d.rows = P.steps[g].rows;
+            d.p0 = ints + off[g].p0; d.p1 = ints + off[g].p1; d.seed_off = ints + off[g].so; d.seed_col = ints + off[g].sc;
+            d.col0 = (int32_t) c0; d.ncols = (int32_t) w;
+            GK_CUDA_C(gk::launch_gc_step(d, st));
+        }
+        GK_CUDA_C(gk::launch_gc_gather(V[(P.G - 1) & 1], ldb, ints + orow, dout, m, w, st));
+        GK_CUDA_C(cudaEventRecord(ev[1], st));
+        launches += P.G + 1;
+        GK_CUDA_C(cudaMemcpy2DAsync(out + c0, (size_t) a * sizeof(double), dout, (size_t) w * sizeof(double), (size_t) w * sizeof(double),
+                                    (size_t) m, cudaMemcpyDeviceToHost, st));
+        GK_CUDA_C(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        GK_CUDA_C(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+        kernel_ms += ms;
+    }
+    g_gc_stats.kernel_ms = kernel_ms;
+    g_gc_stats.algorithmic_bytes = 24 * member_rows * (int64_t) a;          // 2 parent rows read + 1 row written per member, per ancestor
+    g_gc_stats.member_rows = member_rows;
+    g_gc_stats.column_blocks = nblocks;
+    g_gc_stats.block_columns = blk;
+    g_gc_stats.kernel_launches = launches;
+    g_gc_stats.n_cuts = P.G;
     cleanup();
 #undef GK_CUDA_C
+    g_gc_stats.total_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+    return GK_OK;
+}
+
+int gk_gc_last_stats(gk_gc_stats *s) {
+    if (!s) return fail(GK_ERR_ARG, "null argument");
+    *s = g_gc_stats;
     return GK_OK;
 }
 

@@ -28,6 +28,7 @@
 // segment.  In RANKED mode (pedigrees deeper than 26 generations) the planner orders the classes
 // by descending rank, which makes "J <= I" the reference's rounding order (gk_plan.hpp).
 #include <cstdlib>
+#include <cstring>
 #include "gk_kernels.cuh"
 #include "gk_plan.hpp"
 
@@ -62,7 +63,8 @@ __device__ __forceinline__ int ld_relaxed(const int *p) {
 // Poll a completion counter.  Relaxed loads (an acquire would invalidate the whole L1 on every
 // iteration); everything read after the wait comes from L2 (bulk copies / stores to fresh lines).
 __device__ __forceinline__ void wait_count(const int *p, int target) {
-    while (ld_relaxed(p) < target) __nanosleep(100);
+    unsigned ns = 64;
+    while (ld_relaxed(p) < target) { __nanosleep(ns); if (ns < 1024) ns *= 2; }
 }
 __device__ __forceinline__ void signal_count(int *p) {
     asm volatile("red.release.gpu.global.add.s32 [%0], 1;\n" ::"l"(p) : "memory");
@@ -434,6 +436,428 @@ __global__ void __launch_bounds__(kThreadsTma, 1) phi_step_tma_kernel(const Step
     }
 }
 
+// THIRD STEP KERNEL (one GPU): the Blackwell data-movement path.  Measured on B200 (scripts/micro/gather4_bench.cu):
+// TMA tile::gather4 (four arbitrary rows of a 2-D tensor per instruction) moves 1 KB row segments at 5.4 TB/s and
+// 2 KB ones at 6.9 TB/s with nothing but 2-3 stages of shared memory in flight, no registers, no L1; reads that hit
+// L2 run at 19 TB/s, stores at 7.5 TB/s.  So:
+//
+//  PHASE 1 through the TMA engine.  An item = one PANEL (32 classes) x W columns of the previous matrix (W = 128,
+//  or 64 for the few panels with more than 48 distinct parent rows).  The producer warp issues one gather4 per four
+//  distinct parent rows (the planner pads the row list with the matrix's all-zero row, which also stands for an
+//  unknown parent) into one of kG4Stages stages, completion on the stage's mbarrier.  The consumer warp that owns
+//  the stage averages father and mother rows with lane = COLUMN (rows of a stage are packed, so a warp reading
+//  one staged row is conflict-free), transposes 16 x 32 pieces through a 4 KB scratch and stores the 128-byte
+//  half rows N^T[c][16 classes] of the L2-resident panel ring (only rows some tile J <= I will read).  The
+//  producer also does the cross-CTA bookkeeping: it waits for the ring slot to be drained (done2 of panel
+//  I - ring_n) before it loads the first item of panel I, and it publishes finished items (done1) when it
+//  recycles their stage -- one gpu-scope fence per item instead of one per warp and tile.
+//
+//  PHASE 2 straight from L2.  A warp takes a tile pair (I, J <= I): for each class j of tile J it loads the two
+//  256-byte ring rows N^T[F_j], N^T[M_j] (lane = class of the panel; ld.global.cg, L2 hits, 32 loads in flight),
+//  stores row j of tile (J, I) and, through the scratch, the transposed 128-byte pieces of the mirror tile (I, J).
+//
+// Dependencies as in the first kernel: phase 2 of panel I waits for done1[I]; phase 1 of panel I for
+// done2[I - ring_n]; every wait is on strictly earlier work and all CTAs are resident.
+constexpr int G4NS = kG4Stages, G4NC = kG4Consumers, G4P2 = kG4P2Warps;
+constexpr int kThreadsG4 = (G4NC + G4P2 + 2) * 32;        // consumers, phase-2 warps, the producer, the publisher
+constexpr int G4SCRP = 33;                                 // scratch pitch (doubles)
+constexpr int G4SCR = 16 * G4SCRP;                         // scratch doubles per warp
+constexpr size_t kStepSmemG4 = (size_t) G4NS * kG4StageBytes + (size_t) G4P2 * G4SCR * sizeof(double) + 2 * G4NS * sizeof(unsigned long long) + 64;
+
+struct alignas(64) TMap { unsigned long long v[16]; };    // CUtensorMap, opaque
+
+__device__ __forceinline__ void tma_gather4(unsigned dst, const TMap *map, int col, int4 r, unsigned bar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;\n"
+                 ::"r"(dst), "l"(map), "r"(col), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void signal_add(int *p, int v) {
+    asm volatile("fence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreadsG4, 1) phi_step_g4_kernel(const StepDev s, const __grid_constant__ TMap m128, const __grid_constant__ TMap m64) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int spub[8][2];                           // (panel, blocks) of the last 8 items issued, for the publisher
+    __shared__ volatile int ctl[G4NC + 1];               // items consumed by each consumer warp; items published
+    __shared__ volatile int p2box[G4P2][2];              // phase-2 warp -> publisher: (panel << 8 | tiles, sequence number)
+    __shared__ volatile int p2ack[G4P2];                 // sequence number the publisher has published
+    __shared__ volatile int p2live;                      // phase-2 warps still running
+    unsigned char *stages = smem_raw;
+    double *scratch = reinterpret_cast<double *>(smem_raw + (size_t) G4NS * kG4StageBytes);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(scratch + (size_t) G4P2 * G4SCR);   // full[NS], empty[NS]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x <= G4NC) ctl[threadIdx.x] = 0;
+    if (threadIdx.x < G4P2) { p2box[threadIdx.x][0] = 0; p2box[threadIdx.x][1] = 0; p2ack[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) p2live = G4P2;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < G4NS; i++) { mbar_init(smem_u32(bars + i), 1); mbar_init(smem_u32(bars + G4NS + i), G4NC); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    __shared__ double *sprev[kMaxShards];
+    if (threadIdx.x < kMaxShards) sprev[threadIdx.x] = s.prev.base[threadIdx.x];
+    __syncthreads();
+    const RowLookup prev{ sprev, s.prev.base[0], s.prev.n > 1 ? s.prev.row0[1] : 1, s.prev.n, s.ld_prev };
+    const unsigned long long pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+    // debug_nowait (timing experiments only, results are garbage): bit 0 = skip the dependency waits, bit 1 = no phase 1, bit 2 = no phase 2
+    const long long n_cta = (s.debug_nowait & 2) ? 0 : (s.total_g4 > blockIdx.x ? (s.total_g4 - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+    const long long total2 = (s.debug_nowait & 4) ? 0 : s.total2;
+    const int nblk_panel = 2 * (s.Kpad_prev / T);        // blocks (16 classes x 32 columns) of a panel = its done1 target
+
+    // item t of this launch -> (unit, column block): the units' item prefix is searched 32 entries at a time (one coalesced
+    // load per ~16 items instead of a chain of dependent loads per item)
+    struct ItemCursor {
+        int base = 0;                 // unit of the window's first entry
+        long long lo = 0, hi = 0;     // lo = item_off[base]; lane l holds hi = item_off[base + 1 + l]
+        bool loaded = false;
+    };
+    auto locate = [&](ItemCursor &c, const long long t, const int nunits, int &unit, int &cb) {
+        for (;;) {
+            if (!c.loaded) {
+                c.lo = s.item_off[c.base];
+                const int u = c.base + 1 + lane;
+                c.hi = u <= nunits ? s.item_off[u] : 0x7fffffffffffffffLL;
+                c.loaded = true;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, c.hi > t);
+            if (m) {
+                const int l = __ffs(m) - 1;
+                const long long start = l ? __shfl_sync(0xffffffffu, c.hi, l - 1) : c.lo;
+                unit = c.base + l; cb = (int) (t - start);
+                return;
+            }
+            c.base += 32; c.loaded = false;
+        }
+    };
+    const int nunits = 2 * s.np;
+
+    if (warp == G4NC + G4P2) {
+        // ============================ producer: one bulk copy per staged row ===========================
+        const long long pt0 = clock64();
+        long long p_stage = 0, p_ring = 0;
+        ItemCursor cur;
+        // descriptors are decoded two items ahead (their global loads -- prefix window, row list -- land before they are needed)
+        int dU[2] = { 0, 0 }, dcb[2] = { 0, 0 }, dn[2] = { 0, 0 }, dr0[2] = { 0, 0 }, dr1[2] = { 0, 0 };
+        auto decode = [&](const long long k, const int q) {
+            if (k >= n_cta) return;
+            int unit, cb;
+            locate(cur, blockIdx.x + k * gridDim.x, nunits, unit, cb);
+            dU[q] = unit; dcb[q] = cb; dn[q] = s.pcnt4[unit];
+            const int32_t *pr = s.prow4 + (long long) unit * kG4RowsMax;
+            dr0[q] = pr[lane]; dr1[q] = lane < kG4RowsMax - 32 ? pr[32 + lane] : -1;
+        };
+        decode(0, 0);
+        decode(1, 1);
+        int checked_panel = -1;
+#pragma unroll 1
+        for (long long k0 = 0; k0 < n_cta; k0 += 2) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const long long k = k0 + q;
+                if (k >= n_cta) break;
+                const int U = dU[q], cb = dcb[q], I = U >> 1;
+                const int npos = dn[q] & 0xFF, nrows = (dn[q] >> 8) & 0xFF;     // staged positions (some unused), rows copied
+                const int stage = (int) (k % G4NS);
+                if (lane == 0) {
+                    // the stage's previous item must have been consumed by every consumer warp, and its publication slot freed
+                    if (k >= G4NS) {
+                        const long long c0 = clock64();
+                        for (;;) {
+                            int mn = ctl[0];
+#pragma unroll
+                            for (int w = 1; w < G4NC; w++) mn = min(mn, ctl[w]);
+                            if (mn > (int) (k - G4NS) && (int) k - ctl[G4NC] < 8) break;
+                            __nanosleep(32);
+                        }
+                        p_stage += clock64() - c0;
+                    }
+                    if (I != checked_panel) {              // first item of a panel here: its ring slot must have been drained
+                        const int old = I - s.ring_n;
+                        const long long c0 = clock64();
+                        if (old >= s.panel_begin && !(s.debug_nowait & 1)) wait_count(s.done2 + old, old + 1);
+                        p_ring += clock64() - c0;
+                    }
+                }
+                checked_panel = I;
+                __syncwarp();
+                const int W = (dn[q] >> 16) ? 512 : 256;
+                const int w = min(W, s.Kpad_prev - cb * W);                    // columns of this item (a multiple of 32)
+                const unsigned full = smem_u32(bars + stage);
+                if (lane == 0) {
+                    spub[k & 7][0] = I; spub[k & 7][1] = w / T;
+                    __threadfence_block();
+                    mbar_arrive_expect_tx(full, (unsigned) (nrows * w * sizeof(double)));
+                }
+                __syncwarp();
+                const unsigned pitch = (unsigned) (W + 2) * 8u;
+                const unsigned sbase = smem_u32(stages + (size_t) stage * kG4StageBytes);
+                // one bulk copy per staged row: 4 KB (2 KB) segments -- the TMA engine spends ~105 cycles per copy whatever its size
+                if (lane < npos && dr0[q] >= 0) bulk_copy(sbase + (unsigned) lane * pitch, prev(dr0[q]) + (long long) cb * W, (unsigned) (w * sizeof(double)), full, pol_stream);
+                if (lane + 32 < npos && dr1[q] >= 0) bulk_copy(sbase + (unsigned) (lane + 32) * pitch, prev(dr1[q]) + (long long) cb * W, (unsigned) (w * sizeof(double)), full, pol_stream);
+                decode(k + 2, q);
+            }
+        }
+        if (s.prof && lane == 0) {
+            atomicAdd(s.prof + 0, (unsigned long long) (clock64() - pt0));
+            atomicAdd(s.prof + 2, (unsigned long long) p_stage); atomicAdd(s.prof + 3, (unsigned long long) p_ring);
+        }
+    } else if (warp == G4NC + G4P2 + 1) {
+        // ============================ publisher: makes consumed items visible to the other SMs =========
+        // (one gpu-scope fence per item, off the producer's and the consumers' critical paths: the consumers only bump a
+        // shared-memory counter, the release/acquire chain consumer -> counter -> this warp -> fence.gpu carries their stores)
+        // One loop iteration = snapshot of everything finished (phase-1 items consumed by all consumer warps, phase-2
+        // mailboxes), ONE fence, then the counter updates: the fence rate does not grow with the number of messages.
+        if (lane == 0) {
+            long long k = 0;                         // next phase-1 item to publish
+            int seen[G4P2];
+#pragma unroll
+            for (int w = 0; w < G4P2; w++) seen[w] = 0;
+            for (;;) {
+                const int live = p2live;
+                int mn = ctl[0];
+#pragma unroll
+                for (int w = 1; w < G4NC; w++) mn = min(mn, ctl[w]);
+                int msg[G4P2], seq[G4P2];
+                bool any = mn > (int) k;
+#pragma unroll
+                for (int w = 0; w < G4P2; w++) { seq[w] = p2box[w][1]; msg[w] = p2box[w][0]; any |= seq[w] != seen[w]; }
+                if (any) {
+                    __threadfence_block();
+                    asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+                    for (; k < mn; k++) {
+                        asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;\n" ::"l"(s.done1 + spub[k & 7][0]), "r"(spub[k & 7][1]) : "memory");
+                    }
+                    ctl[G4NC] = (int) k;
+#pragma unroll
+                    for (int w = 0; w < G4P2; w++)
+                        if (seq[w] != seen[w]) {
+                            asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;\n" ::"l"(s.done2 + (msg[w] >> 8)), "r"(msg[w] & 0xFF) : "memory");
+                            seen[w] = seq[w];
+                            p2ack[w] = seq[w];
+                        }
+                } else {
+                    if (k >= n_cta && live == 0) break;
+                    __nanosleep(32);
+                }
+            }
+        }
+    } else if (warp < G4NC) {
+        // ============================ phase-1 consumers ===============================================
+        // The stages are a FIFO: the producer runs up to kG4Stages items ahead, and ALL consumer warps work on the oldest
+        // full stage together, each on its own 32-column blocks, so loading an item overlaps with consuming the previous ones.
+        const long long ct0 = clock64();
+        long long c_wait = 0;
+        const int cls = lane & 15, par = lane >> 4;       // lane = (class of the unit, parity of the column pair)
+        // the next item, decoded one iteration ahead (its global loads fly while the current item is consumed)
+        int nU = 0, ncb = 0, nW = 0, npk = 0;
+        ItemCursor cur;
+        auto decode_next = [&](long long k) {
+            if (k >= n_cta) return;
+            locate(cur, blockIdx.x + k * gridDim.x, nunits, nU, ncb);
+            nW = (s.pcnt4[nU] >> 16) ? 512 : 256;
+            npk = s.slots4[nU * 16 + cls];
+        };
+        decode_next(0);
+        for (long long k = 0; k < n_cta; k++) {
+            const int stage = (int) (k % G4NS);
+            const unsigned S = smem_u32(stages + (size_t) stage * kG4StageBytes);
+            const unsigned full = smem_u32(bars + stage);
+            const int U = nU, cb = ncb, W = nW, pk = npk;
+            const int I = U >> 1;
+            const int w = min(W, s.Kpad_prev - cb * W);
+            const int nb64 = (w + 63) >> 6;
+            double *buf = s.ring + (long long) ((I - s.panel_begin) % s.ring_n) * s.ring_stride + (U & 1) * 16 + cls;
+            // lane = class: its father / mother rows in the stage.  Staged rows are (W + 2) * 8 bytes apart -- an odd number
+            // of 16-byte units: the 128-bit reads of 8 consecutive classes (whose rows are mostly distinct mod 8: the
+            // planner numbers them in order of first use) do not collide on a bank.
+            const unsigned pitch = (unsigned) (W + 2) * 8u;
+            const unsigned aF = S + (unsigned) (pk & 0xFF) * pitch + par * 16u, aM = S + (unsigned) ((pk >> 8) & 0xFF) * pitch + par * 16u;
+            // rows of the panel some tile J <= I reads, for this warp's (at most two) blocks of 64 columns
+            int fu[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int c = cb * W + (warp + (q >> 1) * G4NC) * 64 + (q & 1) * 32 + lane;
+                fu[q] = c < s.Kpad_prev ? s.first_use[c] : 0x7fffffff;
+            }
+            decode_next(k + 1);
+            const long long cw0 = clock64();
+            mbar_wait(full, (unsigned) ((k / G4NS) & 1));
+            c_wait += clock64() - cw0;
+#pragma unroll
+            for (int bi = 0; bi < 2; bi++) {
+                const int b = warp + bi * G4NC;
+                if (b < nb64) {
+                    const int c0 = cb * W + b * 64;
+                    const unsigned need_lo = __ballot_sync(0xffffffffu, fu[2 * bi] <= I), need_hi = __ballot_sync(0xffffffffu, fu[2 * bi + 1] <= I);
+                    double *dst = buf + (long long) c0 * T;
+                    const unsigned bF = aF + (unsigned) b * 512u, bM = aM + (unsigned) b * 512u;
+#pragma unroll
+                    for (int u0 = 0; u0 < 16; u0 += 4) {
+                        double2 x[4], y[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) { x[u] = lds_f64x2(bF + (u0 + u) * 32); y[u] = lds_f64x2(bM + (u0 + u) * 32); }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int c = 4 * (u0 + u) + 2 * par;                     // column of x[u].x inside the block
+                            const unsigned need = c < 32 ? need_lo >> c : need_hi >> (c - 32);
+                            if (need & 1u) st_hint(dst + c * T, 0.5 * (x[u].x + y[u].x), pol_keep);
+                            if (need & 2u) st_hint(dst + (c + 1) * T, 0.5 * (x[u].y + y[u].y), pol_keep);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); ctl[warp] = (int) k + 1; }
+        }
+        if (s.prof && lane == 0) { atomicAdd(s.prof + 4, (unsigned long long) (clock64() - ct0)); atomicAdd(s.prof + 5, (unsigned long long) c_wait); }
+    } else {
+        // ============================ phase-2 warps (L2 -> registers) ==================================
+        const int w2 = warp - G4NC;
+        double *scr = scratch + (size_t) w2 * G4SCR;
+        double *const out = s.out_base;
+        const long long ldn = s.ld_new;
+        const unsigned long long pol_out = s.out_policy == 0 ? pol_stream : (s.out_policy == 2 ? pol_keep : policy_evict_normal());
+        const int hi = lane >> 4, lo = lane & 15;
+        const bool nostore = (s.debug_nowait & 8) != 0;
+        // finished tiles go to the publisher warp through a shared-memory mailbox (lane 0 only): the release / acquire chain
+        // this warp -> mailbox -> publisher -> fence.gpu makes the warp's stores visible before the counter moves
+        int myseq = 0;
+        auto post = [&](const int panel, const int count) {
+            while (p2ack[w2] != myseq) __nanosleep(32);        // the previous message has been taken
+            __threadfence_block();
+            p2box[w2][0] = (panel << 8) | count;
+            __threadfence_block();
+            p2box[w2][1] = ++myseq;
+        };
+        const long long nw2 = (long long) gridDim.x * G4P2;
+        int g = 0, ready_panel = -1;
+        const long long qt0 = clock64();
+        long long q_wait = 0, q_sig = 0;
+        // tiles are dealt in chunks of kG4Chunk consecutive queue items (mostly one panel I, tiles J, J + 1, ...): one
+        // gpu-scope fence and one counter update per chunk and panel instead of one per tile
+        const int CH = s.chunk2 > 0 ? s.chunk2 : 1;
+        const long long nchunks = (total2 + CH - 1) / CH;
+        // chunks are taken from a global counter in queue order, so every phase-2 warp of the GPU works on the OLDEST panel
+        // that still has tiles (a static deal left most warps waiting for panels phase 1 had not reached yet while the
+        // ready panel's tiles sat with a few busy warps, and phase 1 stalled on the ring slot that panel occupied)
+        for (;;) {
+            long long cq = 0;
+            if (lane == 0) cq = (long long) atomicAdd(s.queue2, 1ULL);
+            cq = __shfl_sync(0xffffffffu, cq, 0);
+            if (cq >= nchunks) break;
+            int sig_panel = -1, sig_count = 0;
+            const long long q_end = (cq + 1) * CH < total2 ? (cq + 1) * CH : total2;
+            for (long long q = cq * CH; q < q_end; q++) {
+                while (q >= s.grp_off2[g + 1]) ++g;
+                const int I = s.panel_begin + g, J = (int) (q - s.grp_off2[g]);
+                const double *buf = s.ring + (long long) ((I - s.panel_begin) % s.ring_n) * s.ring_stride + lane;
+                const int pf = s.pF[J * T + lane], pm = s.pM[J * T + lane];
+                if (I != sig_panel && sig_count > 0) {    // the chunk crosses into the next panel: publish the tiles of the previous one
+                    __syncwarp();
+                    const long long s0 = clock64();
+                    if (lane == 0) post(sig_panel, sig_count);
+                    __syncwarp();
+                    q_sig += clock64() - s0;
+                    sig_count = 0;
+                }
+                sig_panel = I;
+                if (I != ready_panel) {              // phase 1 of panel I must be complete before its rows are read
+                    const long long w0 = clock64();
+                    if (lane == 0 && !s.debug_nowait) wait_count(s.done1 + I, nblk_panel);
+                    ready_panel = I;
+                    __syncwarp();
+                    q_wait += clock64() - w0;
+                }
+                double *drow = out + ((long long) J * T - s.out_row0) * ldn + I * T + lane;    // row j of tile J, columns of panel I
+                double *mrow = out + ((long long) I * T - s.out_row0) * ldn + J * T;           // row i of panel I, columns of tile J
+                if (J != I) {
+                    // Four batches of eight classes, software-pipelined over two register buffers: the loads of batch b + 1
+                    // are in flight while batch b is averaged and stored (a warp alone otherwise sits through one L2
+                    // latency per batch).  No predicates: an unknown parent reads a row of zeros.
+                    double xa[8], ya[8], xb[8], yb[8];
+                    const double *zrow = s.zero_row + lane;              // the row of an unknown parent
+                    auto issue = [&](double (&x)[8], double (&y)[8], const int bt) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int rf = __shfl_sync(0xffffffffu, pf, 8 * bt + i), rm = __shfl_sync(0xffffffffu, pm, 8 * bt + i);
+                            x[i] = __ldcg(rf >= 0 ? buf + (long long) rf * T : zrow);
+                            y[i] = __ldcg(rm >= 0 ? buf + (long long) rm * T : zrow);
+                        }
+                    };
+                    auto consume = [&](double (&x)[8], double (&y)[8], const int bt) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const double v = 0.5 * (x[i] + y[i]);
+                            if (!nostore) st_hint(drow + (long long) (8 * bt + i) * ldn, v, pol_out);
+                            scr[((8 * bt + i) & 15) * G4SCRP + lane] = v;
+                        }
+                    };
+                    // mirror of 16 rows j: rows 2p (lanes 0-15) and 2p + 1 (lanes 16-31) of panel I, columns 16h .. 16h + 15 of tile J
+                    auto mirror = [&](const int h) {
+                        __syncwarp();
+#pragma unroll
+                        for (int p0 = 0; p0 < 16; p0 += 8) {
+                            double v[8];
+#pragma unroll
+                            for (int p = 0; p < 8; p++) v[p] = scr[lo * G4SCRP + 2 * (p0 + p) + hi];
+#pragma unroll
+                            for (int p = 0; p < 8; p++) if (!nostore || v[p] == 12345.678) st_hint(mrow + (long long) (2 * (p0 + p) + hi) * ldn + 16 * h + lo, v[p], pol_out);
+                        }
+                        __syncwarp();
+                    };
+                    issue(xa, ya, 0);
+                    issue(xb, yb, 1);
+                    consume(xa, ya, 0);
+                    issue(xa, ya, 2);
+                    consume(xb, yb, 1);
+                    issue(xb, yb, 3);
+                    mirror(0);
+                    consume(xa, ya, 2);
+                    consume(xb, yb, 3);
+                    mirror(1);
+                } else {
+                    // diagonal tile (one in I + 1): V[j][i] is valid where j <= i (in RANKED mode that is the reference's grouping);
+                    // the other triangle is its mirror
+#pragma unroll 4
+                    for (int j = 0; j < T; j++) {
+                        const int rf = __shfl_sync(0xffffffffu, pf, j), rm = __shfl_sync(0xffffffffu, pm, j);
+                        const double x = rf >= 0 ? __ldcg(buf + (long long) rf * T) : 0.0, y = rm >= 0 ? __ldcg(buf + (long long) rm * T) : 0.0;
+                        const double v = 0.5 * (x + y);
+                        if (j <= lane) st_hint(drow + (long long) j * ldn, v, pol_out);
+                        if (j < lane) st_hint(mrow + (long long) lane * ldn + j, v, pol_out);
+                    }
+                }
+                sig_count++;
+            }
+            __syncwarp();
+            const long long s0 = clock64();
+            if (lane == 0 && sig_count > 0) post(sig_panel, sig_count);
+            __syncwarp();
+            q_sig += clock64() - s0;
+        }
+        __syncwarp();
+        if (lane == 0) { while (p2ack[w2] != myseq) __nanosleep(32); atomicSub((int *) &p2live, 1); }
+        if (s.prof && lane == 0) {
+            atomicAdd(s.prof + 7, (unsigned long long) (clock64() - qt0)); atomicAdd(s.prof + 8, (unsigned long long) q_wait);
+            atomicAdd(s.prof + 10, (unsigned long long) q_sig);
+        }
+    }
+}
+
 __device__ __forceinline__ double *row_ptr(const RowTable &t, int row, long long ld) {
     double *base = t.base[0];
     int r0 = 0;
@@ -453,6 +877,7 @@ __global__ void __launch_bounds__(256) phi_diag_kernel(const DiagDev d) {
         if (fl & kFlagKept) self = d.dprev[F];                      // bitwise what the reference recomputes
         else if (fl & kFlagBoth) self = 0.5 + 0.5 * row_ptr(d.prev, F, d.ld_prev)[M];
         d.dnew[c] = self;
+        for (int q = 0; q < d.n_peer; q++) d.dnew_peer[q][c] = self;
         if (fl & kFlagSingleton) row_ptr(d.out, c, d.ld_new)[c] = self;
     }
     for (int gidx = t0; gidx < d.ngroups; gidx += stride) {
@@ -624,8 +1049,10 @@ __global__ void __launch_bounds__(256) gc_step_kernel(const GcStepDev g) {
         }
     }
     __syncthreads();
-    for (int k = g.seed_off[row] + threadIdx.x; k < g.seed_off[row + 1]; k += 256)
-        g.Vnew[row * g.ld + g.seed_col[k]] = 1.0;
+    for (int k = g.seed_off[row] + threadIdx.x; k < g.seed_off[row + 1]; k += 256) {
+        const int c = g.seed_col[k] - g.col0;
+        if (c >= 0 && c < g.ncols) g.Vnew[row * g.ld + c] = 1.0;
+    }
 }
 
 __global__ void __launch_bounds__(256) gc_gather_kernel(const double *V, long long ld, const int32_t *row_of,
@@ -648,6 +1075,7 @@ cudaError_t configure_kernels() {
     if ((e = cudaFuncSetAttribute(phi_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kStepSmem))) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phi_step_kernel, kThreads, kStepSmem))) return e;
     if ((e = cudaFuncSetAttribute(phi_step_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kStepSmemTma))) return e;
+    if ((e = cudaFuncSetAttribute(phi_step_g4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kStepSmemG4))) return e;
     const char *env = getenv("GK_CTAS_PER_SM");
     if (env && atoi(env) > 0 && atoi(env) < occ) occ = atoi(env);
     g_step_grid = sms * (occ > 0 ? occ : 1);     // persistent: one wave, every CTA resident (the waits rely on it)
@@ -667,6 +1095,16 @@ cudaError_t launch_step_tma(const StepDev &s, cudaStream_t st) {
     if (s.total1 + s.total2 <= 0) return cudaSuccess;
     const long long grid = g_step_grid > 0 ? g_step_grid : 148;
     phi_step_tma_kernel<<<(unsigned) grid, kThreadsTma, kStepSmemTma, st>>>(s);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step_g4(const StepDev &s, const void *tmap128, const void *tmap64, cudaStream_t st) {
+    if (s.total_g4 + s.total2 <= 0) return cudaSuccess;
+    const long long grid = g_step_grid > 0 ? g_step_grid : 148;
+    TMap a, b;
+    memcpy(&a, tmap128, sizeof a);
+    memcpy(&b, tmap64, sizeof b);
+    phi_step_g4_kernel<<<(unsigned) grid, kThreadsG4, kStepSmemG4, st>>>(s, a, b);
     return cudaGetLastError();
 }
 

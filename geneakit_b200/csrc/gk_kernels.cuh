@@ -14,6 +14,12 @@ constexpr int kStepP1Stages = 3;     // phase-1 TMA stages (33 KB each)
 constexpr int kP1Classes = 8;        // phase-1 item: 8 classes of a panel ...
 constexpr int kP1Cols = 256;         // ... x 256 columns of the previous matrix (2 KB row segments)
 constexpr int kCB = 32;           // columns of the previous matrix per phase-1 work item
+// third step kernel (phi_step_g4_kernel, one GPU): phase 1 through TMA gather4 over a tensor map of the previous matrix
+constexpr int kG4Stages = 2;         // TMA stages (a FIFO the producer fills and all consumer warps drain together)
+constexpr int kG4Consumers = 4;      // phase-1 consumer warps
+constexpr int kG4P2Warps = 10;       // phase-2 warps (ring rows straight from L2 into registers)
+constexpr int kG4StageBytes = 20 * 514 * 8;   // 20 rows x 512 columns (pitch 514), or up to 39 rows x 256 columns (pitch 258)
+constexpr int kG4RowsMax = 40;       // distinct parent rows of a UNIT of 16 classes (<= 32) + an all-zero row, padded
 
 // Where the rows of a (possibly row-sharded) class matrix live: row r is owned by the shard q with
 // row0[q] <= r < row0[q+1] and sits at base[q] + (r - row0[q]) * ld.  Peer shards are CUDA-IPC
@@ -56,6 +62,15 @@ struct StepDev {
     int32_t full_rows;        // 0: tiles J <= I, mirror stored too; 1: every tile J, own rows only
     int32_t out_policy;       // L2 eviction priority of the stores to the new matrix: 0 evict_first, 1 normal, 2 evict_last
     int32_t debug_nowait;     // timing experiments only (GK_DEBUG_NOWAIT=1): skip the dependency waits, results are garbage
+    // phi_step_g4_kernel only
+    const int32_t *prow4;     // 2 np x kG4RowsMax: per UNIT (16 classes) its distinct parent rows, then the zero row (index Kpad_prev)
+    const int32_t *pcnt4;     // 2 np: staged positions | rows copied << 8 | (W == 512) << 16
+    const int32_t *slots4;    // Kpad: staged row of the father | staged row of the mother << 8 (the zero row for an unknown parent)
+    const int64_t *item_off;  // 2 np + 1: first phase-1 item of each unit (a unit has ceil(Kpad_prev / W) items, W = 512 or 256 columns)
+    int64_t total_g4;         // phase-1 items of this launch
+    int32_t chunk2;              // tiles per phase-2 queue grab (GK_CHUNK2, default 2)
+    unsigned long long *queue2;  // phase-2 work queue of this launch: next chunk of tiles (zeroed with the counters)
+    unsigned long long *prof; // optional (GK_PROF=1): 16 cycle counters summed over the warps of each role, see gk_phi_debug_prof
 };
 
 struct DiagDev {
@@ -63,6 +78,8 @@ struct DiagDev {
     int64_t ld_prev, ld_new;
     const double *dprev;      // self kinship per class of cut g-1 (replicated)
     double *dnew;             // self kinship per class of cut g (this launch writes [c_begin, c_end))
+    double *dnew_peer[kMaxShards];   // one-process multi-GPU jobs: the other ranks' replicas of that vector (peer stores, 8 B per class)
+    int32_t n_peer;
     const int32_t *pF, *pM, *flags;
     int32_t c_begin, c_end;   // classes whose rows this launch owns
     const int32_t *pg_i, *pg_j, *pg_off, *pt_cls, *pt_mult;
@@ -88,6 +105,9 @@ struct ExpandDev {
 int step_grid();             // CTAs of the persistent step kernel (SMs x resident CTAs)
 cudaError_t launch_step(const StepDev &s, cudaStream_t st);
 cudaError_t launch_step_tma(const StepDev &s, cudaStream_t st);
+// tmap128 / tmap64: 128-byte CUtensorMap objects over the previous matrix ((Kpad_prev + 1) rows, the last one all zero) with
+// boxes of {130, 1} and {66, 1} doubles (two more columns than an item uses: the staged rows get a bank-conflict-free pitch)
+cudaError_t launch_step_g4(const StepDev &s, const void *tmap128, const void *tmap64, cudaStream_t st);
 cudaError_t launch_diag(const DiagDev &d, cudaStream_t st);
 cudaError_t launch_init(double *G0, double *d0, const int32_t *flags, int64_t K0, int64_t Kpad0, cudaStream_t st);
 cudaError_t launch_init_rows(double *G0, double *d0, const int32_t *flags, int64_t K0, int64_t Kpad0,
@@ -108,6 +128,7 @@ struct GcStepDev {
     const int32_t *p0, *p1;  // parent row in Vprev or -1 (kept: p0 = own old row, p1 = -2)
     const int32_t *seed_off; // rows + 1 : CSR of ancestor columns equal to this individual
     const int32_t *seed_col;
+    int32_t col0, ncols;     // this launch propagates the ancestor columns [col0, col0 + ncols) (column blocks of a wide ancestor list)
 };
 cudaError_t launch_gc_step(const GcStepDev &g, cudaStream_t st);
 cudaError_t launch_gc_gather(const double *V, int64_t ld, const int32_t *row_of /*m, -1 = zero row*/,

@@ -37,7 +37,8 @@ typedef struct gk_opts {
     int32_t verbose;       /* 1: print the cut sizes / "Cut k out of n" lines of lib/compute.cpp:662-676 */
     int32_t compress;      /* -1 auto (default), 0 one matrix row per individual, 1 one row per sibship */
     int32_t order;         /* -1/1 auto: classes ordered by a locality walk; 0: sorted by parent rows (debug) */
-    int32_t rank;          /* row shard owned by this process (multi-GPU), 0 .. world-1 */
+    int32_t rank;          /* row shard owned by this process (multi-GPU), 0 .. world-1; -1 with world > 1: the one-shot
+                              entry points drive GPUs 0 .. world-1 from this process (also: environment GENEAKIT_GPUS=N) */
     int32_t world;         /* number of row shards (<= 8), 0/1 = single GPU */
     int32_t reserved0;
     void   *stream;        /* cudaStream_t to enqueue on, NULL = the library's own stream */
@@ -61,6 +62,19 @@ int gk_phi_f64(int32_t n, const int32_t *sire, const int32_t *dam,
 int gk_gc_f64(int32_t n, const int32_t *sire, const int32_t *dam,
               int32_t m, const int32_t *pro, int32_t a, const int32_t *anc,
               double *out, const gk_opts *opts);
+
+/* Timing / traffic of the last gk_gc_f64 call of this process (the benchmark's --op gc line). */
+typedef struct gk_gc_stats {
+    double  kernel_ms;           /* CUDA-event time of the propagation + gather kernels, all column blocks */
+    double  total_seconds;       /* the whole call: plan, H2D, kernels, D2H */
+    int64_t algorithmic_bytes;   /* 24 B x live members (summed over the cuts) x ancestors */
+    int64_t member_rows;         /* sum over the cuts of their members */
+    int64_t column_blocks;       /* blocks of ancestor columns the call was split into (HBM budget) */
+    int64_t block_columns;
+    int64_t kernel_launches;
+    int32_t n_cuts, reserved;
+} gk_gc_stats;
+int gk_gc_last_stats(gk_gc_stats *stats);
 
 /* Replaces get_required_memory_for_kinships (include/compute.hpp:110-111,
  * lib/compute.cpp:591-635): GB of the two largest adjacent cut matrices.  Host only.
@@ -96,6 +110,9 @@ int32_t gk_abi_version(void);
  * lib/cgeneakit.cpp:420-423); device->host copies into it run at full PCIe rate. */
 void *gk_host_alloc(uint64_t bytes);
 void  gk_host_free(void *p);
+/* The library keeps freed device buffers for the next call (allocating ~110 GB costs more than the kernels of a c4
+ * job); this returns them to the driver.  GENEAKIT_CACHE=0 disables the cache. */
+void  gk_cache_release(void);
 
 /* ---- device-resident job API: plan once, keep everything in HBM ---------------------------
  * Used by the benchmark, by phiMean-only callers that never need the matrix on the host, and
@@ -129,6 +146,13 @@ typedef struct gk_phi_stats {
 int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam,
                 int32_t m, const int32_t *pro, const gk_opts *opts, gk_phi_job **job);
 int gk_phi_upload(gk_phi_job *job);                 /* allocate HBM, copy the plan (H2D) */
+/* Plan again from the job's inputs and copy the plan to the device again, on the buffers already allocated: with
+ * gk_phi_run this is one "flattened arrays on the host -> matrix resident in HBM" pass (what the benchmark times).
+ * gk_phi_reupload only repeats the copy (ranks of a one-process multi-GPU job that share rank 0's plan). */
+int gk_phi_replan(gk_phi_job *job);
+int gk_phi_reupload(gk_phi_job *job);
+/* Another rank of `job` in the same process (shares its plan); device = CUDA ordinal for that rank. */
+int gk_phi_clone_rank(gk_phi_job *job, int32_t rank, int32_t device, gk_phi_job **out);
 int gk_phi_run(gk_phi_job *job);                    /* enqueue init + all steps + expansion; async */
 int gk_phi_sync(gk_phi_job *job);                   /* wait for the job's stream */
 int gk_phi_mean(gk_phi_job *job, double *sum_all, double *sum_diag, double *mean);
@@ -147,6 +171,10 @@ int gk_phi_step_times(gk_phi_job *job, float *ms, int32_t cap);
  * (16 B per updated cell on discrete-generation pedigrees) -- and 8*(m^2 + min(m,K)^2) for the
  * final expansion. */
 int gk_phi_step_bytes(gk_phi_job *job, int64_t *bytes, int32_t cap);
+/* GK_PROF=1 only: cycle counters of the gather4 step kernel's warp roles, summed over warps and steps of the last run:
+ * [0] producer loop, [1] its idle polls, [2] polls blocked on a stage, [3] on the ring slot; [4] phase-1 consumers,
+ * [5] of which waiting for TMA data; [7] phase-2 warps, [8] of which waiting for phase 1, [10] publishing (fence). */
+int gk_phi_debug_prof(gk_phi_job *job, uint64_t *out16);
 void gk_phi_free(gk_phi_job *job);
 
 /* ---- multi-GPU: one job per rank, the class matrices sharded by rows (= columns: they are symmetric) --
