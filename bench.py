@@ -1,18 +1,22 @@
 #!/usr/bin/env python
-"""Benchmark of the kinship hot path: gen.phi (+ fused gen.phiMean) on BASELINE.json's synthetic
-pedigrees.  One "step" = one full pass of the hot path (all generations + the final expansion)
-over one pedigree / proband list.
+"""Benchmark of the kinship hot path: gen.phi (+ fused gen.phiMean) on BASELINE.json's configurations.
+One "step" = one full pass of the hot path from the flattened pedigree arrays ON THE HOST to the m x m matrix and its
+mean resident in HBM (SURVEY.md 8d's t_phi): host planning, the copy of the plan to the device, all generations, the
+final expansion.  The buffers are allocated once, before the timed region.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c5s|tiny] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c1|c2|c5|c5s|tiny] [--op phi|gc] [--impl reference]
 
 Prints ONE JSON line (contract in the task statement): metric = kinship pairs/s, with
-`roofline` (dominant kernel, algorithmic bytes / CUDA-event time / measured HBM peak),
-`cpu_baseline` (the unmodified reference on a bounded sample of the same workload),
-`e2e` (the same metric through the host-buffer C-ABI call gk_phi_f64, copies included),
-`clocks` and `gpu_launches`.
+  `resident`     the same pass with the plan already in HBM (kernels only),
+  `roofline`     dominant kernel: algorithmic bytes / CUDA-event time / measured HBM peak,
+  `parity_check` after the timed region every rank compares result rows with an independent one-GPU job on a sub-list,
+  `cpu_baseline` the unmodified reference on a bounded sample of the same workload, all host threads,
+  `e2e`          the same metric through the host-buffer C-ABI call gk_phi_f64 (N > 1: ONE process driving the N GPUs),
+  `clocks`, `gpu_launches`.
 """
 import argparse
 import ctypes as C
+import importlib.util
 import json
 import os
 import subprocess
@@ -36,8 +40,11 @@ WORKLOADS = {
     "c5s": dict(n=1_250_000, gens=30, m=12_500, seed=5, founders=500,
                 desc="1/4-scale founder-population pedigree, 30 generations (BASELINE configs[4] shape)"),
     "tiny": dict(n=20_000, gens=8, m=1_500, seed=3, founders=None, desc="tiny synthetic (debug)"),
+    # the reference's bundled datasets, from the fixtures the unmodified reference produced (tests/golden)
+    "c1": dict(fixture="genea140", desc="genea140 bundled dataset: gen.phi(ped, pro=gen.pro(ped)) + gen.phiMean (BASELINE configs[0])"),
+    "c2": dict(fixture="genea140_pop140", desc="pop140 bundled dataset: gen.phi on the 140 probands of pop140 + gen.gc of the founders (BASELINE configs[1])"),
 }
-SAMPLE_DIV = 20   # the CPU reference runs a 1/20-width replica of the workload (same generator, same depth)
+SAMPLE_DIV = 10   # the CPU reference runs a 1/10-width replica of the synthetic workloads (same generator, same depth)
 
 
 def peaks():
@@ -78,70 +85,104 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_workload(name, div=1):
-    import geneakit_b200 as gk
+def _synth():
+    """geneakit_b200/synth.py loaded by path: numpy only, so the reference arm never loads the product library."""
+    spec = importlib.util.spec_from_file_location("gk_synth_numpy", os.path.join(ROOT, "geneakit_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def workload_arrays(name, div=1):
+    """(ids, fathers, mothers, sexes, proband ids, ancestor ids for gc) -- numpy / lists only."""
     w = WORKLOADS[name]
+    if "fixture" in w:
+        z = np.load(os.path.join(ROOT, "tests", "golden", w["fixture"] + ".npz"))
+        r = z["rows"]
+        return r[:, 0], r[:, 1], r[:, 2], r[:, 3], [int(x) for x in z["pro"]], [int(x) for x in z["anc"]], bool(z["sorted"])
+    s = _synth()
     n, m = w["n"] // div, w["m"] // div
     founders = None if w["founders"] is None else max(4, w["founders"] // div)
+    ids, f, mo, sx, offs = s.synthetic_arrays(n, w["gens"], w["seed"], founders)
+    pro = s.synthetic_probands(ids, offs, m, w["seed"])
+    anc = [int(x) for x in ids[:offs[1]][:2000]]          # gc: (up to 2000 of) the founders
+    return ids, f, mo, sx, pro, anc, True
+
+
+def make_workload(name, div=1):
+    import geneakit_b200 as gk
     t0 = time.time()
-    ped, pro = gk.synthetic_pedigree(n, w["gens"], m, seed=w["seed"], founders=founders)
+    ids, f, mo, sx, pro, _, srt = workload_arrays(name, div)
+    ped = gk.cgeneakit.load_pedigree_from_vectors(ids, f, mo, sx, srt)
     return ped, pro, time.time() - t0
 
 
-def reference_handle(ped):
-    """The same pedigree inside the unmodified reference (oracle/_ref) or, if that library was not
-    built in this tree, the C port of it (oracle/libgkoracle.so)."""
+def reference_engine():
+    """The unmodified reference (oracle/_ref) or, if that library was not built in this tree, the C port of it
+    (oracle/libgkoracle.so) -- with ALL host threads, whatever OMP_NUM_THREADS the launcher exported."""
     from oracle.api import Oracle, Reference
-    f = np.where(ped.sire >= 0, ped.ids[np.maximum(ped.sire, 0)], 0)
-    d = np.where(ped.dam >= 0, ped.ids[np.maximum(ped.dam, 0)], 0)
+    threads = os.cpu_count() or 1
     if Reference.available():
         R = Reference()
-        return "reference", R, R.genealogy(ped.ids, f, d, ped.sex, sorted=True), R.L.gkref_max_threads()
+        R.set_threads(threads)
+        return "reference", R, int(R.L.gkref_max_threads())
     O = Oracle()
-    return "port", O, O.genealogy(ped.ids, f, d, ped.sex, sorted=True), O.L.gko_max_threads()
+    O.set_threads(threads)
+    return "port", O, int(O.L.gko_max_threads())
 
 
-def cpu_sample(workload, repeats=1):
-    ped, pro, _ = make_workload(workload, SAMPLE_DIV)
-    kind, eng, h, cores = reference_handle(ped)
-    best = None
-    for _ in range(repeats):
-        t0 = time.time()
-        eng.phi(h, pro)
-        dt = time.time() - t0
-        best = dt if best is None else min(best, dt)
+def sample_text(name, div, n_ind, m):
+    w = WORKLOADS[name]
+    if "fixture" in w:
+        return "%s in full: %d individuals, %d probands, full gen.phi" % (name, n_ind, m)
+    return ("1/%d-width replica of %s: %d individuals, %d generations, %d probands, full gen.phi"
+            % (div, name, n_ind, w["gens"], m))
+
+
+def cpu_sample(name):
+    kind, eng, cores = reference_engine()
+    div = 1 if "fixture" in WORKLOADS[name] else SAMPLE_DIV
+    ids, f, mo, sx, pro, _, srt = workload_arrays(name, div)
+    h = eng.genealogy(ids, f, mo, sx, sorted=srt)
+    t0 = time.time()
+    eng.phi(h, pro)
+    dt = time.time() - t0
     m = len(pro)
-    w = WORKLOADS[workload]
-    return {"value": m * (m + 1) / 2 / best, "unit": "pairs/s", "cores": int(cores), "kind": kind,
-            "seconds": best,
-            "sample": "1/%d-width replica of %s: %d individuals, %d generations, %d probands, full gen.phi"
-                      % (SAMPLE_DIV, workload, w["n"] // SAMPLE_DIV, w["gens"], m)}
+    return {"value": m * (m + 1) / 2 / dt, "unit": "pairs/s", "cores": cores, "kind": kind, "seconds": dt,
+            "sample": sample_text(name, div, len(ids), m)}
 
 
 def run_reference(args, out):
-    """--impl reference: the reference's own CPU implementation, all host threads, bounded sample."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's own CPU implementation, all host threads, bounded sample.  Never imports the product."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    ped, pro, _ = make_workload(args.workload, SAMPLE_DIV)
-    kind, eng, h, cores = reference_handle(ped)
+    kind, eng, cores = reference_engine()
+    div = 1 if "fixture" in WORKLOADS[args.workload] else SAMPLE_DIV
+    ids, f, mo, sx, pro, _, srt = workload_arrays(args.workload, div)
+    h = eng.genealogy(ids, f, mo, sx, sorted=srt)
+    t0 = time.time()
+    eng.phi(h, pro)
+    first = time.time() - t0
+    if first > 15.0 and div == SAMPLE_DIV:        # a small host: keep the whole run within a few minutes
+        div = 2 * SAMPLE_DIV
+        ids, f, mo, sx, pro, _, srt = workload_arrays(args.workload, div)
+        h = eng.genealogy(ids, f, mo, sx, sorted=srt)
     m = len(pro)
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup - 1, 0)):
         eng.phi(h, pro)
     t0 = time.time()
     for _ in range(args.steps):
         eng.phi(h, pro)
     dt = (time.time() - t0) / max(args.steps, 1)
     val = m * (m + 1) / 2 / dt
-    w = WORKLOADS[args.workload]
-    sample = ("1/%d-width replica of %s: %d individuals, %d generations, %d probands, full gen.phi"
-              % (SAMPLE_DIV, args.workload, w["n"] // SAMPLE_DIV, w["gens"], m))
+    sample = sample_text(args.workload, div, len(ids), m)
     line = {"impl": "reference", "metric": "kinship pairs/sec for gen.phi", "value": val, "unit": "pairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": w["desc"], "sample": sample},
-            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": int(cores), "kind": kind, "sample": sample},
-            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "data": "synthetic", "config": {"workload": WORKLOADS[args.workload]["desc"], "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "product_library_loaded": "geneakit_b200" in sys.modules}
     out.write(json.dumps(line) + "\n")
     out.flush()
 
@@ -155,15 +196,88 @@ def _claim_stdout():
     return real
 
 
+def parity_check(sp, ped, pro, local, rows_per_rank=48):
+    """Result rows of THIS rank (after the timed passes) against an independent one-GPU job on a sub-list of the probands:
+    kinship of a sub-list = the sub-matrix (other cuts, other classes, other kernels' tiles), bit for bit."""
+    import geneakit_b200 as gk
+    m = len(pro)
+    r0, r1 = sp.row0, sp.row1
+    own = np.unique(np.linspace(r0, r1 - 1, num=min(rows_per_rank, r1 - r0)).astype(np.int64))
+    cols = np.unique(np.linspace(0, m - 1, num=min(rows_per_rank, m)).astype(np.int64))
+    sub = np.unique(np.concatenate([own, cols]))
+    small = gk.cgeneakit.compute_kinships(ped, [pro[i] for i in sub], False, device=local)
+    pos = {int(i): k for k, i in enumerate(sub)}
+    ok = True
+    for i in own:
+        row = sp.job.rows(int(i), 1)[0]
+        ok = ok and row[sub].tobytes() == small[pos[int(i)]].tobytes()
+    return int(len(own)), int(len(sub)), bool(ok)
+
+
+def run_gc(args, out, torch, dist, rank, world, local):
+    """--op gc: gen.gc of the workload's founders (up to 2000) to its probands, ancestor columns sharded over the ranks
+    (no exchange), each rank through the one-shot C-ABI call gk_gc_f64 (host buffers, copies included)."""
+    import geneakit_b200 as gk
+    from geneakit_b200 import _lib
+    from geneakit_b200.distributed import shard_ancestors
+    ped, pro, _ = make_workload(args.workload)
+    anc = workload_arrays(args.workload)[5]
+    a0, a1 = shard_ancestors(len(anc), rank, world)
+    mine = anc[a0:a1]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    st = _lib.gk_gc_stats()
+    for _ in range(max(args.warmup, 1)):
+        gk.cgeneakit.compute_genetic_contributions(ped, pro, mine, device=local)
+    barrier()
+    t0 = time.time()
+    for _ in range(args.steps):
+        block = gk.cgeneakit.compute_genetic_contributions(ped, pro, mine, device=local)
+    barrier()
+    dt = (time.time() - t0) / args.steps
+    _lib.lib.gk_gc_last_stats(C.byref(st))
+    vals = torch.tensor([dt, st.kernel_ms, float(block.sum())], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dt, kms, total = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        kms, total = st.kernel_ms, float(block.sum())
+    if rank == 0:
+        peak, peak_src = peaks()
+        cells = len(pro) * len(anc)
+        ach = st.algorithmic_bytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+        line = {"metric": "genetic contributions/sec for gen.gc", "value": cells / dt, "unit": "proband-ancestor cells/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOADS[args.workload]["desc"], "op": "gen.gc", "probands": len(pro), "ancestors": len(anc),
+                           "sharding": "ancestor columns, no exchange", "sum_of_contributions": total,
+                           "timed": "gk_gc_f64 from host arrays to a host matrix (plan, H2D, kernels, D2H)"},
+                "roofline": {"bound": "hbm", "kernel": "gc_step_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                             "traffic": None, "peak_source": peak_src, "note": "rank 0: 24 B x live members x its ancestor columns / kernel time",
+                             "kernel_ms": kms, "column_blocks": int(st.column_blocks), "launches": int(st.kernel_launches)},
+                "cpu_baseline": None, "e2e": {"value": cells / dt, "unit": "proband-ancestor cells/s",
+                                              "h2d_bytes_per_step": int(8 * len(ped) + 4 * len(pro)), "d2h_bytes_per_step": int(8 * cells)},
+                "gpu_launches": int(st.kernel_launches) * args.steps * world}
+        out.write(json.dumps(line) + "\n")
+        out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--op", default="phi", choices=["phi", "gc"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--compress", type=int, default=-1)
     ap.add_argument("--order", type=int, default=-1)
     args = ap.parse_args()
@@ -183,17 +297,28 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
-    dist = None
+    dist = host_group = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_group = dist.new_group(backend="gloo")        # host-side barriers: no kernel may sit on a GPU another process drives
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (args.gpus, world))
+    if args.op == "gc":
+        run_gc(args, out, torch, dist, rank, world, local)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier(group=host_group)
 
     ped, pro, gen_s = make_workload(args.workload)
     m = len(pro)
@@ -201,12 +326,11 @@ def main():
     torch.cuda.set_stream(stream)
     sp = ShardedPhi(ped, pro, rank=rank, world=world, compress=args.compress, order=args.order, device=local,
                     stream=stream.cuda_stream)
-    sp.upload()                                    # plan + buffers resident in HBM before timing
+    sp.upload()                                    # buffers allocated, peers mapped: not part of a pass
     job = sp.job
-    st = job.stats()
     warm = max(args.warmup, 3)
     for _ in range(warm):
-        sp.run()
+        sp.replan().run()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -215,99 +339,118 @@ def main():
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
-        sp.run()
+        sp.replan().run()                          # host planning + H2D of the plan + every kernel of the pass
     e1.record(stream)
     barrier()
     sampler.stop.set()
     ms = e0.elapsed_time(e1) / args.steps
+    st = job.stats()
+    # the same pass with the plan resident in HBM (kernels only)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    r0.record(stream)
+    for _ in range(3):
+        sp.run()
+    r1.record(stream)
+    barrier()
+    ms_res = r0.elapsed_time(r1) / 3
     if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, ms_res], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)             # device time, max over ranks
-        ms = float(t[0])
+        ms, ms_res = float(t[0]), float(t[1])
     mean = sp.mean()
     pairs = m * (m + 1) / 2
     value = pairs / (ms * 1e-3)
 
-    # dominant kernel: phi_step_kernel, one launch per generation; CUDA events recorded by the
-    # library on this same stream around every launch of the LAST timed pass (this rank's launches)
+    # dominant kernel: the step kernel, one launch per generation; CUDA events recorded by the library on this same
+    # stream around every launch of the LAST pass (this rank's launches)
     t_ms = job.step_times_ms()
     b = job.step_bytes()
     nstep = st["n_steps"]
     step_ms, step_bytes = sum(t_ms[:nstep]), sum(b[:nstep]) / world      # a rank produces 1/world of every cut's matrix
     peak, peak_src = peaks()
     achieved = step_bytes / (step_ms * 1e-3) / 1e9 if step_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "phi_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kernel = "phi_step_g4_kernel" if world == 1 and max(job.class_sizes()) >= 8192 else ("phi_step_tma_kernel" if world > 1 else "phi_step_kernel")
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "launches": nstep, "bytes_per_launch_avg": step_bytes / max(nstep, 1),
-                "ms_per_launch_avg": step_ms / max(nstep, 1), "share_of_step": step_ms / ms,
+                "ms_per_launch_avg": step_ms / max(nstep, 1), "share_of_step": step_ms / ms_res,
                 "expand_ms": t_ms[nstep] if len(t_ms) > nstep else None,
                 "expand_gbs": (b[nstep] / world / (t_ms[nstep] * 1e-3) / 1e9) if len(t_ms) > nstep and t_ms[nstep] > 0 else None}
-    rank_ms = None
     if dist is not None:
-        # every rank's step-kernel and expansion time of the last pass (imbalance shows up here)
-        mine = torch.tensor([step_ms, t_ms[nstep] if len(t_ms) > nstep else 0.0], dtype=torch.float64, device="cuda")
+        # every rank's step-kernel and expansion time of the last pass (imbalance shows up here) and its NVLink rate
+        mine = torch.tensor([step_ms, t_ms[nstep] if len(t_ms) > nstep else 0.0,
+                             st["rank_remote_row_bytes"] / (step_ms * 1e-3) / 1e9 if step_ms > 0 else 0.0], dtype=torch.float64, device="cuda")
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
-        rank_ms = [[round(float(x[0]), 3), round(float(x[1]), 3)] for x in allr]
-    if world > 1:
-        roofline["rank_step_expand_ms"] = rank_ms
+        roofline["rank_step_expand_ms"] = [[round(float(x[0]), 3), round(float(x[1]), 3)] for x in allr]
+        roofline["nvlink_gbs"] = [round(float(x[2]), 1) for x in allr]
         roofline["note"] = "per GPU (rank 0): 1/%d of every cut's algorithmic bytes over this rank's launch time" % world
         roofline["nvlink_bytes_per_pass_rank0"] = int(st["rank_remote_row_bytes"])
-        roofline["nvlink_gbs_rank0"] = st["rank_remote_row_bytes"] / (step_ms * 1e-3) / 1e9 if step_ms > 0 else None
     tr = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
     if os.path.exists(tr) and world == 1:
         try:
             roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+            roofline["traffic_source"] = "profiles/traffic_%s.json (ncu --set full of this kernel, per launch)" % args.workload
         except Exception:
             pass
 
-    # end to end through the host-buffer entry points (plan + H2D of the plan + kernels + D2H of the
-    # result rows inside the timed region).  One GPU: the one-shot C-ABI call gk_phi_f64.
+    # correctness of what was just timed, on every rank
+    pc = None
+    if not args.no_parity_check:
+        n_rows, n_cols, ok = parity_check(sp, ped, pro, local)
+        flags = torch.tensor([n_rows, 1 if ok else 0], dtype=torch.int64, device="cuda")
+        if dist is not None:
+            allf = [torch.zeros_like(flags) for _ in range(world)]
+            dist.all_gather(allf, flags)
+        else:
+            allf = [flags]
+        pc = {"rows": int(sum(int(x[0]) for x in allf)), "columns_per_row": n_cols, "ranks": world,
+              "bit_exact": bool(all(int(x[1]) == 1 for x in allf)),
+              "against": "independent one-GPU job on the sub-list of probands (sub-list kinship = sub-matrix)"}
+    plan_bytes = int(st["plan_bytes"])
+    launches = int(st["kernel_launches"])
+    cuts, classes = job.cut_sizes(), job.class_sizes()
+    rows_per_rank = job.row1 - job.row0
+    sp.close()
+    lib.gk_cache_release()                          # the end-to-end leg allocates for itself (rank 0 drives every GPU)
+    host_barrier()
+
+    # end to end through the host-buffer entry point (plan + H2D of the plan + kernels + D2H of the m x m result inside
+    # the timed region): the one-shot C-ABI call gk_phi_f64 from ONE process -- rank 0 drives all `world` GPUs
     e2e = None
     if args.e2e_steps > 0:
-        rows = job.row1 - job.row0
-        nbytes = rows * m * 8
-        ptr = lib.gk_host_alloc(nbytes)
-        pinned = bool(ptr)
-        if not pinned:
-            hostbuf = np.empty((rows, m), dtype=np.float64)
-            ptr = hostbuf.ctypes.data
-        host = np.frombuffer((C.c_double * (rows * m)).from_address(ptr), dtype=np.float64).reshape(rows, m)
-        r = ped.ranks(pro)
-        mu = C.c_double()
-        dts = []
-        for it in range(args.e2e_steps + 1):
-            barrier()
-            t0 = time.time()
-            if world == 1:
-                opts = _lib.make_opts(device=local, compress=args.compress, order=args.order)
+        if rank == 0:
+            nbytes = m * m * 8
+            ptr = lib.gk_host_alloc(nbytes)
+            pinned = bool(ptr)
+            if not pinned:
+                hostbuf = np.empty((m, m), dtype=np.float64)
+                ptr = hostbuf.ctypes.data
+            r = ped.ranks(pro)
+            mu = C.c_double()
+            dts = []
+            for it in range(args.e2e_steps + 1):
+                opts = _lib.make_opts(device=local, compress=args.compress, order=args.order, gpus=world)
+                t0 = time.time()
                 check(lib.gk_phi_f64(len(ped), ped.sire, ped.dam, m, r, ptr, C.byref(mu), C.byref(opts)))
-                got = mu.value
-            else:
-                j2 = ShardedPhi(ped, pro, rank=rank, world=world, compress=args.compress, order=args.order,
-                                device=local, stream=stream.cuda_stream)
-                j2.upload().run()
-                j2.to_host(host)
-                got = j2.mean()
-                j2.close()
-            barrier()
-            if it > 0:
-                dts.append(time.time() - t0)
-        assert got == mean, (got, mean)
-        dt = sum(dts) / len(dts)
-        if dist is not None:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t[0])
-        e2e = {"value": pairs / dt, "unit": "pairs/s", "seconds_per_step": dt,
-               "h2d_bytes_per_step": int(st["plan_bytes"]) * world,
-               "d2h_bytes_per_step": int(m) * int(m) * 8 + 16 * world, "host_buffer": "pinned" if pinned else "pageable",
-               "plan_seconds": st["plan_seconds"], "steps": args.e2e_steps}
-        if pinned:
-            lib.gk_host_free(ptr)
+                if it > 0:
+                    dts.append(time.time() - t0)
+            got = mu.value
+            assert abs(got - mean) <= 1e-12 * abs(mean), (got, mean)
+            dt = sum(dts) / len(dts)
+            e2e = {"value": pairs / dt, "unit": "pairs/s", "seconds_per_step": dt,
+                   "h2d_bytes_per_step": plan_bytes * world,
+                   "d2h_bytes_per_step": int(m) * int(m) * 8 + 16 * world, "host_buffer": "pinned" if pinned else "pageable",
+                   "driver": "one process, gk_phi_f64 with opts.world = %d" % world if world > 1 else "gk_phi_f64",
+                   "phi_mean": got, "steps": args.e2e_steps}
+            lib.gk_cache_release()
+            if pinned:
+                lib.gk_host_free(ptr)
+        host_barrier()
 
     cpu = None
-    if not args.no_cpu_baseline and rank == 0 and world == 1:
+    if not args.no_cpu_baseline and rank == 0:
         cpu = cpu_sample(args.workload)
 
     if rank == 0:
@@ -319,21 +462,23 @@ def main():
                     "+ all-reduce of 2 doubles (phiMean)" % world)
         line = {"metric": "kinship pairs/sec for gen.phi", "value": value, "unit": "pairs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": w["desc"], "individuals": len(ped), "generations": w["gens"], "probands": m,
-                           "seed": w["seed"], "cuts": job.cut_sizes(), "classes": job.class_sizes(),
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic" if "fixture" not in w else "bundled dataset (reference-generated fixture)",
+                "config": {"workload": w["desc"], "individuals": len(ped), "generations": w.get("gens"), "probands": m,
+                           "seed": w.get("seed"), "cuts": cuts, "classes": classes,
                            "compressed": bool(st["compressed"]), "ranked": bool(st["ranked"]), "panel": st["tile"],
-                           "sharding": sharding, "rows_per_rank": job.row1 - job.row0,
+                           "sharding": sharding, "rows_per_rank": rows_per_rank,
+                           "timed_region": "per step: host planning + H2D of the plan + all cuts + expansion + mean (SURVEY 8d t_phi); buffers pre-allocated",
                            "l2": "inputs larger than L2 (%.1f GB of matrices per pass)" % (st["algorithmic_bytes_device"] / 1e9),
                            "cells_reference": st["cells_reference"], "cells_device": st["cells_device"],
                            "parent_row_bytes_per_pass": st["panel_row_bytes"], "corrections": st["corrections"],
-                           "phi_mean": mean, "pedigree_build_s": gen_s},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
-                "gpu_launches": int(st["kernel_launches"]) * args.steps * world,
-                "reference_algorithmic_gbs": st["algorithmic_bytes_reference"] / (ms * 1e-3) / 1e9}
+                           "phi_mean": mean, "plan_seconds": st["plan_seconds"], "pedigree_build_s": gen_s},
+                "resident": {"value": pairs / (ms_res * 1e-3), "unit": "pairs/s", "ms_per_step": ms_res,
+                             "note": "plan already in HBM: kernels of one pass only"},
+                "roofline": roofline, "parity_check": pc, "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
+                "gpu_launches": launches * (warm + args.steps + 3) * world,
+                "reference_algorithmic_gbs": st["algorithmic_bytes_reference"] / (ms_res * 1e-3) / 1e9}
         out.write(json.dumps(line) + "\n")
         out.flush()
-    sp.close()
     if dist is not None:
         dist.destroy_process_group()
 

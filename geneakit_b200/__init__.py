@@ -4,8 +4,8 @@ importing this package fails loudly when that library has not been built."""
 from . import cgeneakit                                   # noqa: F401
 from .create import genealogy                             # noqa: F401
 from .identify import pro, founder                        # noqa: F401
-from .compute import phi, phiMean, gc, phi_device         # noqa: F401
+from .compute import phi, phiMean, phiOver, phiCI, f, gc, phi_device   # noqa: F401
 from .synth import synthetic_pedigree                     # noqa: F401
 
-__all__ = ["genealogy", "pro", "founder", "phi", "phiMean", "gc", "phi_device",
+__all__ = ["genealogy", "pro", "founder", "phi", "phiMean", "phiOver", "phiCI", "f", "gc", "phi_device",
            "synthetic_pedigree", "cgeneakit"]

@@ -21,7 +21,7 @@ _F = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 class gk_opts(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("verbose", C.c_int32),
                 ("compress", C.c_int32), ("order", C.c_int32), ("rank", C.c_int32),
-                ("world", C.c_int32), ("reserved0", C.c_int32), ("stream", C.c_void_p)]
+                ("world", C.c_int32), ("flags", C.c_int32), ("stream", C.c_void_p)]
 
 
 class gk_phi_stats(C.Structure):
@@ -52,11 +52,17 @@ class gk_gc_stats(C.Structure):
                 ("kernel_launches", C.c_int64), ("n_cuts", C.c_int32), ("reserved", C.c_int32)]
 
 
-def make_opts(device=-1, verbose=False, compress=-1, order=-1, rank=0, world=1, stream=None):
+GK_FLAG_DIAGONAL_ONLY = 1
+
+
+def make_opts(device=-1, verbose=False, compress=-1, order=-1, rank=0, world=1, stream=None, flags=0, gpus=None):
+    """gpus=N (one-shot entry points only): this process drives GPUs 0 .. N-1 (rank = -1, world = N)."""
     o = gk_opts()
     o.struct_size = C.sizeof(gk_opts)
     o.device, o.verbose, o.compress, o.order = int(device), int(bool(verbose)), int(compress), int(order)
-    o.rank, o.world, o.reserved0 = int(rank), int(world), 0
+    o.rank, o.world, o.flags = int(rank), int(world), int(flags)
+    if gpus is not None and int(gpus) > 1:
+        o.rank, o.world = -1, int(gpus)
     o.stream = stream
     return o
 
@@ -71,6 +77,7 @@ def _load():
     OP = C.POINTER(gk_opts)
     L.gk_last_error.restype = C.c_char_p
     L.gk_abi_version.restype = i32
+    L.gk_opts_init.argtypes = [OP]; L.gk_opts_init.restype = None
     L.gk_host_alloc.argtypes = [C.c_uint64]; L.gk_host_alloc.restype = vp
     L.gk_host_free.argtypes = [vp]
     L.gk_phi_f64.argtypes = [i32, _I, _I, i32, _I, vp, C.POINTER(C.c_double), OP]
@@ -98,6 +105,8 @@ def _load():
                                     C.POINTER(i64)]
     L.gk_phi_ipc_export.argtypes = [vp, vp]
     L.gk_phi_ipc_open.argtypes = [vp, i32, vp]
+    L.gk_phi_stream.argtypes = [vp, C.POINTER(vp)]
+    L.gk_phi_set_stream.argtypes = [vp, vp]
     L.gk_phi_local_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.gk_phi_set_peer.argtypes = [vp, i32, vp, vp]
     L.gk_phi_peers_ready.argtypes = [vp]
@@ -106,6 +115,17 @@ def _load():
     L.gk_phi_dvec.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
     L.gk_phi_dvec_copy_from.argtypes = [vp, vp, i32]
     L.gk_phi_free.argtypes = [vp]; L.gk_phi_free.restype = None
+    L.gk_f_f64.argtypes = [i32, _I, _I, i32, _I, vp, OP]
+    for name in ("gk_phi_replan", "gk_phi_reupload"):
+        getattr(L, name).argtypes = [vp]
+    L.gk_phi_clone_rank.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    L.gk_phi_diag.argtypes = [vp, vp]
+    L.gk_phi_f.argtypes = [vp, vp]
+    L.gk_phi_over.argtypes = [vp, C.c_double, C.POINTER(i64)]
+    L.gk_phi_over_fetch.argtypes = [vp, vp, vp, vp]
+    L.gk_phi_sparse.argtypes = [vp, C.POINTER(i64)]
+    L.gk_phi_sparse_fetch.argtypes = [vp, vp, vp, vp]
+    L.gk_phi_ci_stats.argtypes = [vp, _I, i32, i32, vp]
     L.gk_phi_debug_prof.argtypes = [vp, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")]
     L.gk_cache_release.argtypes = []; L.gk_cache_release.restype = None
     L.gk_gc_last_stats.argtypes = [C.POINTER(gk_gc_stats)]
@@ -123,6 +143,8 @@ EXPORTS = [
     "gk_phi_ipc_export", "gk_phi_ipc_open", "gk_phi_local_buffers", "gk_phi_set_peer", "gk_phi_peers_ready",
     "gk_phi_run_step", "gk_phi_finish", "gk_phi_dvec", "gk_phi_dvec_copy_from",
     "gk_phi_debug_prof", "gk_cache_release", "gk_gc_last_stats",
+    "gk_opts_init", "gk_f_f64", "gk_phi_stream", "gk_phi_set_stream", "gk_phi_replan", "gk_phi_reupload", "gk_phi_clone_rank", "gk_phi_diag", "gk_phi_f",
+    "gk_phi_over", "gk_phi_over_fetch", "gk_phi_sparse", "gk_phi_sparse_fetch", "gk_phi_ci_stats",
 ]
 
 

@@ -177,6 +177,25 @@ def compute_kinships(pedigree, proband_ids=(), verbose=False, **gk):
     return out
 
 
+def compute_inbreedings(pedigree, proband_ids=(), **gk):
+    """lib/cgeneakit.cpp (compute_inbreedings binding) -> gk_f_f64: F of every proband, caller order."""
+    r = _pro_ranks(pedigree, proband_ids)
+    out = np.empty(len(r), dtype=np.float64)
+    opts = make_opts(**gk)
+    check(lib.gk_f_f64(len(pedigree), pedigree.sire, pedigree.dam, len(r), r, out.ctypes.data, C.byref(opts)))
+    return out
+
+
+def compute_kinships_sparse(pedigree, proband_ids=(), verbose=False, **gk):
+    """lib/cgeneakit.cpp:433-486 (CSR branch): (data float32, indices int32, indptr) of the lower-triangular kinship matrix,
+    compacted on the device from the dense result."""
+    job = DevicePhi(pedigree, proband_ids, verbose, **gk).upload().run()
+    try:
+        return job.sparse_csr()
+    finally:
+        job.close()
+
+
 def compute_genetic_contributions(pedigree, proband_ids=(), ancestor_ids=(), **gk):
     """lib/cgeneakit.cpp:491-511 -> gk_gc_f64.  Rows = probands, columns = ancestors."""
     r = _pro_ranks(pedigree, proband_ids)
@@ -229,6 +248,47 @@ class DevicePhi:
         else:
             ptr = out.ctypes.data
         check(lib.gk_phi_copy_out(self._h, ptr))
+        return out
+
+    def replan(self):
+        """Plan again on the host and copy the plan to the device again (buffers stay allocated)."""
+        check(lib.gk_phi_replan(self._h)); return self
+
+    def diag(self):
+        out = np.empty(self.m, dtype=np.float64)
+        check(lib.gk_phi_diag(self._h, out.ctypes.data))
+        return out
+
+    def f(self):
+        """Inbreeding coefficients 2 phi(i, i) - 1 of the probands (gen.f), from the device's self kinships."""
+        out = np.empty(self.m, dtype=np.float64)
+        check(lib.gk_phi_f(self._h, out.ctypes.data))
+        return out
+
+    def over(self, threshold):
+        """gen.phiOver on the device: (row index, column index, kinship) of the pairs i > j above the threshold."""
+        n = C.c_int64()
+        check(lib.gk_phi_over(self._h, float(threshold), C.byref(n)))
+        i = np.empty(max(n.value, 1), dtype=np.int32); j = np.empty(max(n.value, 1), dtype=np.int32)
+        v = np.empty(max(n.value, 1), dtype=np.float64)
+        check(lib.gk_phi_over_fetch(self._h, i.ctypes.data, j.ctypes.data, v.ctypes.data))
+        return i[:n.value], j[:n.value], v[:n.value]
+
+    def sparse_csr(self):
+        """(data float32, indices int32, indptr int64): the CSR of gen.phi(sparse=True), lower triangle with the diagonal."""
+        n = C.c_int64()
+        check(lib.gk_phi_sparse(self._h, C.byref(n)))
+        indptr = np.empty(self.m + 1, dtype=np.int64)
+        indices = np.empty(max(n.value, 1), dtype=np.int32); data = np.empty(max(n.value, 1), dtype=np.float32)
+        check(lib.gk_phi_sparse_fetch(self._h, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data))
+        return data[:n.value], indices[:n.value], indptr
+
+    def ci_stats(self, idx):
+        """gen.phiCI's statistic for every row of `idx` (b x n resample indices): mean of the entries < 0.5 of phi[idx][:, idx]."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        b, n = idx.shape
+        out = np.empty(b, dtype=np.float64)
+        check(lib.gk_phi_ci_stats(self._h, idx.reshape(-1), b, n, out.ctypes.data))
         return out
 
     def rows(self, row_begin, nrows):

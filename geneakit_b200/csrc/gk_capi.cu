@@ -11,8 +11,6 @@
 #include <thread>
 #include <vector>
 
-#include <cuda.h>     // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked
-
 #include "../../include/geneakit_b200.h"
 #include "gk_gcplan.hpp"
 #include "gk_kernels.cuh"
@@ -112,29 +110,6 @@ struct StepOffsets {
     int32_t use_g4 = 0, ring_g4 = 4;
 };
 
-typedef CUresult (*gk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                       const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-gk_encode_tiled_fn tensor_map_encoder() {
-    static gk_encode_tiled_fn fn = [] {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
-        return (gk_encode_tiled_fn) p;
-    }();
-    return fn;
-}
-// 2-D FP64 tensor map over a row-major matrix of `rows` x `cols` doubles (pitch ld doubles), box = {W, 1}: the shape
-// cp.async.bulk.tensor ... tile::gather4 wants (four row coordinates per instruction)
-bool make_row_gather_map(CUtensorMap *m, double *base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t W) {
-    gk_encode_tiled_fn enc = tensor_map_encoder();
-    if (!enc) return false;
-    cuuint64_t dims[2] = { cols, rows }, strides[1] = { ld * sizeof(double) };
-    cuuint32_t box[2] = { W, 1 }, es[2] = { 1, 1 };
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 }  // namespace
 
 struct gk_plan_inputs {             // what the plan was built from (kept for gk_phi_replan)
@@ -149,6 +124,7 @@ struct gk_phi_job {
     int device = 0;
     int rank = 0, world = 1;
     bool uploaded = false, ran = false;
+    bool no_expand = false;           // opts.flags & GK_FLAG_DIAGONAL_ONLY: no m x m result (gen.f only needs the self kinships)
     int steps_done = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -327,7 +303,7 @@ static size_t build_arena(gk_phi_job *j, std::vector<int32_t> &arena) {
         }
         // ---- one-GPU TMA gather4 kernel: per panel the distinct parent rows padded to a multiple of four with the
         //      matrix's all-zero row (index Kpad_prev), which also is the staged row of an unknown parent ----------
-        o.use_g4 = (j->use_g4 && tensor_map_encoder() && S.Kpad_prev >= (j->g4_min_k > 0 ? j->g4_min_k : 8192)) ? 1 : 0;   // small cuts: the warp-autonomous kernel has less fixed cost
+        o.use_g4 = (j->use_g4 && S.Kpad_prev >= (j->g4_min_k > 0 ? j->g4_min_k : 8192)) ? 1 : 0;   // small cuts: the warp-autonomous kernel has less fixed cost
         if (o.use_g4) {
             const int zero_row = (int) S.Kpad_prev;
             const int nu = 2 * S.np;                                   // units of 16 classes
@@ -421,6 +397,7 @@ static size_t build_arena(gk_phi_job *j, std::vector<int32_t> &arena) {
 // Everything of a job that follows from (plan, rank, world): kernel choice, panel ranges, result rows, NVLink statistics.
 static void configure_job(gk_phi_job *j) {
     j->row_bytes = j->remote_row_bytes = 0;
+    j->no_expand = (j->opts.flags & GK_FLAG_DIAGONAL_ONLY) != 0;
     // a rank of a multi-GPU job evaluates every tile J and stores only its own rows; RANKED jobs (rounding order
     // fixed by rank) must keep J <= I and store the mirror tile into the rows of J's owner instead
     j->full_rows = (j->world > 1 && !j->planp->ranked) ? 1 : 0;
@@ -460,6 +437,13 @@ static void configure_job(gk_phi_job *j) {
 extern "C" {
 
 const char *gk_last_error(void) { return g_err.c_str(); }
+
+void gk_opts_init(gk_opts *o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof *o);
+    o->struct_size = (int32_t) sizeof *o;
+    o->device = -1; o->compress = -1; o->order = -1; o->rank = 0; o->world = 1;
+}
 int32_t gk_abi_version(void) { return GK_ABI_VERSION; }
 
 void *gk_host_alloc(uint64_t bytes) {
@@ -580,7 +564,13 @@ int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, c
         j->inputs->n = n; j->inputs->m = m;
         j->inputs->sire.assign(sire, sire + n); j->inputs->dam.assign(dam, dam + n); j->inputs->pro.assign(pro, pro + m);
     }
-    if (!gk::build_phi_plan(n, sire, dam, m, pro, j->opts.compress, j->opts.order, j->world, *j->planp)) {
+    bool planned = gk::build_phi_plan(n, sire, dam, m, pro, j->opts.compress, j->opts.order, j->world, *j->planp);
+    if (!planned && j->planp->error_code == 3) {
+        // the sibship compression does not pay for this pedigree: the same job, one row per individual (same results)
+        j->opts.compress = 0;
+        planned = gk::build_phi_plan(n, sire, dam, m, pro, 0, j->opts.order, j->world, *j->planp);
+    }
+    if (!planned) {
         int code = j->planp->error_code == 2 ? GK_ERR_INDEX : GK_ERR_ARG;
         std::string msg = j->planp->error;
         delete j;
@@ -623,7 +613,7 @@ int gk_phi_upload(gk_phi_job *j) {
         if (g + 1 < G) max_prev = std::max(max_prev, S.Kpad);
         dlen = std::max(dlen, (int64_t) j->off[g].cpp * gk::kPanel * j->world);
     }
-    const int64_t mm = (j->row1 - j->row0) * (int64_t) P.m;
+    const int64_t mm = j->no_expand ? 0 : (j->row1 - j->row0) * (int64_t) P.m;
     const int out_buf = P.single_cut ? 0 : 1 - ((G - 1) & 1);
     if (j->world == 1) need[out_buf] = std::max(need[out_buf], mm);
     for (int p = 0; p < 2; p++) {
@@ -688,6 +678,16 @@ int gk_phi_ipc_open(gk_phi_job *j, int32_t q, const void *handles) {
         j->peer[q][p] = static_cast<double *>(ptr);
         j->peer_ipc[q][p] = true;
     }
+    return GK_OK;
+}
+int gk_phi_set_stream(gk_phi_job *j, void *stream) {
+    if (!j || j->uploaded) return fail(GK_ERR_STATE, "gk_phi_set_stream after gk_phi_upload");
+    j->opts.stream = stream;
+    return GK_OK;
+}
+int gk_phi_stream(gk_phi_job *j, void **stream) {
+    if (!j || !j->uploaded || !stream) return fail(GK_ERR_STATE, "job not uploaded");
+    *stream = (void *) j->stream;
     return GK_OK;
 }
 int gk_phi_local_buffers(gk_phi_job *j, void **buf0, void **buf1) {
@@ -790,17 +790,13 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     if (o.use_g4) {
         double *prev = j->buf[(g - 1) & 1];
         GK_CUDA(cudaMemsetAsync(prev + S.Kpad_prev * S.Kpad_prev, 0, (size_t) S.Kpad_prev * sizeof(double), st));   // row Kpad_prev := 0
-        CUtensorMap m128, m64;
-        if (!make_row_gather_map(&m128, prev, (uint64_t) S.Kpad_prev + 1, (uint64_t) S.Kpad_prev, (uint64_t) S.Kpad_prev, 130) ||
-            !make_row_gather_map(&m64, prev, (uint64_t) S.Kpad_prev + 1, (uint64_t) S.Kpad_prev, (uint64_t) S.Kpad_prev, 66))
-            return fail(GK_ERR_CUDA, "cuTensorMapEncodeTiled failed");
         d.prow4 = j->ints + o.prow4; d.pcnt4 = j->ints + o.pcnt4; d.slots4 = j->ints + o.slots4;
         d.item_off = reinterpret_cast<const int64_t *>(j->ints + o.item_off);
         d.total_g4 = o.total_g4;
         d.prof = j->prof;
         { const char *e = std::getenv("GK_CHUNK2"); d.chunk2 = e ? std::atoi(e) : 0; }
         d.queue2 = reinterpret_cast<unsigned long long *>(j->counters + ((o.done + 2 * (size_t) S.np + 1) / 2 * 2));
-        GK_CUDA(gk::launch_step_g4(d, &m128, &m64, st));
+        GK_CUDA(gk::launch_step_g4(d, st));
     } else if (j->use_tma) GK_CUDA(gk::launch_step_tma(d, st));
     else GK_CUDA(gk::launch_step(d, st));
     gk::DiagDev q{};
@@ -830,6 +826,11 @@ int gk_phi_finish(gk_phi_job *j) {
     cudaStream_t st = j->stream;
     const int last = G - 1;
     GK_CUDA(cudaEventRecord(j->ev[0], st));
+    if (j->no_expand) {
+        GK_CUDA(cudaEventRecord(j->ev[1], st));
+        j->ran = true;
+        return GK_OK;
+    }
     if (P.single_cut) {
         GK_CUDA(gk::launch_eye(j->out, P.m, j->row0, j->row1, j->partials, st));
     } else {
@@ -879,6 +880,7 @@ int gk_phi_sync(gk_phi_job *j) {
 
 int gk_phi_mean(gk_phi_job *j, double *sum_all, double *sum_diag, double *mean) {
     if (!j || !j->ran) return fail(GK_ERR_STATE, "gk_phi_mean before gk_phi_run");
+    if (j->no_expand) return fail(GK_ERR_STATE, "the job was planned with GK_FLAG_DIAGONAL_ONLY: it has no m x m result");
     int rc = gk_phi_sync(j);
     if (rc) return rc;
     const double total = j->sums_host[0], diag = j->sums_host[1];
@@ -893,6 +895,7 @@ int gk_phi_mean(gk_phi_job *j, double *sum_all, double *sum_diag, double *mean) 
 
 int gk_phi_copy_out(gk_phi_job *j, double *host_out) {
     if (!j || !j->ran) return fail(GK_ERR_STATE, "gk_phi_copy_out before gk_phi_run");
+    if (j->no_expand) return fail(GK_ERR_STATE, "the job was planned with GK_FLAG_DIAGONAL_ONLY: it has no m x m result");
     if (!host_out) return fail(GK_ERR_ARG, "null output");
     GK_CUDA(cudaSetDevice(j->device));
     const size_t bytes = (size_t) (j->row1 - j->row0) * j->planp->m * sizeof(double);
@@ -904,6 +907,7 @@ int gk_phi_copy_out(gk_phi_job *j, double *host_out) {
 int gk_phi_copy_rows(gk_phi_job *j, int64_t row_begin, int64_t nrows, double *host_out) {
     if (!j || !j->ran) return fail(GK_ERR_STATE, "gk_phi_copy_rows before gk_phi_run");
     if (!host_out || row_begin < j->row0 || nrows < 0 || row_begin + nrows > j->row1) return fail(GK_ERR_ARG, "rows outside this job's block");
+    if (j->no_expand) return fail(GK_ERR_STATE, "the job was planned with GK_FLAG_DIAGONAL_ONLY: it has no m x m result");
     GK_CUDA(cudaSetDevice(j->device));
     GK_CUDA(cudaMemcpyAsync(host_out, j->out + (row_begin - j->row0) * (int64_t) j->planp->m, (size_t) nrows * j->planp->m * sizeof(double),
                             cudaMemcpyDeviceToHost, j->stream));
@@ -1018,6 +1022,129 @@ int gk_phi_debug_prof(gk_phi_job *j, uint64_t *out16) {
 
 void gk_phi_free(gk_phi_job *j) { destroy(j); }
 
+// Self kinship of every caller entry (the diagonal of the result, lib/compute.cpp:553-568) from the device's d vector.
+int gk_phi_diag(gk_phi_job *j, double *host_out) {
+    if (!j || !j->ran) return fail(GK_ERR_STATE, "gk_phi_diag before gk_phi_run");
+    if (!host_out) return fail(GK_ERR_ARG, "null output");
+    const gk::PhiPlan &P = *j->planp;
+    GK_CUDA(cudaSetDevice(j->device));
+    if (P.single_cut) { for (int32_t i = 0; i < P.m; i++) host_out[i] = 0.5; return GK_OK; }
+    const int last = P.G - 1;
+    std::vector<double> d((size_t) P.steps[last].Kpad);
+    GK_CUDA(cudaMemcpyAsync(d.data(), j->dvec[last & 1], d.size() * sizeof(double), cudaMemcpyDeviceToHost, j->stream));
+    GK_CUDA(cudaStreamSynchronize(j->stream));
+    for (int32_t i = 0; i < P.m; i++) host_out[i] = d[P.final_cls[i]];
+    return GK_OK;
+}
+
+// Inbreeding coefficients F = 2 phi(i, i) - 1 = phi(father, mother) (gen.f, geneakit/compute.py:255-282; the reference
+// computes them with a separate algorithm, lib/compute.cpp:725-814).
+int gk_phi_f(gk_phi_job *j, double *host_out) {
+    int rc = gk_phi_diag(j, host_out);
+    if (rc) return rc;
+    for (int32_t i = 0; i < j->planp->m; i++) host_out[i] = 2.0 * host_out[i] - 1.0;
+    return GK_OK;
+}
+
+namespace {
+// count + fill of the selected pairs of this job's result rows; the arrays stay on the device until fetched
+struct Selection {
+    int64_t *cnt = nullptr, *off = nullptr;
+    int32_t *oi = nullptr, *oj = nullptr;
+    double *ov = nullptr;
+    float *ovf = nullptr;
+    int64_t total = 0;
+    int mode = 0;
+    std::vector<int64_t> host_off;
+    void release() { pool_free(cnt); pool_free(off); pool_free(oi); pool_free(oj); pool_free(ov); pool_free(ovf); *this = Selection(); }
+};
+thread_local Selection g_sel;
+
+int run_selection(gk_phi_job *j, int mode, double thr, int64_t *total) {
+    if (!j || !j->ran) return fail(GK_ERR_STATE, "no result: run the job first");
+    if (j->no_expand) return fail(GK_ERR_STATE, "the job was planned with GK_FLAG_DIAGONAL_ONLY: it has no m x m result");
+    GK_CUDA(cudaSetDevice(j->device));
+    g_sel.release();
+    g_sel.mode = mode;
+    const int64_t rows = j->row1 - j->row0;
+    gk::SelectDev q{};
+    q.M = j->out; q.m = j->planp->m; q.row0 = j->row0; q.row1 = j->row1; q.mode = mode; q.thr = thr;
+    GK_CUDA(pool_alloc_t(&g_sel.cnt, (size_t) std::max<int64_t>(rows, 1) * 8, j->device));
+    GK_CUDA(pool_alloc_t(&g_sel.off, (size_t) std::max<int64_t>(rows, 1) * 8, j->device));
+    q.row_count = g_sel.cnt; q.row_off = g_sel.off;
+    GK_CUDA(gk::launch_select(q, 0, j->stream));
+    std::vector<int64_t> cnt((size_t) rows);
+    GK_CUDA(cudaMemcpyAsync(cnt.data(), g_sel.cnt, (size_t) rows * 8, cudaMemcpyDeviceToHost, j->stream));
+    GK_CUDA(cudaStreamSynchronize(j->stream));
+    g_sel.host_off.assign((size_t) rows + 1, 0);
+    for (int64_t r = 0; r < rows; r++) g_sel.host_off[r + 1] = g_sel.host_off[r] + cnt[r];
+    g_sel.total = g_sel.host_off[rows];
+    GK_CUDA(cudaMemcpyAsync(g_sel.off, g_sel.host_off.data(), (size_t) rows * 8, cudaMemcpyHostToDevice, j->stream));
+    const size_t n = (size_t) std::max<int64_t>(g_sel.total, 1);
+    GK_CUDA(pool_alloc_t(&g_sel.oj, n * 4, j->device));
+    if (mode == 0) { GK_CUDA(pool_alloc_t(&g_sel.oi, n * 4, j->device)); GK_CUDA(pool_alloc_t(&g_sel.ov, n * 8, j->device)); }
+    else GK_CUDA(pool_alloc_t(&g_sel.ovf, n * 4, j->device));
+    q.oi = g_sel.oi; q.oj = g_sel.oj; q.ov = g_sel.ov; q.ovf = g_sel.ovf;
+    GK_CUDA(gk::launch_select(q, 1, j->stream));
+    GK_CUDA(cudaStreamSynchronize(j->stream));
+    if (total) *total = g_sel.total;
+    return GK_OK;
+}
+}  // namespace
+
+// gen.phiOver on the device (geneakit/compute.py:135-190, dense branch): pairs (i > j) with kinship > threshold, in the
+// reference's order (row by row).  gk_phi_over counts and keeps the pairs in HBM; gk_phi_over_fetch copies the `count`
+// triples (row index, column index in CALLER order, value) to the host and frees them.
+int gk_phi_over(gk_phi_job *j, double threshold, int64_t *count) { return run_selection(j, 0, threshold, count); }
+int gk_phi_over_fetch(gk_phi_job *j, int32_t *pro1_idx, int32_t *pro2_idx, double *kinship) {
+    if (!j || g_sel.mode != 0 || !g_sel.oj) return fail(GK_ERR_STATE, "gk_phi_over_fetch without gk_phi_over");
+    GK_CUDA(cudaSetDevice(j->device));
+    if (g_sel.total > 0) {
+        GK_CUDA(cudaMemcpy(pro1_idx, g_sel.oi, (size_t) g_sel.total * 4, cudaMemcpyDeviceToHost));
+        GK_CUDA(cudaMemcpy(pro2_idx, g_sel.oj, (size_t) g_sel.total * 4, cudaMemcpyDeviceToHost));
+        GK_CUDA(cudaMemcpy(kinship, g_sel.ov, (size_t) g_sel.total * 8, cudaMemcpyDeviceToHost));
+    }
+    g_sel.release();
+    return GK_OK;
+}
+
+// The CSR that gen.phi(sparse=True) returns (compute_kinships_sparse, lib/compute.cpp:272-487; binding
+// lib/cgeneakit.cpp:433-486): lower triangle incl. the diagonal, float32 values (float) (2 phi) / 2, entries with
+// |2 phi| > 1e-9, rows and columns in caller order -- here compacted on the device from the dense result.
+int gk_phi_sparse(gk_phi_job *j, int64_t *nnz) { return run_selection(j, 1, 1e-9, nnz); }
+int gk_phi_sparse_fetch(gk_phi_job *j, int64_t *indptr, int32_t *indices, float *data) {
+    if (!j || g_sel.mode != 1 || !g_sel.oj) return fail(GK_ERR_STATE, "gk_phi_sparse_fetch without gk_phi_sparse");
+    GK_CUDA(cudaSetDevice(j->device));
+    std::memcpy(indptr, g_sel.host_off.data(), g_sel.host_off.size() * 8);
+    if (g_sel.total > 0) {
+        GK_CUDA(cudaMemcpy(indices, g_sel.oj, (size_t) g_sel.total * 4, cudaMemcpyDeviceToHost));
+        GK_CUDA(cudaMemcpy(data, g_sel.ovf, (size_t) g_sel.total * 4, cudaMemcpyDeviceToHost));
+    }
+    g_sel.release();
+    return GK_OK;
+}
+
+// gen.phiCI's bootstrap statistic on the device (geneakit/compute.py:193-252): for each of the b resamples idx[r][0..n)
+// (indices into the result, with replacement) the mean of the entries < 0.5 of phi[idx][:, idx]; NaN if there is none.
+int gk_phi_ci_stats(gk_phi_job *j, const int32_t *idx, int32_t b, int32_t n, double *stats) {
+    if (!j || !j->ran) return fail(GK_ERR_STATE, "no result: run the job first");
+    if (j->no_expand || j->world != 1) return fail(GK_ERR_STATE, "gk_phi_ci_stats needs the whole m x m result on one GPU");
+    if (!idx || !stats || b < 0 || n < 0) return fail(GK_ERR_ARG, "bad argument");
+    for (int64_t k = 0; k < (int64_t) b * n; k++) if (idx[k] < 0 || idx[k] >= j->planp->m) return fail(GK_ERR_INDEX, "resample index out of range");
+    GK_CUDA(cudaSetDevice(j->device));
+    int32_t *didx = nullptr;
+    double *dstat = nullptr;
+    GK_CUDA(pool_alloc_t(&didx, (size_t) std::max<int64_t>((int64_t) b * n, 1) * 4, j->device));
+    cudaError_t e = pool_alloc_t(&dstat, (size_t) std::max(b, 1) * 8, j->device);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(didx, idx, (size_t) b * n * 4, cudaMemcpyHostToDevice, j->stream);
+    if (e == cudaSuccess) e = gk::launch_ci(j->out, j->planp->m, didx, b, n, dstat, j->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(stats, dstat, (size_t) b * 8, cudaMemcpyDeviceToHost, j->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(j->stream);
+    pool_free(didx); pool_free(dstat);
+    if (e != cudaSuccess) return cuda_fail(e, "gk_phi_ci_stats");
+    return GK_OK;
+}
+
 // Plan again from the inputs the job was created with and copy the plan arrays to the device once more (same sizes:
 // the planner is deterministic).  With gk_phi_run it is one "flattened arrays on the host -> matrix resident in HBM"
 // pass (SURVEY 8d's t_phi) on buffers that are already allocated.
@@ -1072,7 +1199,7 @@ struct MultiPhi {
     bool virtual_devices = false;             // tests on a one-GPU box: every rank on the current device, ONE stream
     ~MultiPhi() {
         for (size_t q = 0; q < cut_done.size(); q++) if (cut_done[q]) { cudaSetDevice(jobs[q]->device); cudaEventDestroy(cut_done[q]); }
-        for (gk_phi_job *j : jobs) destroy(j);
+        for (size_t q = jobs.size(); q-- > 0;) destroy(jobs[q]);      // rank 0 last: with virtual devices the others enqueue on its stream
     }
 };
 
@@ -1211,6 +1338,27 @@ int gk_phi_f64(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, co
     if (!rc) rc = gk_phi_run(j);
     if (!rc) rc = gk_phi_copy_out(j, out);
     if (!rc && mean_or_null) rc = gk_phi_mean(j, nullptr, nullptr, mean_or_null);
+    std::string keep = g_err;
+    destroy(j);
+    if (rc) g_err = keep;
+    return rc;
+}
+
+// Replaces compute_inbreedings(Pedigree<>&, proband_ids) (include/compute.hpp, lib/compute.cpp:725-814) behind the
+// binding of gen.f: out[i] = F of proband i (caller order).  Runs the kinship recurrence without the final expansion.
+int gk_f_f64(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, const int32_t *pro, double *out, const gk_opts *opts) {
+    if (!out) return fail(GK_ERR_ARG, "null output");
+    std::lock_guard<std::mutex> call_lock(g_call_mu);
+    gk_opts o{};
+    if (opts) std::memcpy(&o, opts, std::min<size_t>(sizeof(gk_opts), (size_t) std::max(0, opts->struct_size)));
+    else { o.device = -1; o.compress = -1; o.order = -1; }
+    o.struct_size = sizeof(gk_opts); o.rank = 0; o.world = 1; o.flags |= GK_FLAG_DIAGONAL_ONLY;
+    gk_phi_job *j = nullptr;
+    int rc = gk_phi_plan(n, sire, dam, m, pro, &o, &j);
+    if (rc) return rc;
+    rc = gk_phi_upload(j);
+    if (!rc) rc = gk_phi_run(j);
+    if (!rc) rc = gk_phi_f(j, out);
     std::string keep = g_err;
     destroy(j);
     if (rc) g_err = keep;

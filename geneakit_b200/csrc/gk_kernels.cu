@@ -436,40 +436,37 @@ __global__ void __launch_bounds__(kThreadsTma, 1) phi_step_tma_kernel(const Step
     }
 }
 
-// THIRD STEP KERNEL (one GPU): the Blackwell data-movement path.  Measured on B200 (scripts/micro/gather4_bench.cu):
-// TMA tile::gather4 (four arbitrary rows of a 2-D tensor per instruction) moves 1 KB row segments at 5.4 TB/s and
-// 2 KB ones at 6.9 TB/s with nothing but 2-3 stages of shared memory in flight, no registers, no L1; reads that hit
-// L2 run at 19 TB/s, stores at 7.5 TB/s.  So:
+// THIRD STEP KERNEL (one GPU, the default for large cuts).  What was measured on B200 to get here
+// (scripts/micro/gather4_bench.cu, the GK_PROF role counters, ncu): reads that hit L2 run at 19 TB/s, DRAM reads at 7.3,
+// stores at 5.9-7.5 TB/s, so the step is bound by DRAM time = reads of A + writes of B (they ADD: ~4.3 ms at c4); a 1-D
+// TMA bulk copy costs ~105 cycles of the SM's TMA engine whatever its size, tile::gather4 ~50 cycles per row but packs the
+// four rows at a 128-byte-aligned pitch (every row on the same banks), and per-item chains of dependent global loads or a
+// gpu-scope fence on a critical warp cost more than the data movement itself.  Hence, one CTA per SM, four kinds of warps:
 //
-//  PHASE 1 through the TMA engine.  An item = one PANEL (32 classes) x W columns of the previous matrix (W = 128,
-//  or 64 for the few panels with more than 48 distinct parent rows).  The producer warp issues one gather4 per four
-//  distinct parent rows (the planner pads the row list with the matrix's all-zero row, which also stands for an
-//  unknown parent) into one of kG4Stages stages, completion on the stage's mbarrier.  The consumer warp that owns
-//  the stage averages father and mother rows with lane = COLUMN (rows of a stage are packed, so a warp reading
-//  one staged row is conflict-free), transposes 16 x 32 pieces through a 4 KB scratch and stores the 128-byte
-//  half rows N^T[c][16 classes] of the L2-resident panel ring (only rows some tile J <= I will read).  The
-//  producer also does the cross-CTA bookkeeping: it waits for the ring slot to be drained (done2 of panel
-//  I - ring_n) before it loads the first item of panel I, and it publishes finished items (done1) when it
-//  recycles their stage -- one gpu-scope fence per item instead of one per warp and tile.
+//  PRODUCER (1 warp): phase-1 items = one UNIT (16 classes = half a panel) x 512 columns of the previous matrix.  One bulk
+//  copy (UBLKCP) per distinct parent row of the unit -- 4 KB each, ~20 per item -- into a 2-stage FIFO; staged rows are
+//  (W + 2) * 8 bytes apart (an odd number of 16-byte units) at positions the planner chose so that the rows eight
+//  consecutive classes read are distinct mod 8: bank-conflict-free 128-bit reads.  Items are decoded two ahead; the unit
+//  of an item is found in a 32-entry window of the item prefix (one coalesced load per ~16 items).
+//  CONSUMERS (4 warps): all work on the oldest full stage, lane = (class, column-pair parity): two 128-bit shared loads,
+//  N = 1/2 (father + mother), 128-byte half rows N^T[c][16 classes] straight into the L2-resident panel ring (only the rows
+//  some tile J <= I will read).  No transposition, no barrier wider than a warp; a finished item bumps a shared counter.
+//  PHASE-2 WARPS (10): tiles (I, J <= I) are taken from a global queue in order, so the whole GPU drains the oldest panel.
+//  Per class j the two 256-byte ring rows N^T[F_j], N^T[M_j] are loaded straight from L2 into registers (lane = class of
+//  panel I; four batches of eight classes software-pipelined over two register buffers), row j of tile (J, I) is stored,
+//  and the mirror tile (I, J) leaves through a 16 x 33 scratch as 128-byte pieces.  Finished tiles go to a mailbox.
+//  PUBLISHER (1 warp): snapshots the consumers' counters and the mailboxes, executes ONE fence.acq_rel.gpu, then updates
+//  done1 / done2 -- the release / acquire chain worker -> shared memory -> publisher -> fence carries the workers' stores,
+//  and no worker ever stalls on a membar.
 //
-//  PHASE 2 straight from L2.  A warp takes a tile pair (I, J <= I): for each class j of tile J it loads the two
-//  256-byte ring rows N^T[F_j], N^T[M_j] (lane = class of the panel; ld.global.cg, L2 hits, 32 loads in flight),
-//  stores row j of tile (J, I) and, through the scratch, the transposed 128-byte pieces of the mirror tile (I, J).
-//
-// Dependencies as in the first kernel: phase 2 of panel I waits for done1[I]; phase 1 of panel I for
-// done2[I - ring_n]; every wait is on strictly earlier work and all CTAs are resident.
+// Dependencies as in the first kernel: phase 2 of panel I waits for done1[I]; phase 1 of panel I for done2 of panel
+// I - ring_n; every wait is on strictly earlier work and all CTAs are resident.
 constexpr int G4NS = kG4Stages, G4NC = kG4Consumers, G4P2 = kG4P2Warps;
 constexpr int kThreadsG4 = (G4NC + G4P2 + 2) * 32;        // consumers, phase-2 warps, the producer, the publisher
 constexpr int G4SCRP = 33;                                 // scratch pitch (doubles)
 constexpr int G4SCR = 16 * G4SCRP;                         // scratch doubles per warp
 constexpr size_t kStepSmemG4 = (size_t) G4NS * kG4StageBytes + (size_t) G4P2 * G4SCR * sizeof(double) + 2 * G4NS * sizeof(unsigned long long) + 64;
 
-struct alignas(64) TMap { unsigned long long v[16]; };    // CUtensorMap, opaque
-
-__device__ __forceinline__ void tma_gather4(unsigned dst, const TMap *map, int col, int4 r, unsigned bar, unsigned long long pol) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;\n"
-                 ::"r"(dst), "l"(map), "r"(col), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w), "r"(bar), "l"(pol) : "memory");
-}
 __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
     unsigned ok;
     asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
@@ -489,7 +486,7 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
     return v;
 }
 
-__global__ void __launch_bounds__(kThreadsG4, 1) phi_step_g4_kernel(const StepDev s, const __grid_constant__ TMap m128, const __grid_constant__ TMap m64) {
+__global__ void __launch_bounds__(kThreadsG4, 1) phi_step_g4_kernel(const StepDev s) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int spub[8][2];                           // (panel, blocks) of the last 8 items issued, for the publisher
     __shared__ volatile int ctl[G4NC + 1];               // items consumed by each consumer warp; items published
@@ -1062,6 +1059,59 @@ __global__ void __launch_bounds__(256) gc_gather_kernel(const double *V, long lo
     for (long long c = threadIdx.x; c < a; c += 256) out[i * a + c] = r >= 0 ? V[(long long) r * ld + c] : 0.0;
 }
 
+// ---- device-side consumers of the result: the m x m matrix never has to cross PCIe -------------------
+// One warp per result row, two passes (count, then fill at the row's offset): entries come out in the reference's order
+// (row by row, columns ascending).  mode 0 = gen.phiOver (geneakit/compute.py:170-178): j < i and value > threshold;
+// mode 1 = the CSR of gen.phi(sparse=True) (lib/compute.cpp:402-413,458-476): j <= i and |2 value| > 1e-9.
+__global__ void __launch_bounds__(256) select_kernel(const SelectDev q, const int fill) {
+    const int lane = threadIdx.x & 31;
+    const long long row = q.row0 + (long long) blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= q.row1) return;
+    const double *src = q.M + (row - q.row0) * q.m;
+    const long long jend = q.mode == 0 ? row : row + 1;
+    long long n = 0;
+    const long long base = fill ? q.row_off[row - q.row0] : 0;
+    for (long long j0 = 0; j0 < jend; j0 += 32) {
+        const long long j = j0 + lane;
+        double v = 0.0;
+        bool ok = false;
+        if (j < jend) { v = src[j]; ok = q.mode == 0 ? v > q.thr : fabs(2.0 * v) > q.thr; }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (fill && ok) {
+            const long long at = base + n + __popc(m & ((1u << lane) - 1));
+            q.oj[at] = (int32_t) j;
+            if (q.mode == 0) { q.oi[at] = (int32_t) row; q.ov[at] = v; }
+            else q.ovf[at] = (float) (2.0 * v) / 2.0f;
+        }
+        n += __popc(m);
+    }
+    if (!fill && lane == 0) q.row_count[row - q.row0] = n;
+}
+
+// gen.phiCI's statistic (geneakit/compute.py:226-229) for one bootstrap resample per CTA: the mean of the entries < 0.5 of
+// the sub-matrix phi[idx][:, idx].  Fixed assignment of entries to threads and a fixed reduction tree: deterministic.
+__global__ void __launch_bounds__(256) ci_kernel(const double *M, long long ld, const int32_t *idx, int n, double *stat) {
+    __shared__ double ssum[256];
+    __shared__ unsigned long long scnt[256];
+    const int32_t *ix = idx + (long long) blockIdx.x * n;
+    double s = 0.0;
+    unsigned long long c = 0;
+    for (int a = threadIdx.x >> 5; a < n; a += 8) {
+        const double *row = M + (long long) ix[a] * ld;
+        for (int b = threadIdx.x & 31; b < n; b += 32) {
+            const double v = row[ix[b]];
+            if (v < 0.5) { s += v; c++; }
+        }
+    }
+    ssum[threadIdx.x] = s; scnt[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; scnt[threadIdx.x] += scnt[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) stat[blockIdx.x] = scnt[0] ? ssum[0] / (double) scnt[0] : nan("");
+}
+
 }  // namespace
 
 static int g_step_grid = 0;
@@ -1098,13 +1148,10 @@ cudaError_t launch_step_tma(const StepDev &s, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_step_g4(const StepDev &s, const void *tmap128, const void *tmap64, cudaStream_t st) {
+cudaError_t launch_step_g4(const StepDev &s, cudaStream_t st) {
     if (s.total_g4 + s.total2 <= 0) return cudaSuccess;
     const long long grid = g_step_grid > 0 ? g_step_grid : 148;
-    TMap a, b;
-    memcpy(&a, tmap128, sizeof a);
-    memcpy(&b, tmap64, sizeof b);
-    phi_step_g4_kernel<<<(unsigned) grid, kThreadsG4, kStepSmemG4, st>>>(s, a, b);
+    phi_step_g4_kernel<<<(unsigned) grid, kThreadsG4, kStepSmemG4, st>>>(s);
     return cudaGetLastError();
 }
 
@@ -1155,6 +1202,19 @@ cudaError_t launch_mean_finish(const double *partials, int64_t nblocks, double *
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     mean_finish_kernel<<<1, 256, 0, st>>>(scratch, 256, sums);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_select(const SelectDev &q, int fill, cudaStream_t st) {
+    const long long rows = q.row1 - q.row0;
+    if (rows <= 0) return cudaSuccess;
+    select_kernel<<<(unsigned) ((rows + 7) / 8), 256, 0, st>>>(q, fill);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ci(const double *M, int64_t ld, const int32_t *idx, int32_t b, int32_t n, double *stat, cudaStream_t st) {
+    if (b <= 0) return cudaSuccess;
+    ci_kernel<<<(unsigned) b, 256, 0, st>>>(M, ld, idx, n, stat);
     return cudaGetLastError();
 }
 

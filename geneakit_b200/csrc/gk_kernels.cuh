@@ -14,7 +14,7 @@ constexpr int kStepP1Stages = 3;     // phase-1 TMA stages (33 KB each)
 constexpr int kP1Classes = 8;        // phase-1 item: 8 classes of a panel ...
 constexpr int kP1Cols = 256;         // ... x 256 columns of the previous matrix (2 KB row segments)
 constexpr int kCB = 32;           // columns of the previous matrix per phase-1 work item
-// third step kernel (phi_step_g4_kernel, one GPU): phase 1 through TMA gather4 over a tensor map of the previous matrix
+// third step kernel (phi_step_g4_kernel, one GPU): phase 1 through TMA bulk copies of 4 KB row segments, phase 2 straight from L2
 constexpr int kG4Stages = 2;         // TMA stages (a FIFO the producer fills and all consumer warps drain together)
 constexpr int kG4Consumers = 4;      // phase-1 consumer warps
 constexpr int kG4P2Warps = 10;       // phase-2 warps (ring rows straight from L2 into registers)
@@ -105,9 +105,7 @@ struct ExpandDev {
 int step_grid();             // CTAs of the persistent step kernel (SMs x resident CTAs)
 cudaError_t launch_step(const StepDev &s, cudaStream_t st);
 cudaError_t launch_step_tma(const StepDev &s, cudaStream_t st);
-// tmap128 / tmap64: 128-byte CUtensorMap objects over the previous matrix ((Kpad_prev + 1) rows, the last one all zero) with
-// boxes of {130, 1} and {66, 1} doubles (two more columns than an item uses: the staged rows get a bank-conflict-free pitch)
-cudaError_t launch_step_g4(const StepDev &s, const void *tmap128, const void *tmap64, cudaStream_t st);
+cudaError_t launch_step_g4(const StepDev &s, cudaStream_t st);
 cudaError_t launch_diag(const DiagDev &d, cudaStream_t st);
 cudaError_t launch_init(double *G0, double *d0, const int32_t *flags, int64_t K0, int64_t Kpad0, cudaStream_t st);
 cudaError_t launch_init_rows(double *G0, double *d0, const int32_t *flags, int64_t K0, int64_t Kpad0,
@@ -119,6 +117,21 @@ cudaError_t launch_eye(double *out, int64_t m, int64_t row0, int64_t row1, doubl
 // two-stage deterministic reduction of the per-CTA partials: scratch holds 2*256 doubles
 cudaError_t launch_mean_finish(const double *partials, int64_t nblocks, double *scratch, double *sums /*2*/, cudaStream_t st);
 cudaError_t configure_kernels();
+
+// device-side consumers of the m x m result: pair selection (gen.phiOver, sparse CSR) and gen.phiCI's bootstrap statistic
+struct SelectDev {
+    const double *M;          // rows [row0, row1) of the result, m columns
+    int64_t m, row0, row1;
+    int32_t mode;             // 0: j < i and value > thr (phiOver); 1: j <= i and |2 value| > thr (sparse CSR, float values)
+    double thr;
+    int64_t *row_count;       // pass 1 out
+    const int64_t *row_off;   // pass 2 in: exclusive prefix of row_count
+    int32_t *oi, *oj;
+    double *ov;
+    float *ovf;
+};
+cudaError_t launch_select(const SelectDev &q, int fill, cudaStream_t st);
+cudaError_t launch_ci(const double *M, int64_t ld, const int32_t *idx /* b x n */, int32_t b, int32_t n, double *stat /* b */, cudaStream_t st);
 
 // gen.gc propagation: out row = 0.5*w0*row(p0) + 0.5*w1*row(p1), then seed own ancestor columns.
 struct GcStepDev {

@@ -289,7 +289,7 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
             for (int g = G - 1 - maxp[x]; g <= G - 1 - minp[x]; g++) W[g].members.push_back(x);
     }
     auto enter = [&](int32_t x) { return G - 1 - maxp[x]; };
-    std::atomic<bool> failed(false);
+    std::atomic<bool> failed(false), over_budget(false);
 
     // ---- stage A (parallel): classes of every cut, in natural order --------------------------------
     parallel_steps(0, G, threads, [&](int g) {
@@ -492,7 +492,7 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
             while (b < uses.size() && uses[b].ind == uses[a].ind) b++;
             const int64_t k = (int64_t) (b - a);
             budget -= k * (k + 1) / 2;
-            if (budget < 0) { failed = true; return; }
+            if (budget < 0) { over_budget = true; return; }
             const int32_t pc = Cp->pos[Cp->nat(uses[a].ind)];
             for (size_t x = a; x < b; x++)
                 for (size_t y = a; y <= x; y++) {
@@ -520,9 +520,15 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
             a = b;
         }
     });
+    if (over_budget) {
+        // an individual of a multi-member sibship with tens of thousands of mates: the "same individual" correction list would
+        // be quadratic in the mates.  Code 3: the caller plans again with one matrix row per individual (no corrections at all).
+        P.error = "the sibship compression needs too many corrections for this pedigree (an individual of a multi-member sibship "
+                  "has tens of thousands of mates); plan with compress=0";
+        P.error_code = 3; return false;
+    }
     if (failed) {
-        P.error = "internal: a parent is missing from the previous cut, or an individual of a multi-member sibship has too many "
-                  "mates for the correction list (compress=0 avoids the latter)";
+        P.error = "internal: a parent is missing from the previous cut";
         P.error_code = 1; return false;
     }
 

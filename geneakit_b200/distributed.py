@@ -54,17 +54,30 @@ def _dvec(job, g):
 
 class ShardedPhi:
     """gen.phi across the ranks of the default process group: `.local` rows stay in this rank's
-    HBM, `.mean()` is the global gen.phiMean, `.to_host()` copies this rank's row block."""
+    HBM, `.mean()` is the global gen.phiMean, `.to_host()` copies this rank's row block.
 
-    def __init__(self, pedigree, proband_ids=(), rank=None, world=None, **gk):
+    The job's kernels and the per-cut collectives run on ONE torch stream owned by this object (the caller may pass its
+    own with stream=<cudaStream_t handle of a non-default torch stream>): the all-gather after a cut is what orders the
+    peers' reads of this rank's rows, so it must be enqueued behind the cut's kernels."""
+
+    def __init__(self, pedigree, proband_ids=(), rank=None, world=None, stream=None, **gk):
         import torch.distributed as dist
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
-        self.job = cgeneakit.DevicePhi(pedigree, proband_ids, rank=self.rank, world=self.world, **gk)
+        self._tstream = None
+        if self.world > 1:
+            import torch
+            if stream is None:
+                self._tstream = torch.cuda.Stream()
+                stream = self._tstream.cuda_stream
+            else:
+                self._tstream = torch.cuda.ExternalStream(int(stream))
+        self.job = cgeneakit.DevicePhi(pedigree, proband_ids, rank=self.rank, world=self.world, stream=stream, **gk)
         self.m = self.job.m
         self.row0, self.row1 = self.job.row0, self.job.row1
         self.G = self.job.stats()["n_cuts"]
         self._dv = None
+        self._fence = None
 
     def upload(self):
         """Allocate, then make every rank's matrix buffers addressable by every rank (CUDA IPC)."""
@@ -86,20 +99,30 @@ class ShardedPhi:
             for g in range(self.G):
                 p, chunk, total = _dvec(self.job, g)
                 self._dv.append((torch.as_tensor(_DevArray(p, total), device="cuda"), chunk))
+            self._fence = torch.zeros(1, dtype=torch.int32, device="cuda")
             dist.barrier()
         return self
 
+    def replan(self):
+        """Plan again on the host + copy the plan to the device again (every rank plans the same pedigree)."""
+        self.job.replan()
+        return self
+
     def run(self):
+        import torch
         import torch.distributed as dist
         if self.world == 1:
             self.job.run()
             return self
-        for g in range(self.G):
-            check(lib.gk_phi_run_step(self.job._h, g))
-            full, chunk = self._dv[g]
-            # the only per-cut collective: 8 bytes per class, and the barrier between cuts
-            dist.all_gather_into_tensor(full, full[self.rank * chunk:(self.rank + 1) * chunk])
-        check(lib.gk_phi_finish(self.job._h))
+        with torch.cuda.stream(self._tstream):
+            for g in range(self.G):
+                check(lib.gk_phi_run_step(self.job._h, g))
+                full, chunk = self._dv[g]
+                # the only per-cut collective: 8 bytes per class, and the barrier between cuts
+                dist.all_gather_into_tensor(full, full[self.rank * chunk:(self.rank + 1) * chunk])
+            check(lib.gk_phi_finish(self.job._h))
+            # the expansion read the peers' rows: nobody may start the next pass (or free) before everybody is done
+            dist.all_reduce(self._fence)
         return self
 
     def mean(self):
@@ -120,13 +143,19 @@ class ShardedPhi:
         return np.concatenate(parts, axis=0)
 
     def close(self):
+        if self.world > 1 and self._dv is not None:
+            import torch
+            import torch.distributed as dist
+            self.job.sync()
+            torch.cuda.synchronize()
+            dist.barrier()                 # a peer may still be reading this rank's buffers
         self._dv = None
         self.job.close()
 
 
 class VirtualShardedPhi:
     """The sharded algorithm with all `world` ranks emulated in ONE process on ONE GPU: every
-    rank's job runs its step back to back on one stream, peers are plain pointers, the all-gather
+    rank's job runs its step back to back on ONE stream (rank 0's), peers are plain pointers, the all-gather
     is a device copy.  Used by the GPU tests (a fresh box has one GPU) and to study the sharded
     kernels without NVLink."""
 
@@ -137,7 +166,13 @@ class VirtualShardedPhi:
         self.G = self.jobs[0].stats()["n_cuts"]
 
     def upload(self):
-        for j in self.jobs:
+        # ONE stream for every rank's job: the persistent step kernels of different ranks must run one after the other
+        self.jobs[0].upload()
+        st = C.c_void_p()
+        check(lib.gk_phi_stream(self.jobs[0]._h, C.byref(st)))
+        for j in self.jobs[1:]:
+            j._opts.stream = st
+            check(lib.gk_phi_set_stream(j._h, st))
             j.upload()
         bufs = []
         for j in self.jobs:

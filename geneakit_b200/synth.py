@@ -3,8 +3,6 @@ monogamous couples drawn at random inside the previous generation, each child dr
 uniformly; ids 1..N in generation order (already topologically sorted: load with sorted=True)."""
 import numpy as np
 
-from . import cgeneakit
-
 
 def generation_widths(n_individuals, n_generations, founders=None):
     """Equal widths, or (founders given) w_g = min(W, founders*2^g) with W solved so that the
@@ -50,13 +48,19 @@ def synthetic_arrays(n_individuals, n_generations, seed, founders=None):
     return ids, fathers, mothers, sexes, offs
 
 
-def synthetic_pedigree(n_individuals, n_generations, n_probands, seed, founders=None):
-    """(Pedigree, proband ids): probands sampled without replacement from the last generation,
-    sorted by id."""
-    ids, fathers, mothers, sexes, offs = synthetic_arrays(n_individuals, n_generations, seed, founders)
-    ped = cgeneakit.load_pedigree_from_vectors(ids, fathers, mothers, sexes, True)
+def synthetic_probands(ids, offs, n_probands, seed):
+    """Probands sampled without replacement from the last generation, sorted by id (numpy only)."""
     rng = np.random.default_rng(seed + 1000003)
     last = ids[offs[-2]:offs[-1]]
     k = min(n_probands, len(last))
     pro = np.sort(rng.choice(last, size=k, replace=False)) if k < len(last) else last.copy()
-    return ped, [int(x) for x in pro]
+    return [int(x) for x in pro]
+
+
+def synthetic_pedigree(n_individuals, n_generations, n_probands, seed, founders=None):
+    """(Pedigree, proband ids): probands sampled without replacement from the last generation,
+    sorted by id."""
+    from . import cgeneakit          # (this module stays importable without the CUDA library: the reference arm of bench.py)
+    ids, fathers, mothers, sexes, offs = synthetic_arrays(n_individuals, n_generations, seed, founders)
+    ped = cgeneakit.load_pedigree_from_vectors(ids, fathers, mothers, sexes, True)
+    return ped, synthetic_probands(ids, offs, n_probands, seed)

@@ -29,7 +29,9 @@ extern "C" {
 #define GK_ERR_OOM       4   /* device (or host) memory exhausted */
 #define GK_ERR_STATE     5   /* call order violated on a job handle */
 
-#define GK_ABI_VERSION   1
+#define GK_ABI_VERSION   2
+
+#define GK_FLAG_DIAGONAL_ONLY 1   /* job without the m x m result: only the self kinships / inbreeding coefficients (gen.f) */
 
 typedef struct gk_opts {
     int32_t struct_size;   /* sizeof(gk_opts); lets the ABI grow */
@@ -40,9 +42,13 @@ typedef struct gk_opts {
     int32_t rank;          /* row shard owned by this process (multi-GPU), 0 .. world-1; -1 with world > 1: the one-shot
                               entry points drive GPUs 0 .. world-1 from this process (also: environment GENEAKIT_GPUS=N) */
     int32_t world;         /* number of row shards (<= 8), 0/1 = single GPU */
-    int32_t reserved0;
+    int32_t flags;         /* GK_FLAG_* bits */
     void   *stream;        /* cudaStream_t to enqueue on, NULL = the library's own stream */
 } gk_opts;
+
+/* Defaults: current device, automatic compression and class order, one GPU.  (A zero-filled gk_opts is NOT the default:
+ * compress = 0 and order = 0 are the uncompressed / debug-order settings.) */
+void gk_opts_init(gk_opts *opts);
 
 /* ---- one-shot entry points: what the binding lambdas call -------------------------------- */
 
@@ -62,6 +68,11 @@ int gk_phi_f64(int32_t n, const int32_t *sire, const int32_t *dam,
 int gk_gc_f64(int32_t n, const int32_t *sire, const int32_t *dam,
               int32_t m, const int32_t *pro, int32_t a, const int32_t *anc,
               double *out, const gk_opts *opts);
+
+/* Replaces compute_inbreedings(Pedigree<>&, proband_ids) (lib/compute.cpp:725-814) behind gen.f (geneakit/compute.py:255-282):
+ * out[i] = inbreeding coefficient of proband i = 2 phi(i, i) - 1, caller order.  The recurrence runs without the expansion. */
+int gk_f_f64(int32_t n, const int32_t *sire, const int32_t *dam,
+             int32_t m, const int32_t *pro, double *out, const gk_opts *opts);
 
 /* Timing / traffic of the last gk_gc_f64 call of this process (the benchmark's --op gc line). */
 typedef struct gk_gc_stats {
@@ -171,6 +182,21 @@ int gk_phi_step_times(gk_phi_job *job, float *ms, int32_t cap);
  * (16 B per updated cell on discrete-generation pedigrees) -- and 8*(m^2 + min(m,K)^2) for the
  * final expansion. */
 int gk_phi_step_bytes(gk_phi_job *job, int64_t *bytes, int32_t cap);
+/* ---- device-side consumers of a finished job: the m x m matrix need not cross PCIe ------------- */
+int gk_phi_diag(gk_phi_job *job, double *self_kinship /* m, caller order */);
+int gk_phi_f(gk_phi_job *job, double *inbreeding /* m: 2 phi(i,i) - 1 */);
+/* gen.phiOver (geneakit/compute.py:135-190): pairs i > j with kinship > threshold, reference order; indices are positions
+ * in the caller's proband list.  gk_phi_over leaves the pairs in HBM, gk_phi_over_fetch copies `count` triples out. */
+int gk_phi_over(gk_phi_job *job, double threshold, int64_t *count);
+int gk_phi_over_fetch(gk_phi_job *job, int32_t *pro1_idx, int32_t *pro2_idx, double *kinship);
+/* the CSR gen.phi(sparse=True) returns (lib/compute.cpp:272-487 behind lib/cgeneakit.cpp:433-486): lower triangle with
+ * the diagonal, float32, |2 phi| > 1e-9; indptr has m + 1 entries. */
+int gk_phi_sparse(gk_phi_job *job, int64_t *nnz);
+int gk_phi_sparse_fetch(gk_phi_job *job, int64_t *indptr, int32_t *indices, float *data);
+/* gen.phiCI's bootstrap statistic (geneakit/compute.py:226-229) for b resamples of n indices each: mean of the entries
+ * < 0.5 of phi[idx][:, idx]. */
+int gk_phi_ci_stats(gk_phi_job *job, const int32_t *idx /* b*n */, int32_t b, int32_t n, double *stats /* b */);
+
 /* GK_PROF=1 only: cycle counters of the gather4 step kernel's warp roles, summed over warps and steps of the last run:
  * [0] producer loop, [1] its idle polls, [2] polls blocked on a stage, [3] on the ring slot; [4] phase-1 consumers,
  * [5] of which waiting for TMA data; [7] phase-2 warps, [8] of which waiting for phase 1, [10] publishing (fence). */
@@ -185,10 +211,14 @@ void gk_phi_free(gk_phi_job *job);
  *     gk_phi_finish(job)
  * The step kernel reads the parent rows of its own panels straight from the owners' HBM over NVLink
  * (peer loads inside the kernel); the all-gather of d (8 bytes per class) is the only collective and
- * doubles as the barrier between cuts.  gk_phi_set_peer wires jobs that live in ONE process
- * (several ranks emulated on one GPU, used by the tests). */
+ * doubles as the barrier between cuts; it must be enqueued on the job's stream (or ordered against it), and
+ * gk_phi_finish reads the peers' rows once more: a stream-ordered collective after it must precede the next
+ * gk_phi_run_step(job, 0) and gk_phi_free.  gk_phi_set_peer wires jobs that live in ONE process (several ranks emulated
+ * on one GPU -- all on ONE stream: persistent kernels of different ranks must never be co-scheduled on a GPU). */
 int gk_phi_ipc_export(gk_phi_job *job, void *handles /* 2 x 64 bytes */);
 int gk_phi_ipc_open(gk_phi_job *job, int32_t peer_rank, const void *handles);
+int gk_phi_set_stream(gk_phi_job *job, void *stream);     /* before gk_phi_upload: enqueue on this cudaStream_t */
+int gk_phi_stream(gk_phi_job *job, void **stream);        /* the cudaStream_t the job enqueues on (after gk_phi_upload) */
 int gk_phi_local_buffers(gk_phi_job *job, void **buf0, void **buf1);
 int gk_phi_set_peer(gk_phi_job *job, int32_t peer_rank, void *buf0, void *buf1);
 int gk_phi_peers_ready(gk_phi_job *job);

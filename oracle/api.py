@@ -213,6 +213,10 @@ class Reference:
         L.gkref_cut_sizes.argtypes = [C.c_void_p, C.c_int, _I, _I, C.c_int]
         L.gkref_set_threads.argtypes = [C.c_int]
         L.gkref_last_error.restype = C.c_char_p
+        if hasattr(L, "gkref_f"):
+            L.gkref_f.argtypes = [C.c_void_p, C.c_int, _I, _D]
+            L.gkref_sparse.argtypes = [C.c_void_p, C.c_int, _I, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.gkref_sparse.restype = C.c_longlong
 
     def genealogy(self, ids, fathers, mothers, sexes, sorted=False):
         h = self.L.gkref_load_vectors(len(ids), _i32(ids), _i32(fathers), _i32(mothers), _i32(sexes),
@@ -270,6 +274,27 @@ class Reference:
         if rc:
             raise RuntimeError(self.L.gkref_last_error().decode())
         return out
+
+    def f(self, h, pro=None):
+        """gen.f: the reference's compute_inbreedings."""
+        pro = self.pro(h) if pro is None or len(pro) == 0 else list(pro)
+        p = _i32(pro)
+        out = np.empty(len(p), dtype=np.float64)
+        if self.L.gkref_f(h, len(p), p, out):
+            raise RuntimeError(self.L.gkref_last_error().decode())
+        return out
+
+    def sparse(self, h, pro=None):
+        """gen.phi(sparse=True): (data float32, indices int32, indptr int64) of the reference's CSR."""
+        pro = self.pro(h) if pro is None or len(pro) == 0 else list(pro)
+        p = _i32(pro)
+        nnz = self.L.gkref_sparse(h, len(p), p, None, None, None)
+        if nnz < 0:
+            raise RuntimeError(self.L.gkref_last_error().decode())
+        data = np.empty(max(nnz, 1), dtype=np.float32); idx = np.empty(max(nnz, 1), dtype=np.int32)
+        ptr = np.empty(len(p) + 1, dtype=np.int64)
+        self.L.gkref_sparse(h, len(p), p, data.ctypes.data, idx.ctypes.data, ptr.ctypes.data)
+        return data[:nnz], idx[:nnz], ptr
 
     def cut_sizes(self, h, pro=None):
         p = _i32([] if pro is None else pro)

@@ -100,6 +100,9 @@ def emit(R, name, rows, pro=None, anc=None, sorted_flag=False, with_gc=True, gc_
              cut_sizes=np.asarray(R.cut_sizes(h, pro_l), dtype=np.int32),
              required_gb=np.float64(R.required_gb(h, pro_l)),
              phi=phi, phi_sha256=np.bytes_(hashlib.sha256(phi.tobytes()).hexdigest()))
+    d["f"] = R.f(h, pro_l)                                   # gen.f (compute_inbreedings)
+    if len(set(pro_l)) == len(pro_l):                        # gen.phi(sparse=True): CSR of the lower triangle, float32
+        d["sp_data"], d["sp_indices"], d["sp_indptr"] = R.sparse(h, pro_l)
     if with_gc:
         gc = R.gc(h, pro_l, anc_l)
         d["gc_sha256"] = np.bytes_(hashlib.sha256(gc.tobytes()).hexdigest())

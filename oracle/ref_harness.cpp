@@ -16,6 +16,8 @@
 //   gkref_phi           -> compute_kinships             (compute.cpp:638-700)
 //   gkref_gc            -> compute_genetic_contributions(compute.cpp:832-862)
 //   gkref_required_gb   -> get_required_memory_for_kinships (compute.cpp:591-635)
+//   gkref_f             -> compute_inbreedings          (compute.cpp:725-814)
+//   gkref_sparse        -> compute_kinships_sparse      (compute.cpp:272-487)
 //   gkref_cut_sizes     -> cut_vertices                 (compute.cpp:119-135)
 #include <cstring>
 #include <stdexcept>
@@ -113,6 +115,40 @@ int gkref_gc(void *h, int m, const int *pro, int a, const int *anc, double *out)
     } catch (const std::exception &e) {
         g_err = e.what();
         return 2;
+    }
+}
+
+// gen.f: compute_inbreedings (compute.cpp:725-814).  out: m doubles.
+int gkref_f(void *h, int m, const int *pro, double *out) {
+    try {
+        std::vector<int> ids(pro, pro + m);
+        std::vector<double> f = compute_inbreedings(*static_cast<Pedigree<> *>(h), ids);
+        std::memcpy(out, f.data(), f.size() * sizeof(double));
+        return 0;
+    } catch (const std::out_of_range &e) {
+        g_err = e.what();
+        return 1;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return 2;
+    }
+}
+
+// gen.phi(sparse=True): compute_kinships_sparse (compute.cpp:272-487), CSR branch.  First call with data == NULL returns
+// nnz; the second fills data (nnz floats), indices (nnz ints), indptr (m + 1 int64).
+long long gkref_sparse(void *h, int m, const int *pro, float *data, int *indices, long long *indptr) {
+    try {
+        std::vector<int> ids(pro, pro + m);
+        SparseResult r = compute_kinships_sparse(*static_cast<Pedigree<> *>(h), ids, false, false);
+        if (data) {
+            std::memcpy(data, r.data.data(), r.data.size() * sizeof(float));
+            std::memcpy(indices, r.indices.data(), r.indices.size() * sizeof(int));
+            for (size_t i = 0; i < r.indptr.size(); i++) indptr[i] = (long long) r.indptr[i];
+        }
+        return (long long) r.data.size();
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
     }
 }
 

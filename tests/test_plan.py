@@ -22,13 +22,13 @@ def _ped(g):
 def test_library_exports_every_declared_symbol():
     header = open(ROOT + "/include/geneakit_b200.h").read()
     declared = set(re.findall(r"\b(gk_[a-z0-9_]+)\s*\(", header))
-    declared -= {"gk_opts", "gk_phi_stats", "gk_step_view"}
+    declared -= {"gk_opts", "gk_phi_stats", "gk_step_view", "gk_gc_stats"}
     assert declared, "no declarations found"
     raw = C.CDLL(_lib.LIB_PATH)
     missing = [s for s in sorted(declared) if not hasattr(raw, s)]
     assert not missing, missing
     assert set(_lib.EXPORTS) <= declared
-    assert _lib.lib.gk_abi_version() == 1
+    assert _lib.lib.gk_abi_version() == 2
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -79,3 +79,27 @@ def test_compression_shrinks_the_matrices():
     assert sum(b.class_sizes()) < sum(a.class_sizes())
     assert b.stats()["cells_device"] < a.stats()["cells_device"]
     a.close(); b.close()
+
+
+def test_correction_overflow_falls_back_to_one_row_per_individual():
+    """An individual of a multi-member sibship with tens of thousands of mates would need a quadratic correction list:
+    the planner reports it and gk_phi_plan plans again uncompressed on its own (a drop-in must not ask the caller)."""
+    mates = 17000
+    # founders 0, 1 -> full sibs 2, 3 (a two-member class: both are parents); 2 mates with `mates` founders, one child each
+    sire = [-1, -1, 0, 0] + [-1] * mates + [2] * (mates - 1) + [3]
+    dam = [-1, -1, 1, 1] + [-1] * mates + list(range(4, 4 + mates))
+    n = len(sire)
+    ids = np.arange(1, n + 1)
+    ped = gk.cgeneakit.Pedigree(ids, sire, dam, np.ones(n))
+    pro = [int(x) for x in ids[4 + mates:]]                   # every child
+    job = gk.cgeneakit.DevicePhi(ped, pro)                    # planning is host-only
+    st = job.stats()
+    assert st["compressed"] == 0 and st["n_cuts"] == 3
+    job.close()
+    few = 50
+    sire2 = [-1, -1, 0, 0] + [-1] * few + [2] * (few - 1) + [3]
+    dam2 = [-1, -1, 1, 1] + [-1] * few + list(range(4, 4 + few))
+    ids2 = np.arange(1, len(sire2) + 1)
+    small = gk.cgeneakit.DevicePhi(gk.cgeneakit.Pedigree(ids2, sire2, dam2, np.ones(len(sire2))), [int(x) for x in ids2[4 + few:]])
+    assert small.stats()["compressed"] == 1 and small.stats()["corrections"] > 0
+    small.close()
