@@ -340,6 +340,7 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         sp.replan().run()                          # host planning + H2D of the plan + every kernel of the pass
+        stream.synchronize()                       # a pass ends before the next one is planned (no overlap across passes)
     e1.record(stream)
     barrier()
     sampler.stop.set()
@@ -437,13 +438,16 @@ def main():
                 if it > 0:
                     dts.append(time.time() - t0)
             got = mu.value
+            tm = np.zeros(6)
+            lib.gk_phi_last_timing(tm)
             assert abs(got - mean) <= 1e-12 * abs(mean), (got, mean)
             dt = sum(dts) / len(dts)
             e2e = {"value": pairs / dt, "unit": "pairs/s", "seconds_per_step": dt,
                    "h2d_bytes_per_step": plan_bytes * world,
                    "d2h_bytes_per_step": int(m) * int(m) * 8 + 16 * world, "host_buffer": "pinned" if pinned else "pageable",
                    "driver": "one process, gk_phi_f64 with opts.world = %d" % world if world > 1 else "gk_phi_f64",
-                   "phi_mean": got, "steps": args.e2e_steps}
+                   "phi_mean": got, "steps": args.e2e_steps,
+                   "last_call_seconds": {"plan": tm[0], "alloc_and_h2d": tm[1], "kernels": tm[2], "d2h": tm[3], "total": tm[4]}}
             lib.gk_cache_release()
             if pinned:
                 lib.gk_host_free(ptr)

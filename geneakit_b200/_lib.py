@@ -78,6 +78,7 @@ def _load():
     L.gk_last_error.restype = C.c_char_p
     L.gk_abi_version.restype = i32
     L.gk_opts_init.argtypes = [OP]; L.gk_opts_init.restype = None
+    L.gk_phi_last_timing.argtypes = [np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")]; L.gk_phi_last_timing.restype = None
     L.gk_host_alloc.argtypes = [C.c_uint64]; L.gk_host_alloc.restype = vp
     L.gk_host_free.argtypes = [vp]
     L.gk_phi_f64.argtypes = [i32, _I, _I, i32, _I, vp, C.POINTER(C.c_double), OP]
@@ -143,7 +144,7 @@ EXPORTS = [
     "gk_phi_ipc_export", "gk_phi_ipc_open", "gk_phi_local_buffers", "gk_phi_set_peer", "gk_phi_peers_ready",
     "gk_phi_run_step", "gk_phi_finish", "gk_phi_dvec", "gk_phi_dvec_copy_from",
     "gk_phi_debug_prof", "gk_cache_release", "gk_gc_last_stats",
-    "gk_opts_init", "gk_f_f64", "gk_phi_stream", "gk_phi_set_stream", "gk_phi_replan", "gk_phi_reupload", "gk_phi_clone_rank", "gk_phi_diag", "gk_phi_f",
+    "gk_opts_init", "gk_phi_last_timing", "gk_f_f64", "gk_phi_stream", "gk_phi_set_stream", "gk_phi_replan", "gk_phi_reupload", "gk_phi_clone_rank", "gk_phi_diag", "gk_phi_f",
     "gk_phi_over", "gk_phi_over_fetch", "gk_phi_sparse", "gk_phi_sparse_fetch", "gk_phi_ci_stats",
 ]
 

@@ -21,6 +21,8 @@ namespace {
 thread_local std::string g_err;
 std::mutex g_call_mu;              // the one-shot entry points run one call at a time (SURVEY 8b "internal mutex")
 gk_gc_stats g_gc_stats{};
+double g_phi_timing[6] = {};       // last gk_phi_f64: plan, upload, kernels, D2H, total seconds; GPUs used
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -173,7 +175,7 @@ void destroy(gk_phi_job *j) {
     for (int q = 0; q < gk::kMaxShards; q++)
         for (int p = 0; p < 2; p++)
             if (j->peer_ipc[q][p] && j->peer[q][p]) cudaIpcCloseMemHandle(j->peer[q][p]);
-    if (j->stream) cudaStreamSynchronize(j->stream);     // nothing of this job may still run when its blocks go back to the cache
+    if (j->stream && cudaStreamSynchronize(j->stream) != cudaSuccess) cudaGetLastError();   // nothing of this job may still run when its blocks go back to the cache
     for (int p = 0; p < 2; p++) { pool_free(j->buf[p]); pool_free(j->dvec[p]); }
     pool_free(j->ring);
     pool_free(j->zero_row);
@@ -208,8 +210,19 @@ int select_device(const gk_opts *o, int *dev_out) {
     return GK_OK;
 }
 
-std::once_flag g_cfg_once;
+// function attributes (dynamic shared memory) are per device: configure each device the first time a job uploads to it
+std::mutex g_cfg_mu;
+int g_cfg_state[64] = {};            // 0 = not configured, 1 = ok, 2 = failed
 cudaError_t g_cfg_err = cudaSuccess;
+cudaError_t configure_device(int dev) {
+    std::lock_guard<std::mutex> lock(g_cfg_mu);
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (g_cfg_state[dev] == 0) {
+        g_cfg_err = gk::configure_kernels();
+        g_cfg_state[dev] = g_cfg_err == cudaSuccess ? 1 : 2;
+    }
+    return g_cfg_state[dev] == 1 ? cudaSuccess : g_cfg_err;
+}
 
 // panels of step g owned by each rank: equal blocks of cpp = ceil(np / world) panels
 void panel_range(int np, int rank, int world, int32_t *pb, int32_t *pe, int32_t *cpp) {
@@ -402,8 +415,9 @@ static void configure_job(gk_phi_job *j) {
     // fixed by rank) must keep J <= I and store the mirror tile into the rows of J's owner instead
     j->full_rows = (j->world > 1 && !j->planp->ranked) ? 1 : 0;
     j->use_tma = j->world > 1 ? 1 : 0;
-    j->use_g4 = j->world > 1 ? 0 : 1;
-    if (const char *e = std::getenv("GK_STEP_KERNEL")) { j->use_tma = (e[0] == 't') ? 1 : 0; j->use_g4 = (e[0] == 'g' && j->world == 1) ? 1 : 0; }
+    j->use_g4 = 1;                       // large cuts; ranked multi-GPU jobs need the kernel that stores mirror tiles into a peer's rows
+    if (const char *e = std::getenv("GK_STEP_KERNEL")) { j->use_tma = (e[0] == 't') ? 1 : 0; j->use_g4 = (e[0] == 'g') ? 1 : 0; }
+    if (j->world > 1 && j->planp->ranked) j->use_g4 = 0;
     if (j->world > 1 && j->planp->ranked) j->use_tma = 1;      // only that kernel stores mirror tiles into a peer's rows
     if (const char *e = std::getenv("GK_FULL_ROWS")) if (e[0] == '1' && !j->planp->ranked) j->full_rows = 1;
     if (const char *e = std::getenv("GK_G4_MIN_K")) j->g4_min_k = std::atoi(e);
@@ -421,7 +435,7 @@ static void configure_job(gk_phi_job *j) {
         const StepOffsets &o = j->off[g];
         const int64_t rps = (int64_t) j->off[g - 1].cpp * gk::kPanel;
         std::vector<int32_t> stamp((size_t) std::max<int64_t>(S.K_prev, 1), -1);
-        const int unit = j->use_tma ? gk::kSub : gk::kPanel;          // classes whose parent rows are staged together
+        const int unit = j->use_g4 ? 16 : (j->use_tma ? gk::kSub : gk::kPanel);   // classes whose parent rows are staged together
         for (int p = o.pb * gk::kPanel / unit; p < o.pe * gk::kPanel / unit; p++)
             for (int i = p * unit; i < (p + 1) * unit; i++)
                 for (int q = 0; q < 2; q++) {
@@ -586,8 +600,7 @@ int gk_phi_upload(gk_phi_job *j) {
     if (j->uploaded) return GK_OK;
     int rc = select_device(&j->opts, &j->device);
     if (rc) return rc;
-    std::call_once(g_cfg_once, [] { g_cfg_err = gk::configure_kernels(); });
-    if (g_cfg_err != cudaSuccess) return cuda_fail(g_cfg_err, "kernel configuration (is this an sm_100 device?)");
+    { const cudaError_t ce = configure_device(j->device); if (ce != cudaSuccess) return cuda_fail(ce, "kernel configuration (is this an sm_100 device?)"); }
     gk::PhiPlan &P = *j->planp;
     const int G = P.G;
     if (j->opts.stream) j->stream = (cudaStream_t) j->opts.stream;
@@ -609,7 +622,7 @@ int gk_phi_upload(gk_phi_job *j) {
     for (int g = 0; g < G; g++) {
         const gk::StepPlan &S = P.steps[g];
         const int64_t rows = (int64_t) (j->off[g].pe - j->off[g].pb) * gk::kPanel;
-        need[g & 1] = std::max(need[g & 1], rows * S.Kpad + S.Kpad);       // + the all-zero row the gather4 kernel addresses as row Kpad
+        need[g & 1] = std::max(need[g & 1], rows * S.Kpad);
         if (g + 1 < G) max_prev = std::max(max_prev, S.Kpad);
         dlen = std::max(dlen, (int64_t) j->off[g].cpp * gk::kPanel * j->world);
     }
@@ -642,8 +655,8 @@ int gk_phi_upload(gk_phi_job *j) {
     int64_t ring_doubles = 32;
     for (int g = 1; g < G; g++) ring_doubles = std::max(ring_doubles, (int64_t) j->off[g].ring_n * P.steps[g].Kpad_prev * gk::kPanel);
     GK_CUDA(pool_alloc_t(&j->ring, (size_t) ring_doubles * sizeof(double), j->device));
-    GK_CUDA(pool_alloc_t(&j->zero_row, gk::kP1Cols * sizeof(double), j->device));
-    GK_CUDA(cudaMemsetAsync(j->zero_row, 0, gk::kP1Cols * sizeof(double), j->stream));
+    GK_CUDA(pool_alloc_t(&j->zero_row, 1024 * sizeof(double), j->device));
+    GK_CUDA(cudaMemsetAsync(j->zero_row, 0, 1024 * sizeof(double), j->stream));
     j->device_bytes += ring_doubles * 8;
     GK_CUDA(pool_alloc_t(&j->partials, (size_t) std::max<int64_t>(j->nblocks_expand, 1) * 2 * sizeof(double), j->device));
     GK_CUDA(pool_alloc_t(&j->scratch, 2 * 256 * sizeof(double), j->device));
@@ -788,8 +801,6 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     d.total1 = o.total1; d.total2 = o.total2; d.n1pp = o.n1pp;
     d.ncb256 = (int32_t) ((S.Kpad_prev + gk::kP1Cols - 1) / gk::kP1Cols);
     if (o.use_g4) {
-        double *prev = j->buf[(g - 1) & 1];
-        GK_CUDA(cudaMemsetAsync(prev + S.Kpad_prev * S.Kpad_prev, 0, (size_t) S.Kpad_prev * sizeof(double), st));   // row Kpad_prev := 0
         d.prow4 = j->ints + o.prow4; d.pcnt4 = j->ints + o.pcnt4; d.slots4 = j->ints + o.slots4;
         d.item_off = reinterpret_cast<const int64_t *>(j->ints + o.item_off);
         d.total_g4 = o.total_g4;
@@ -1228,8 +1239,10 @@ int multi_phi(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, con
     if (virt) GK_CUDA(cudaGetDevice(&base));
     o.struct_size = sizeof(gk_opts); o.world = ndev; o.rank = 0; o.device = virt ? base : 0; o.stream = nullptr;
     gk_phi_job *j0 = nullptr;
+    const double t0 = now_s();
     int rc = gk_phi_plan(n, sire, dam, m, pro, &o, &j0);
     if (rc) return rc;
+    const double t1 = now_s();
     M.jobs.push_back(j0);
     for (int q = 1; q < ndev; q++) {
         gk_phi_job *jq = nullptr;
@@ -1278,6 +1291,7 @@ int multi_phi(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, con
         GK_CUDA(cudaEventCreateWithFlags(&M.cut_done[q], cudaEventDisableTiming));
     }
     const int G = j0->planp->G;
+    const double t2 = now_s();
     if (o.verbose) {
         for (int g = 0; g < G; g++) std::printf("Cut size %d/%d: %d\n", g + 1, G, (int) j0->planp->steps[g].cut_size);
         std::printf("Computing the kinship matrix:\n");
@@ -1294,6 +1308,8 @@ int multi_phi(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, con
         }
     }
     for (int q = 0; q < ndev; q++) { rc = gk_phi_finish(M.jobs[q]); if (rc) return rc; }
+    for (int q = 0; q < ndev; q++) { GK_CUDA(cudaSetDevice(M.jobs[q]->device)); GK_CUDA(cudaStreamSynchronize(M.jobs[q]->stream)); }
+    const double t3 = now_s();
     // result rows: every GPU copies its block into the caller's matrix (its own PCIe link), all at once
     for (int q = 0; q < ndev; q++) {
         gk_phi_job *j = M.jobs[q];
@@ -1313,6 +1329,9 @@ int multi_phi(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, con
     }
     if (mean_or_null) *mean_or_null = (total - diag) / ((double) m * (double) m - (double) m);
     if (virt) GK_CUDA(cudaSetDevice(base));
+    const double t4 = now_s();
+    g_phi_timing[0] = t1 - t0; g_phi_timing[1] = t2 - t1; g_phi_timing[2] = t3 - t2; g_phi_timing[3] = t4 - t3;
+    g_phi_timing[4] = t4 - t0; g_phi_timing[5] = ndev;
     return GK_OK;
 }
 
@@ -1332,17 +1351,27 @@ int gk_phi_f64(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, co
     if (opts) std::memcpy(&o, opts, std::min<size_t>(sizeof(gk_opts), (size_t) std::max(0, opts->struct_size)));
     else { o.device = -1; o.compress = -1; o.order = -1; }
     o.struct_size = sizeof(gk_opts); o.rank = 0; o.world = 1;
+    const double t0 = now_s();
     rc = gk_phi_plan(n, sire, dam, m, pro, &o, &j);
     if (rc) return rc;
+    const double t1 = now_s();
     rc = gk_phi_upload(j);
+    const double t2 = now_s();
     if (!rc) rc = gk_phi_run(j);
+    if (!rc) rc = gk_phi_sync(j);
+    const double t3 = now_s();
     if (!rc) rc = gk_phi_copy_out(j, out);
     if (!rc && mean_or_null) rc = gk_phi_mean(j, nullptr, nullptr, mean_or_null);
+    const double t4 = now_s();
     std::string keep = g_err;
     destroy(j);
     if (rc) g_err = keep;
+    g_phi_timing[0] = t1 - t0; g_phi_timing[1] = t2 - t1; g_phi_timing[2] = t3 - t2; g_phi_timing[3] = t4 - t3;
+    g_phi_timing[4] = now_s() - t0; g_phi_timing[5] = 1;
     return rc;
 }
+
+void gk_phi_last_timing(double *out6) { if (out6) std::memcpy(out6, g_phi_timing, sizeof g_phi_timing); }
 
 // Replaces compute_inbreedings(Pedigree<>&, proband_ids) (include/compute.hpp, lib/compute.cpp:725-814) behind the
 // binding of gen.f: out[i] = F of proband i (caller order).  Runs the kinship recurrence without the final expansion.

@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(kThreadsG4, 1) phi_step_g4_kernel(const StepDe
                     if (I != checked_panel) {              // first item of a panel here: its ring slot must have been drained
                         const int old = I - s.ring_n;
                         const long long c0 = clock64();
-                        if (old >= s.panel_begin && !(s.debug_nowait & 1)) wait_count(s.done2 + old, old + 1);
+                        if (old >= s.panel_begin && !(s.debug_nowait & 1)) wait_count(s.done2 + old, s.full_rows ? s.np : old + 1);
                         p_ring += clock64() - c0;
                     }
                 }
@@ -603,8 +603,13 @@ __global__ void __launch_bounds__(kThreadsG4, 1) phi_step_g4_kernel(const StepDe
                 const unsigned pitch = (unsigned) (W + 2) * 8u;
                 const unsigned sbase = smem_u32(stages + (size_t) stage * kG4StageBytes);
                 // one bulk copy per staged row: 4 KB (2 KB) segments -- the TMA engine spends ~105 cycles per copy whatever its size
-                if (lane < npos && dr0[q] >= 0) bulk_copy(sbase + (unsigned) lane * pitch, prev(dr0[q]) + (long long) cb * W, (unsigned) (w * sizeof(double)), full, pol_stream);
-                if (lane + 32 < npos && dr1[q] >= 0) bulk_copy(sbase + (unsigned) (lane + 32) * pitch, prev(dr1[q]) + (long long) cb * W, (unsigned) (w * sizeof(double)), full, pol_stream);
+                // (row Kpad_prev = the all-zero row of an unknown parent: a small buffer of zeros, whatever the column block)
+                if (lane < npos && dr0[q] >= 0)
+                    bulk_copy(sbase + (unsigned) lane * pitch, dr0[q] < s.Kpad_prev ? prev(dr0[q]) + (long long) cb * W : s.zero_row,
+                              (unsigned) (w * sizeof(double)), full, pol_stream);
+                if (lane + 32 < npos && dr1[q] >= 0)
+                    bulk_copy(sbase + (unsigned) (lane + 32) * pitch, dr1[q] < s.Kpad_prev ? prev(dr1[q]) + (long long) cb * W : s.zero_row,
+                              (unsigned) (w * sizeof(double)), full, pol_stream);
                 decode(k + 2, q);
             }
         }
@@ -699,7 +704,8 @@ __global__ void __launch_bounds__(kThreadsG4, 1) phi_step_g4_kernel(const StepDe
                 const int b = warp + bi * G4NC;
                 if (b < nb64) {
                     const int c0 = cb * W + b * 64;
-                    const unsigned need_lo = __ballot_sync(0xffffffffu, fu[2 * bi] <= I), need_hi = __ballot_sync(0xffffffffu, fu[2 * bi + 1] <= I);
+                    const unsigned need_lo = __ballot_sync(0xffffffffu, s.full_rows ? fu[2 * bi] != 0x7fffffff : fu[2 * bi] <= I),
+                                   need_hi = __ballot_sync(0xffffffffu, s.full_rows ? fu[2 * bi + 1] != 0x7fffffff : fu[2 * bi + 1] <= I);
                     double *dst = buf + (long long) c0 * T;
                     const unsigned bF = aF + (unsigned) b * 512u, bM = aM + (unsigned) b * 512u;
 #pragma unroll
@@ -781,7 +787,9 @@ __global__ void __launch_bounds__(kThreadsG4, 1) phi_step_g4_kernel(const StepDe
                 }
                 double *drow = out + ((long long) J * T - s.out_row0) * ldn + I * T + lane;    // row j of tile J, columns of panel I
                 double *mrow = out + ((long long) I * T - s.out_row0) * ldn + J * T;           // row i of panel I, columns of tile J
-                if (J != I) {
+                if (J != I || s.full_rows) {
+                    // (a rank of a sharded job evaluates every tile J for its own panels and stores only its own rows: the
+                    // transposed pieces)
                     // Four batches of eight classes, software-pipelined over two register buffers: the loads of batch b + 1
                     // are in flight while batch b is averaged and stored (a warp alone otherwise sits through one L2
                     // latency per batch).  No predicates: an unknown parent reads a row of zeros.
@@ -799,7 +807,7 @@ __global__ void __launch_bounds__(kThreadsG4, 1) phi_step_g4_kernel(const StepDe
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
                             const double v = 0.5 * (x[i] + y[i]);
-                            if (!nostore) st_hint(drow + (long long) (8 * bt + i) * ldn, v, pol_out);
+                            if (!nostore && !s.full_rows) st_hint(drow + (long long) (8 * bt + i) * ldn, v, pol_out);
                             scr[((8 * bt + i) & 15) * G4SCRP + lane] = v;
                         }
                     };

@@ -43,7 +43,7 @@ struct StepDev {
     const int32_t *first_use; // Kpad_prev: lowest tile of this cut that reads row c of a transposed panel (np: none)
     const int32_t *prow, *pcnt, *slots;   // per panel: its distinct parent rows (64 slots), their count; per class: father / mother slot
     const int32_t *prow8, *pcnt8, *slots8; // the same per sub-panel of 8 classes (16 slots): phase-1 items of phi_step_tma_kernel
-    const double *zero_row;   // >= 256 zeros (the parent row of a class with an unknown parent)
+    const double *zero_row;   // >= 512 zeros (the parent row of a class with an unknown parent)
     double *ring;             // ring_n x ring_stride doubles: N^T panels, [Kpad_prev][32]
     int64_t ring_stride;
     int32_t ring_n;

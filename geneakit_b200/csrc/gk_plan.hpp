@@ -290,6 +290,19 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
     }
     auto enter = [&](int32_t x) { return G - 1 - maxp[x]; };
     std::atomic<bool> failed(false), over_budget(false);
+    // multi-GPU: lineage owner of every individual that takes part (one top-down sweep)
+    std::vector<uint8_t> owner;
+    if (world > 1) {
+        owner.assign((size_t) n, 0);
+        int32_t rr = 0;
+        for (int32_t x = 0; x < n; x++) {
+            if (maxp[x] < 0) continue;
+            const int32_t f = sire[x], d = dam[x];
+            if (f >= 0 && maxp[f] >= 0) owner[x] = owner[f];
+            else if (d >= 0 && maxp[d] >= 0) owner[x] = owner[d];
+            else owner[x] = (uint8_t) (rr++ % world);
+        }
+    }
 
     // ---- stage A (parallel): classes of every cut, in natural order --------------------------------
     parallel_steps(0, G, threads, [&](int g) {
@@ -364,16 +377,16 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
                 for (int64_t i = 0; i < K; i++) subset[i] = (int32_t) i;
                 locality_order(C.cls, subset, K_prev, order);
             } else {
-                // Multi-GPU: the rows of every matrix are sharded in equal blocks of panels.  Group the new
-                // classes by the rank that owns their first known parent's row (so that row is a LOCAL read
-                // for the rank that will own the class -- up to the spill at the block boundaries), then
-                // order each group for locality.
-                const int64_t np_prev = round_up(std::max<int64_t>(K_prev, 1), kPanel) / kPanel;
-                const int64_t rps = ((np_prev + world - 1) / world) * kPanel;       // rows per shard of the previous matrix
+                // Multi-GPU: the rows of every matrix are sharded in equal blocks of panels.  Group the classes by the
+                // LINEAGE OWNER of their first known parent (owner[x] = owner of x's father, else of its mother; founders
+                // dealt round-robin), then order each group for locality.  A class and its first parent's class fall into
+                // the same group of their respective cuts, so -- up to the spill at the block boundaries -- that parent's
+                // row is a LOCAL read for the rank that owns the class.  The owner of an individual does not depend on the
+                // order of any cut, so the cuts are still ordered independently (in parallel).
                 std::vector<std::vector<int32_t>> groups(world);
                 for (int64_t i = 0; i < K; i++) {
-                    const int32_t pcn = C.cls[i].pc0 >= 0 ? C.cls[i].pc0 : C.cls[i].pc1;
-                    const int q = pcn < 0 ? (int) (i % world) : (int) std::min<int64_t>(world - 1, W[g - 1].pos[pcn] / rps);
+                    const int32_t pi = C.cls[i].pi0 >= 0 ? C.cls[i].pi0 : C.cls[i].pi1;
+                    const int q = pi >= 0 ? owner[pi] : owner[C.cls[i].first_member];
                     groups[q].push_back((int32_t) i);
                 }
                 for (int q = 0; q < world; q++) locality_order(C.cls, groups[q], K_prev, order);
@@ -382,8 +395,7 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
         C.pos.assign(K, 0);
         for (int64_t p = 0; p < K; p++) C.pos[order[p]] = (int32_t) p;
     };
-    if (world > 1 && !P.ranked && order_opt != 0) for (int g = 0; g < G; g++) order_cut(g);
-    else parallel_steps(0, G, threads, order_cut);
+    parallel_steps(0, G, threads, order_cut);
 
     // ---- stage C (parallel): the arrays the kernels read -------------------------------------------
     parallel_steps(0, G, threads, [&](int g) {

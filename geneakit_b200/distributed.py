@@ -213,7 +213,7 @@ class VirtualShardedPhi:
         return np.concatenate([np.asarray(j.to_host()) for j in self.jobs], axis=0)
 
     def close(self):
-        for j in self.jobs:
+        for j in reversed(self.jobs):          # rank 0 owns the stream the others enqueue on: it goes last
             j.close()
 
 

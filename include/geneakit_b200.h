@@ -62,6 +62,10 @@ int gk_phi_f64(int32_t n, const int32_t *sire, const int32_t *dam,
                int32_t m, const int32_t *pro,
                double *out, double *mean_or_null, const gk_opts *opts);
 
+/* Where the last gk_phi_f64 call of this process spent its time: seconds of host planning, allocation + H2D of the plan,
+ * kernels, D2H of the result, the whole call (before the buffers go back to the cache); GPUs used. */
+void gk_phi_last_timing(double *out6);
+
 /* Replaces compute_genetic_contributions(Pedigree<>&, proband_ids, ancestor_ids)
  * (include/compute.hpp:130-131, lib/compute.cpp:832-862) behind lib/cgeneakit.cpp:491-511.
  * out = m*a doubles, row-major: rows = probands (caller order), columns = ancestors. */
