@@ -218,6 +218,17 @@ cudaError_t configure_device(int dev) {
     std::lock_guard<std::mutex> lock(g_cfg_mu);
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (g_cfg_state[dev] == 0) {
+        // GK_L2_PERSIST_MB: set aside L2 for the lines the step kernel marks evict_last (the ring of transposed panels).
+        // Measured at c4: 64 MB cut the DRAM traffic per step from 35.0 to 30.2 GB (27.8 with a 7-deep ring: 1.11 x the
+        // algorithmic bytes) but the step went from 6.9 to 9.5 ms -- the streams need the L2 more than the ring does.  Off.
+        int mb = 0;
+        if (const char *e = std::getenv("GK_L2_PERSIST_MB")) mb = std::atoi(e);
+        if (mb > 0) {
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0)
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t) mb << 20, (size_t) prop.persistingL2CacheMaxSize));
+            cudaGetLastError();
+        }
         g_cfg_err = gk::configure_kernels();
         g_cfg_state[dev] = g_cfg_err == cudaSuccess ? 1 : 2;
     }
@@ -318,64 +329,17 @@ static size_t build_arena(gk_phi_job *j, std::vector<int32_t> &arena) {
         //      matrix's all-zero row (index Kpad_prev), which also is the staged row of an unknown parent ----------
         o.use_g4 = (j->use_g4 && S.Kpad_prev >= (j->g4_min_k > 0 ? j->g4_min_k : 8192)) ? 1 : 0;   // small cuts: the warp-autonomous kernel has less fixed cost
         if (o.use_g4) {
-            const int zero_row = (int) S.Kpad_prev;
-            const int nu = 2 * S.np;                                   // units of 16 classes
-            std::vector<int32_t> prow4((size_t) nu * gk::kG4RowsMax, -1), pcnt4((size_t) nu, 0), slots4((size_t) S.Kpad, 0);
+            const int nu = 2 * S.np;                                   // units of 16 classes (planned in gk_plan.hpp, stage C)
             std::vector<int64_t> ioff((size_t) nu + 1, 0);
-            std::vector<int32_t> stamp((size_t) S.Kpad_prev + 1, -1), slot_of((size_t) S.Kpad_prev + 1, 0);
             for (int u = 0; u < nu; u++) {
-                // distinct parent rows of the unit's 16 classes (an unknown parent = the matrix's all-zero row)
-                int n = 0;
-                int32_t rows[34], rf[16], rm[16];
-                for (int i = 0; i < 16; i++)
-                    for (int q = 0; q < 2; q++) {
-                        int32_t r = q ? S.pM[u * 16 + i] : S.pF[u * 16 + i];
-                        if (r < 0) r = zero_row;
-                        if (stamp[r] != u) { stamp[r] = u; slot_of[r] = n; rows[n++] = r; }
-                        (q ? rm : rf)[i] = slot_of[r];          // index into rows[]
-                    }
-                // Staged position of every row.  The consumer reads, per 128-bit shared load, the father (or mother) rows of
-                // 8 consecutive classes at the same column: conflict-free when those 8 staged positions are distinct mod 8
-                // (rows are an odd number of 16-byte units apart).  Greedy colouring with 8 colours over the four groups
-                // (classes 0-7 / 8-15, father / mother), colours balanced so that position = colour + 8 * k fits the stage.
-                const int W = n * (512 + 2) * 8 <= gk::kG4StageBytes ? 512 : 256;
-                const int cap = gk::kG4StageBytes / ((W + 2) * 8);
-                int load[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, colour[34], pos[34];
-                for (int r = 0; r < n; r++) {
-                    unsigned forbidden = 0;
-                    for (int g4 = 0; g4 < 4; g4++) {
-                        const int32_t *par = (g4 & 1) ? rm : rf;
-                        const int i0 = (g4 >> 1) * 8;
-                        bool member = false;
-                        for (int i = i0; i < i0 + 8; i++) if (par[i] == r) member = true;
-                        if (!member) continue;
-                        for (int i = i0; i < i0 + 8; i++) if (par[i] < r) forbidden |= 1u << colour[par[i]];
-                    }
-                    int best = -1;
-                    for (int pass = 0; pass < 2 && best < 0; pass++)
-                        for (int c = 0; c < 8; c++) {
-                            if (c + 8 * load[c] >= cap) continue;                  // no free position of this colour
-                            if (pass == 0 && (forbidden >> c & 1u)) continue;
-                            if (best < 0 || load[c] < load[best]) best = c;
-                        }
-                    colour[r] = best; pos[r] = best + 8 * load[best]; load[best]++;
-                }
-                int npos = 0;
-                for (int r = 0; r < n; r++) { prow4[(size_t) u * gk::kG4RowsMax + pos[r]] = rows[r]; npos = std::max(npos, pos[r] + 1); }
-                for (int q = 0; q < npos; q++) {                                     // unused positions: -1 (not copied)
-                    bool used = false;
-                    for (int r = 0; r < n; r++) if (pos[r] == q) used = true;
-                    if (!used) prow4[(size_t) u * gk::kG4RowsMax + q] = -1;
-                }
-                for (int i = 0; i < 16; i++) slots4[u * 16 + i] = pos[rf[i]] | (pos[rm[i]] << 8);
-                pcnt4[u] = npos | (n << 8) | ((W == 512 ? 1 : 0) << 16);
+                const int W = (S.ucnt[u] >> 16) ? 512 : 256;
                 const int p = u >> 1;
                 ioff[u + 1] = ioff[u] + (p >= o.pb && p < o.pe ? (S.Kpad_prev + W - 1) / W : 0);
             }
             o.total_g4 = ioff[nu];
             std::vector<int32_t> i32(ioff.size() * 2);
             std::memcpy(i32.data(), ioff.data(), ioff.size() * 8);
-            o.prow4 = push(prow4); o.pcnt4 = push(pcnt4); o.slots4 = push(slots4); o.item_off = push(i32);
+            o.prow4 = push(S.urow); o.pcnt4 = push(S.ucnt); o.slots4 = push(S.uslots); o.item_off = push(i32);
             const int64_t panel_bytes = S.Kpad_prev * gk::kPanel * 8;
             int rn = (int) std::max<int64_t>(2, std::min<int64_t>(12, ((int64_t) 104 << 20) / panel_bytes));   // half of a slot is written on average (rows some tile J <= I reads)
             if (j->ring_env > 0) rn = std::max(2, std::min(j->ring_env, (int) gk::kRingMax));

@@ -3,6 +3,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "gk_plan.hpp"
+
 namespace gk {
 
 constexpr int kMaxShards = 8;     // GPUs of one box
@@ -18,8 +20,8 @@ constexpr int kCB = 32;           // columns of the previous matrix per phase-1 
 constexpr int kG4Stages = 2;         // TMA stages (a FIFO the producer fills and all consumer warps drain together)
 constexpr int kG4Consumers = 4;      // phase-1 consumer warps
 constexpr int kG4P2Warps = 10;       // phase-2 warps (ring rows straight from L2 into registers)
-constexpr int kG4StageBytes = 20 * 514 * 8;   // 20 rows x 512 columns (pitch 514), or up to 39 rows x 256 columns (pitch 258)
-constexpr int kG4RowsMax = 40;       // distinct parent rows of a UNIT of 16 classes (<= 32) + an all-zero row, padded
+constexpr int kG4StageBytes = kUnitStageBytes;  //   // 20 rows x 512 columns (pitch 514), or up to 39 rows x 256 columns (pitch 258)
+constexpr int kG4RowsMax = kUnitRowsMax; //      // distinct parent rows of a UNIT of 16 classes (<= 32) + an all-zero row, padded
 
 // Where the rows of a (possibly row-sharded) class matrix live: row r is owned by the shard q with
 // row0[q] <= r < row0[q+1] and sits at base[q] + (r - row0[q]) * ld.  Peer shards are CUDA-IPC

@@ -37,6 +37,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <thread>
 #include <cstdint>
@@ -52,6 +53,8 @@ constexpr int kFlagBoth = 4;        // new class with both parents known
 constexpr int kZeroSlot = 2 * kPanel;   // staged row 64 = zeros
 constexpr int kSub = 8;                 // classes per sub-panel
 constexpr int kZeroSlot8 = 2 * kSub;    // staged row 16 = zeros
+constexpr int kUnitStageBytes = 20 * 514 * 8;   // a stage of the default step kernel: 20 rows x 512 columns (pitch 514 doubles), or 39 x 256 (pitch 258)
+constexpr int kUnitRowsMax = 40;        // staged positions of a unit: <= 32 distinct parent rows + the zero row, spread over 8 bank colours
 
 struct StepPlan {
     int64_t K = 0, Kpad = 0, K_prev = 0, Kpad_prev = 0;
@@ -72,6 +75,10 @@ struct StepPlan {
     // kZeroSlot8 = unknown parent
     std::vector<int32_t> prow8, pcnt8, slots8;
     int64_t sub_rows = 0;      // sum over sub-panels of their distinct parent rows
+    // per UNIT of 16 classes (the phase-1 items of the default step kernel): urow[kUnitRowsMax u + p] = parent row staged at
+    // position p (-1: unused position; Kpad_prev: the all-zero row of an unknown parent), ucnt[u] = positions | rows << 8 |
+    // (items are 512 columns wide) << 16, uslots[i] = staged position of class i's father | of its mother << 8
+    std::vector<int32_t> urow, ucnt, uslots;
     std::vector<int32_t> flags;        // Kpad
     std::vector<int32_t> cls_ind;      // K: lowest-ranked member (= the individual, uncompressed)
     std::vector<int32_t> cls_size;     // K: members
@@ -275,9 +282,14 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
     P.compressed = P.ranked ? false : (compress_opt != 0);
     P.steps.resize(G);
     int threads = (int) std::thread::hardware_concurrency();
-    threads = std::max(1, std::min(threads, 8));
+    threads = std::max(1, std::min(threads, 24));
     if (const char *e = std::getenv("GK_PLAN_THREADS")) threads = std::max(1, std::atoi(e));
 
+    const bool timing = std::getenv("GK_PLAN_TIMING") != nullptr;
+    auto mark = [&](const char *what) {
+        if (timing) std::fprintf(stderr, "[plan] %-28s %.1f ms\n", what, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    };
+    mark("path lengths");
     // ---- members of every cut (x belongs to cuts enter(x) = G-1-maxp .. leave(x) = G-1-minp), ascending ----
     std::vector<CutWork> W(G);
     {
@@ -288,6 +300,7 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
         for (int32_t x = 0; x < n; x++) if (maxp[x] >= 0)
             for (int g = G - 1 - maxp[x]; g <= G - 1 - minp[x]; g++) W[g].members.push_back(x);
     }
+    mark("members");
     auto enter = [&](int32_t x) { return G - 1 - maxp[x]; };
     std::atomic<bool> failed(false), over_budget(false);
     // multi-GPU: lineage owner of every individual that takes part (one top-down sweep)
@@ -342,6 +355,7 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
         C.build_table();
     });
 
+    mark("stage A (classes)");
     // ---- stage B: parent classes (natural ids in the previous cut) and the order of the classes --------
     // The order only needs to know WHICH classes share a parent row, so the cuts are independent of one
     // another -- except for multi-GPU jobs, which group the classes by the rank that owns the first parent's
@@ -397,6 +411,7 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
     };
     parallel_steps(0, G, threads, order_cut);
 
+    mark("stage B (order)");
     // ---- stage C (parallel): the arrays the kernels read -------------------------------------------
     parallel_steps(0, G, threads, [&](int g) {
         StepPlan &S = P.steps[g];
@@ -479,6 +494,61 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
             }
         }
 
+        // ---- units of 16 classes: staged positions of their parent rows --------------------------------------
+        {
+        const int zero_row = (int) S.Kpad_prev;
+        const int nu = 2 * S.np;
+        S.urow.assign((size_t) nu * kUnitRowsMax, -1); S.ucnt.assign((size_t) nu, 0); S.uslots.assign((size_t) S.Kpad, 0);
+        std::vector<int32_t> ustamp((size_t) S.Kpad_prev + 1, -1), uslot((size_t) S.Kpad_prev + 1, 0);
+        for (int u = 0; u < nu; u++) {
+            // distinct parent rows of the unit's 16 classes (an unknown parent = the matrix's all-zero row)
+            int n = 0;
+            int32_t rows[34], rf[16], rm[16];
+            for (int i = 0; i < 16; i++)
+                for (int q = 0; q < 2; q++) {
+                    int32_t r = q ? S.pM[u * 16 + i] : S.pF[u * 16 + i];
+                    if (r < 0) r = zero_row;
+                    if (ustamp[r] != u) { ustamp[r] = u; uslot[r] = n; rows[n++] = r; }
+                    (q ? rm : rf)[i] = uslot[r];          // index into rows[]
+                }
+            // Staged position of every row.  The consumer reads, per 128-bit shared load, the father (or mother) rows of
+            // 8 consecutive classes at the same column: conflict-free when those 8 staged positions are distinct mod 8
+            // (rows are an odd number of 16-byte units apart).  Greedy colouring with 8 colours over the four groups
+            // (classes 0-7 / 8-15, father / mother), colours balanced so that position = colour + 8 * k fits the stage.
+            const int W = n * (512 + 2) * 8 <= kUnitStageBytes ? 512 : 256;
+            const int cap = kUnitStageBytes / ((W + 2) * 8);
+            int load[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, colour[34], pos[34];
+            for (int r = 0; r < n; r++) {
+                unsigned forbidden = 0;
+                for (int g4 = 0; g4 < 4; g4++) {
+                    const int32_t *par = (g4 & 1) ? rm : rf;
+                    const int i0 = (g4 >> 1) * 8;
+                    bool member = false;
+                    for (int i = i0; i < i0 + 8; i++) if (par[i] == r) member = true;
+                    if (!member) continue;
+                    for (int i = i0; i < i0 + 8; i++) if (par[i] < r) forbidden |= 1u << colour[par[i]];
+                }
+                int best = -1;
+                for (int pass = 0; pass < 2 && best < 0; pass++)
+                    for (int c = 0; c < 8; c++) {
+                        if (c + 8 * load[c] >= cap) continue;                  // no free position of this colour
+                        if (pass == 0 && (forbidden >> c & 1u)) continue;
+                        if (best < 0 || load[c] < load[best]) best = c;
+                    }
+                colour[r] = best; pos[r] = best + 8 * load[best]; load[best]++;
+            }
+            int npos = 0;
+            for (int r = 0; r < n; r++) { S.urow[(size_t) u * kUnitRowsMax + pos[r]] = rows[r]; npos = std::max(npos, pos[r] + 1); }
+            for (int q = 0; q < npos; q++) {                                     // unused positions: -1 (not copied)
+                bool used = false;
+                for (int r = 0; r < n; r++) if (pos[r] == q) used = true;
+                if (!used) S.urow[(size_t) u * kUnitRowsMax + q] = -1;
+            }
+            for (int i = 0; i < 16; i++) S.uslots[u * 16 + i] = pos[rf[i]] | (pos[rm[i]] << 8);
+            S.ucnt[u] = npos | (n << 8) | ((W == 512 ? 1 : 0) << 16);
+        }
+        }
+
         // ---- corrections: class pairs that share a parent INDIVIDUAL whose class has several members ----
         struct Use { int32_t ind, cls, mult; };
         struct Term { int32_t i, j, c, mult; };
@@ -532,6 +602,7 @@ inline bool build_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, i
             a = b;
         }
     });
+    mark("stage C (arrays)");
     if (over_budget) {
         // an individual of a multi-member sibship with tens of thousands of mates: the "same individual" correction list would
         // be quadratic in the mates.  Code 3: the caller plans again with one matrix row per individual (no corrections at all).
