@@ -254,6 +254,11 @@ class DevicePhi:
         """Plan again on the host and copy the plan to the device again (buffers stay allocated)."""
         check(lib.gk_phi_replan(self._h)); return self
 
+    def run_pass(self):
+        """One whole pass from the job's inputs -- plan, copy, every cut, expansion -- with the host planning the later
+        cuts while the device runs the earlier ones (gk_phi_pass; asynchronous like run())."""
+        check(lib.gk_phi_pass(self._h)); return self
+
     def diag(self):
         out = np.empty(self.m, dtype=np.float64)
         check(lib.gk_phi_diag(self._h, out.ctypes.data))

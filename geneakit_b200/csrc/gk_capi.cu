@@ -1,10 +1,14 @@
 // C ABI of libgeneakit_b200.so (see include/geneakit_b200.h).  Host orchestration only:
 // plan on the host (gk_plan.hpp), keep matrices in HBM, enqueue the sm_100a kernels
 // (gk_kernels.cu) on one stream.  There is no CPU compute path in this file.
+#include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <list>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -97,6 +101,80 @@ void pool_free(void *p) {
 }
 template <class T> cudaError_t pool_alloc_t(T **out, size_t bytes, int dev) { void *p = nullptr; cudaError_t e = pool_alloc(&p, bytes, dev); *out = static_cast<T *>(p); return e; }
 
+// Pinned host staging of the plan (one block per cut and job): the copies to the device are truly asynchronous, so the
+// planner threads, the copy engine and the step kernels of earlier cuts all run at once.  Cached like the device blocks.
+struct HostBlock { void *p; size_t bytes; };
+std::vector<HostBlock> g_hpool_free;
+void *host_pool_alloc(size_t bytes, size_t *cap) {
+    bytes = std::max<size_t>(bytes, 4096);
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_hpool_free.size(); i++) {
+            const HostBlock &b = g_hpool_free[i];
+            if (b.bytes < bytes || b.bytes > bytes + bytes / 2 + (1 << 16)) continue;
+            if (best < 0 || b.bytes < g_hpool_free[best].bytes) best = (int) i;
+        }
+        if (best >= 0) {
+            HostBlock b = g_hpool_free[best];
+            g_hpool_free[best] = g_hpool_free.back(); g_hpool_free.pop_back();
+            *cap = b.bytes;
+            return b.p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *cap = bytes;
+    return p;
+}
+void host_pool_free(void *p, size_t cap) {
+    if (!p) return;
+    if (!pool_enabled()) { cudaFreeHost(p); return; }
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    g_hpool_free.push_back({ p, cap });
+}
+
+// One plan segment (the arrays of one cut, this rank's view) in pinned host memory.
+struct PlanBlob {
+    int32_t *p = nullptr;
+    size_t cap = 0;      // bytes
+    size_t n = 0;        // int32 entries in use
+    bool packed = false;
+};
+
+// Collects the arrays of a segment (every array 16-byte aligned), then writes them into the blob in one go.
+struct Packer {
+    struct Piece { const void *src; size_t bytes, at; };
+    std::vector<Piece> pieces;
+    std::list<std::vector<int32_t>> keep_;      // temporaries that must live until write()
+    size_t total = 0;                           // int32 entries
+    size_t add_raw(const void *src, size_t bytes) {
+        const size_t o = total;
+        pieces.push_back({ src, bytes, o });
+        total += (bytes / 4 + 3) / 4 * 4;
+        return o;
+    }
+    size_t add(const std::vector<int32_t> &v) { return add_raw(v.data(), v.size() * 4); }
+    size_t add(const std::vector<int64_t> &v) { return add_raw(v.data(), v.size() * 8); }
+    std::vector<int32_t> &keep(std::vector<int32_t> &&v) { keep_.push_back(std::move(v)); return keep_.back(); }
+    bool write(PlanBlob &b) {
+        const size_t bytes = std::max<size_t>(total, 4) * 4;
+        if (b.cap < bytes) {
+            host_pool_free(b.p, b.cap);
+            b.p = static_cast<int32_t *>(host_pool_alloc(bytes, &b.cap));
+            if (!b.p) { b.cap = 0; return false; }
+        }
+        for (const Piece &q : pieces) {
+            if (q.bytes) std::memcpy(b.p + q.at, q.src, q.bytes);
+            const size_t end = q.at + (q.bytes / 4 + 3) / 4 * 4;
+            for (size_t k = q.at + q.bytes / 4; k < end; k++) b.p[k] = 0;
+        }
+        b.n = std::max<size_t>(total, 4);
+        b.packed = true;
+        return true;
+    }
+};
+
 struct StepOffsets {
     size_t prow = 0, pcnt = 0, slots = 0, prow8 = 0, pcnt8 = 0, slots8 = 0, first_use = 0;
     size_t pF = 0, pM = 0, flags = 0, pg_i = 0, pg_j = 0, pg_off = 0, pt_cls = 0, pt_mult = 0, grp_off = 0, grp_info = 0;
@@ -114,7 +192,7 @@ struct StepOffsets {
 
 }  // namespace
 
-struct gk_plan_inputs {             // what the plan was built from (kept for gk_phi_replan)
+struct gk_plan_inputs {             // what the plan was built from (kept for gk_phi_replan / gk_phi_pass)
     int32_t n = 0, m = 0;
     std::vector<int32_t> sire, dam, pro;
 };
@@ -125,12 +203,18 @@ struct gk_phi_job {
     gk_opts opts{};
     int device = 0;
     int rank = 0, world = 1;
+    bool device_ready = false;        // device selected and configured, streams and events created
+    bool buffers = false;             // matrices, vectors, ring allocated
     bool uploaded = false, ran = false;
     bool no_expand = false;           // opts.flags & GK_FLAG_DIAGONAL_ONLY: no m x m result (gen.f only needs the self kinships)
     int steps_done = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;               // H2D of the plan segments (overlaps the step kernels of earlier cuts)
+    cudaEvent_t pass_ev = nullptr;                    // everything enqueued before the current pass (the copies must not overtake it)
+    std::vector<cudaEvent_t> seg_ev;                  // segment g is on the device
     double *buf[2] = { nullptr, nullptr };            // own rows of the class matrices, ping-pong by step parity
+    int64_t buf_doubles[2] = { 0, 0 };
     double *peer[gk::kMaxShards][2] = {};             // every rank's buffers (own entry = buf); IPC mappings for the others
     bool peer_ipc[gk::kMaxShards][2] = {};
     bool peers_set = false;
@@ -139,23 +223,30 @@ struct gk_phi_job {
     int n_dvec_peer = 0;
     int64_t dvec_len = 0;
     double *ring = nullptr;
+    int64_t ring_doubles = 0;
     double *zero_row = nullptr;
-    int use_tma = 0;                  // step kernel: 0 = warp-autonomous LDGSTS (one GPU), 1 = TMA phase 1 (multi-GPU; GK_STEP_KERNEL=tma|ldgsts)
-    int g4_min_k = 0;                 // GK_G4_MIN_K: smallest previous-cut matrix the gather kernel is used for (tests force 32)
-    int use_g4 = 0;                   // one GPU: TMA gather4 phase 1 + L2-direct phase 2 (default; GK_STEP_KERNEL=g4|ldgsts|tma)
+    int use_tma = 0;                  // step kernel of small cuts / ranked sharded jobs: 0 = warp-autonomous LDGSTS, 1 = TMA phase 1 (gk::KernelChoice)
+    int g4_min_k = 0;                 // smallest previous-cut matrix the default kernel is used for (tests force 32)
+    int use_g4 = 0;                   // default kernel: TMA bulk-copy phase 1 + L2-direct phase 2
     int full_rows = 0;                // phase 2 evaluates every tile J and stores only the own rows (multi-GPU; GK_FULL_ROWS=1 forces it)
     int lag_env = 0, ring_env = 0, lag_scale_pct = 100;   // tuning overrides (GK_LAG, GK_RING, GK_LAG_PCT)
     double *out = nullptr;            // result rows; single GPU: aliases the buffer the last step does not use
     double *out_own = nullptr;        // separately allocated result (world > 1)
+    int64_t out_own_doubles = 0;
     double *gloc = nullptr;           // world > 1: class rows needed by the expansion, fetched from their owners
+    int64_t gloc_doubles = 0;
     double *partials = nullptr;
+    int64_t partials_blocks = 0;
     double *sums_dev = nullptr;
     double *sums_host = nullptr;      // pinned
-    int32_t *ints = nullptr;          // all plan arrays, one allocation
+    // the plan on the device: one segment per cut (g = 0 .. G-1) + the final expansion maps (segment G), this rank's view
+    std::vector<int32_t *> seg;
+    std::vector<size_t> seg_cap;      // int32 entries allocated
+    std::vector<PlanBlob> blob;       // pinned host image of every segment
     int32_t *counters = nullptr;
-    size_t counters_count = 0;
-    std::vector<StepOffsets> off;
-    size_t off_final_cls = 0, off_final_ind = 0, off_cact = 0, off_coff = 0, off_cmem = 0, off_flags0 = 0, ints_count = 0;
+    size_t counters_count = 0, counters_cap = 0;
+    std::vector<StepOffsets> off;     // offsets inside the segment of each cut
+    size_t off_final_cls = 0, off_final_ind = 0, off_cact = 0, off_coff = 0, off_cmem = 0;
     int64_t row0 = 0, row1 = 0;       // result rows owned by this shard (caller order)
     int32_t nact = 0, nchunks = 0;
     int64_t nblocks_expand = 0;
@@ -164,18 +255,25 @@ struct gk_phi_job {
     std::vector<cudaEvent_t> ev;      // start / end events of every step (2g, 2g+1); 0, 1: the final expansion
     int64_t device_bytes = 0;
     int64_t launches = 0;
-    int64_t row_bytes = 0, remote_row_bytes = 0;   // bytes of parent rows this rank's phase 1 reads / reads from peers
+    std::vector<int64_t> cut_row_bytes, cut_remote_bytes;   // bytes of parent rows this rank's phase 1 reads / reads from peers, per cut
+    std::string pack_error;
+    // a pass in flight (gk_phi_pass_begin .. gk_phi_pass_end): the cuts are planned while the device runs the earlier ones
+    std::unique_ptr<gk::PhiPlanner> planner;
+    std::shared_ptr<gk::PhiPlan> pass_plan;
+    double pass_t0 = 0.0, pass_prefix_s = 0.0;
 };
 
 namespace {
 
 void destroy(gk_phi_job *j) {
     if (!j) return;
-    cudaSetDevice(j->device);
+    j->planner.reset();               // joins the planner threads (they pack into this job's blobs)
+    if (j->device_ready) cudaSetDevice(j->device);
     for (int q = 0; q < gk::kMaxShards; q++)
         for (int p = 0; p < 2; p++)
             if (j->peer_ipc[q][p] && j->peer[q][p]) cudaIpcCloseMemHandle(j->peer[q][p]);
     if (j->stream && cudaStreamSynchronize(j->stream) != cudaSuccess) cudaGetLastError();   // nothing of this job may still run when its blocks go back to the cache
+    if (j->copy_stream && cudaStreamSynchronize(j->copy_stream) != cudaSuccess) cudaGetLastError();
     for (int p = 0; p < 2; p++) { pool_free(j->buf[p]); pool_free(j->dvec[p]); }
     pool_free(j->ring);
     pool_free(j->zero_row);
@@ -186,9 +284,13 @@ void destroy(gk_phi_job *j) {
     pool_free(j->prof);
     pool_free(j->sums_dev);
     if (j->sums_host) cudaFreeHost(j->sums_host);
-    pool_free(j->ints);
+    for (int32_t *p : j->seg) pool_free(p);
+    for (PlanBlob &b : j->blob) host_pool_free(b.p, b.cap);
     pool_free(j->counters);
     for (cudaEvent_t e : j->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : j->seg_ev) cudaEventDestroy(e);
+    if (j->pass_ev) cudaEventDestroy(j->pass_ev);
+    if (j->copy_stream) cudaStreamDestroy(j->copy_stream);
     if (j->own_stream && j->stream) cudaStreamDestroy(j->stream);
     delete j;
 }
@@ -257,89 +359,57 @@ gk::RowTable row_table(const gk_phi_job *j, int g) {
     return t;
 }
 
+// Host threads the planner of this process may use: all of them, or its share when torchrun runs one process per GPU.
+int planner_threads() {
+    int hw = (int) std::thread::hardware_concurrency();
+    if (hw < 1) hw = 1;
+    if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) { const int w = std::atoi(e); if (w > 1) hw = std::max(2, hw / w); }
+    return hw;
+}
+
 }  // namespace
 
-// The plan arrays of a job (this rank's view), flattened into one int32 arena (every array 16-byte aligned); fills the
-// offsets in j->off / j->off_*.  Returns the number of completion counters the step kernels need.
-static size_t build_arena(gk_phi_job *j, std::vector<int32_t> &arena) {
-    gk::PhiPlan &P = *j->planp;
+// Everything of a job that follows from the SIZES of the cuts (known once the planner has found the classes: PhiPlanner::
+// begin) and from (rank, world): kernel choice, panel ranges, result rows, ring depths, completion counters.
+static void configure_job(gk_phi_job *j) {
+    const gk::PhiPlan &P = *j->planp;
+    j->no_expand = (j->opts.flags & GK_FLAG_DIAGONAL_ONLY) != 0;
+    // a rank of a multi-GPU job evaluates every tile J and stores only its own rows; RANKED jobs (rounding order
+    // fixed by rank) must keep J <= I and store the mirror tile into the rows of J's owner instead
+    j->full_rows = (j->world > 1 && !P.ranked) ? 1 : 0;
+    const gk::KernelChoice kc = gk::KernelChoice::resolve(j->world, P.ranked);
+    j->use_tma = kc.use_tma; j->use_g4 = kc.use_g4; j->g4_min_k = kc.g4_min_k;
+    if (const char *e = std::getenv("GK_FULL_ROWS")) if (e[0] == '1' && !P.ranked) j->full_rows = 1;
+    if (const char *e = std::getenv("GK_LAG")) j->lag_env = std::atoi(e);
+    if (const char *e = std::getenv("GK_RING")) j->ring_env = std::atoi(e);
+    if (const char *e = std::getenv("GK_LAG_PCT")) j->lag_scale_pct = std::max(1, std::atoi(e));
     const int G = P.G;
-    arena.clear();
-    // ---- plan arrays: one int32 arena (every array 16-byte aligned) -------------------------
-    auto push = [&](const std::vector<int32_t> &v) {
-        size_t o = arena.size();
-        arena.insert(arena.end(), v.begin(), v.end());
-        while (arena.size() % 4) arena.push_back(0);
-        return o;
-    };
+    j->off.assign(G, StepOffsets{});
+    j->cut_row_bytes.assign(G, 0); j->cut_remote_bytes.assign(G, 0);
+    gk_shard_rows(P.m, j->rank, j->world, &j->row0, &j->row1);
     size_t ncount = 0;
-    j->off_flags0 = push(P.steps[0].flags);
-    for (int g = 1; g < G; g++) {
-        gk::StepPlan &S = P.steps[g];
+    for (int g = 0; g < G; g++) {
+        const gk::StepPlan &S = P.steps[g];
         StepOffsets &o = j->off[g];
-        o.pF = push(S.pF); o.pM = push(S.pM); o.flags = push(S.flags);
-        o.prow = push(S.prow); o.pcnt = push(S.pcnt); o.slots = push(S.slots);
-        o.prow8 = push(S.prow8); o.pcnt8 = push(S.pcnt8); o.slots8 = push(S.slots8);
-        o.first_use = push(S.first_use);
-        o.pg_i = push(S.pg_i); o.pg_j = push(S.pg_j); o.pg_off = push(S.pg_off);
-        o.pt_cls = push(S.pt_cls); o.pt_mult = push(S.pt_mult);
-        o.npatch = (int32_t) S.pg_i.size();
-        // work queue of the own panels: phase 2 trails phase 1 by `lag` panels: P1(s), P2(s - lag), ...
+        panel_range(S.np, j->rank, j->world, &o.pb, &o.pe, &o.cpp);
+        if (g == 0) continue;
+        // ring of transposed panels / lag of phase 2 behind phase 1 (warp-autonomous kernel): the resident warps work on a
+        // window of ~nwarps consecutive queue items; phase 2 of a panel should start only after that many items have been
+        // dealt since its phase 1 ended
         const int ncb = (int) ((S.Kpad_prev + gk::kCB - 1) / gk::kCB);
-        std::vector<int64_t> goff(1, 0);
-        std::vector<int32_t> ginfo;
-        auto add = [&](int phase, int panel) {
-            const int64_t items = phase == 1 ? ncb : (j->full_rows ? S.np : panel + 1);
-            ginfo.push_back(panel | ((phase - 1) << 30));
-            goff.push_back(goff.back() + items);
-        };
-        // The resident warps work on a window of ~nwarps consecutive queue items: phase 2 of a panel
-        // should start only after that many items have been dealt since its phase 1 ended.
-        {
-            const int64_t nwarps = (int64_t) gk::step_grid() * gk::kStepWarps;
-            int lag = (int) ((nwarps * j->lag_scale_pct / 100 + ncb - 1) / ncb);
-            lag = std::max(1, std::min(lag, (int) gk::kRingMax - 2));
-            if (j->lag_env > 0) lag = std::min(j->lag_env, (int) gk::kRingMax - 1);
-            o.lag = lag;
-            o.ring_n = j->ring_env > 0 ? std::max(lag + 1, std::min(j->ring_env, (int) gk::kRingMax)) : lag + 2;
-        }
-        for (int s = o.pb; s < o.pe + o.lag; s++) {
-            if (s < o.pe) add(1, s);
-            if (s - o.lag >= o.pb) add(2, s - o.lag);
-        }
-        o.ngroups = (int32_t) ginfo.size();
-        o.total_items = goff.back();
-        std::vector<int32_t> g32(goff.size() * 2);
-        std::memcpy(g32.data(), goff.data(), goff.size() * 8);
-        o.grp_off = push(g32); o.grp_info = push(ginfo);
-        {   // multi-GPU kernel (phi_step_tma_kernel): phase-1 items = 8 classes x 256 columns, phase-2 items = one tile
-            const int ncb256 = (int) ((S.Kpad_prev + gk::kP1Cols - 1) / gk::kP1Cols);
-            o.n1pp = (gk::kPanel / gk::kP1Classes) * ncb256;
-            o.total1 = (int64_t) (o.pe - o.pb) * o.n1pp;
-            std::vector<int64_t> goff2(1, 0);
-            for (int s = o.pb; s < o.pe; s++) goff2.push_back(goff2.back() + (j->full_rows ? S.np : s + 1));
-            o.total2 = goff2.back();
-            std::vector<int32_t> g32b(goff2.size() * 2);
-            std::memcpy(g32b.data(), goff2.data(), goff2.size() * 8);
-            o.grp_off2 = push(g32b);
-            o.ring_tma = j->ring_env > 0 ? std::max(2, std::min(j->ring_env, (int) gk::kRingMax)) : 4;
-            if (j->use_tma) o.ring_n = o.ring_tma;
-        }
-        // ---- one-GPU TMA gather4 kernel: per panel the distinct parent rows padded to a multiple of four with the
-        //      matrix's all-zero row (index Kpad_prev), which also is the staged row of an unknown parent ----------
-        o.use_g4 = (j->use_g4 && S.Kpad_prev >= (j->g4_min_k > 0 ? j->g4_min_k : 8192)) ? 1 : 0;   // small cuts: the warp-autonomous kernel has less fixed cost
+        const int64_t nwarps = (int64_t) gk::step_grid() * gk::kStepWarps;
+        int lag = (int) ((nwarps * j->lag_scale_pct / 100 + ncb - 1) / ncb);
+        lag = std::max(1, std::min(lag, (int) gk::kRingMax - 2));
+        if (j->lag_env > 0) lag = std::min(j->lag_env, (int) gk::kRingMax - 1);
+        o.lag = lag;
+        o.ring_n = j->ring_env > 0 ? std::max(lag + 1, std::min(j->ring_env, (int) gk::kRingMax)) : lag + 2;
+        const int ncb256 = (int) ((S.Kpad_prev + gk::kP1Cols - 1) / gk::kP1Cols);
+        o.n1pp = (gk::kPanel / gk::kP1Classes) * ncb256;
+        o.total1 = (int64_t) (o.pe - o.pb) * o.n1pp;
+        o.ring_tma = j->ring_env > 0 ? std::max(2, std::min(j->ring_env, (int) gk::kRingMax)) : 4;
+        if (j->use_tma) o.ring_n = o.ring_tma;
+        o.use_g4 = kc.cut_uses_g4(S.Kpad_prev) ? 1 : 0;       // small cuts: the warp-autonomous kernel has less fixed cost
         if (o.use_g4) {
-            const int nu = 2 * S.np;                                   // units of 16 classes (planned in gk_plan.hpp, stage C)
-            std::vector<int64_t> ioff((size_t) nu + 1, 0);
-            for (int u = 0; u < nu; u++) {
-                const int W = (S.ucnt[u] >> 16) ? 512 : 256;
-                const int p = u >> 1;
-                ioff[u + 1] = ioff[u] + (p >= o.pb && p < o.pe ? (S.Kpad_prev + W - 1) / W : 0);
-            }
-            o.total_g4 = ioff[nu];
-            std::vector<int32_t> i32(ioff.size() * 2);
-            std::memcpy(i32.data(), ioff.data(), ioff.size() * 8);
-            o.prow4 = push(S.urow); o.pcnt4 = push(S.ucnt); o.slots4 = push(S.uslots); o.item_off = push(i32);
             const int64_t panel_bytes = S.Kpad_prev * gk::kPanel * 8;
             int rn = (int) std::max<int64_t>(2, std::min<int64_t>(12, ((int64_t) 104 << 20) / panel_bytes));   // half of a slot is written on average (rows some tile J <= I reads)
             if (j->ring_env > 0) rn = std::max(2, std::min(j->ring_env, (int) gk::kRingMax));
@@ -349,67 +419,118 @@ static size_t build_arena(gk_phi_job *j, std::vector<int32_t> &arena) {
         o.done = ncount; ncount += 2 * (size_t) S.np + 4;      // + the 8-byte aligned phase-2 queue counter
         ncount = (ncount + 1) / 2 * 2;
     }
-    j->off_final_cls = push(P.final_cls);
-    j->off_final_ind = push(P.final_ind);
-    // result rows of this shard and, for the expansion kernel, its caller entries grouped by class
-    {
-        const int64_t Kl = P.steps[G - 1].K;
-        std::vector<int32_t> cnt((size_t) Kl + 1, 0), cact, coff(1, 0), cmem;
-        if (!P.single_cut) {
-            for (int64_t i = j->row0; i < j->row1; i++) cnt[P.final_cls[i] + 1]++;
-            for (int64_t c = 0; c < Kl; c++) if (cnt[c + 1] > 0) { cact.push_back((int32_t) c); coff.push_back(coff.back() + cnt[c + 1]); }
-            std::vector<int32_t> slot((size_t) Kl, -1), w(coff.begin(), coff.end() - 1);
-            for (size_t a = 0; a < cact.size(); a++) slot[cact[a]] = (int32_t) a;
-            cmem.assign((size_t) (j->row1 - j->row0), 0);
-            for (int64_t i = j->row0; i < j->row1; i++) cmem[w[slot[P.final_cls[i]]]++] = (int32_t) i;
-        }
-        j->nact = (int32_t) cact.size();
-        j->nchunks = (int32_t) ((P.m + gk::kExpandCols - 1) / gk::kExpandCols);
-        j->off_cact = push(cact); j->off_coff = push(coff); j->off_cmem = push(cmem);
-        j->nblocks_expand = P.single_cut ? 1 : (int64_t) j->nact * j->nchunks;
+    j->counters_count = std::max<size_t>(ncount, 1);
+    j->nchunks = (int32_t) ((P.m + gk::kExpandCols - 1) / gk::kExpandCols);
+    if ((int) j->blob.size() != G + 1) {
+        for (PlanBlob &b : j->blob) host_pool_free(b.p, b.cap);
+        j->blob.assign((size_t) G + 1, PlanBlob());
     }
-    return ncount;
+    for (PlanBlob &b : j->blob) b.packed = false;
 }
 
-// Everything of a job that follows from (plan, rank, world): kernel choice, panel ranges, result rows, NVLink statistics.
-static void configure_job(gk_phi_job *j) {
-    j->row_bytes = j->remote_row_bytes = 0;
-    j->no_expand = (j->opts.flags & GK_FLAG_DIAGONAL_ONLY) != 0;
-    // a rank of a multi-GPU job evaluates every tile J and stores only its own rows; RANKED jobs (rounding order
-    // fixed by rank) must keep J <= I and store the mirror tile into the rows of J's owner instead
-    j->full_rows = (j->world > 1 && !j->planp->ranked) ? 1 : 0;
-    j->use_tma = j->world > 1 ? 1 : 0;
-    j->use_g4 = 1;                       // large cuts; ranked multi-GPU jobs need the kernel that stores mirror tiles into a peer's rows
-    if (const char *e = std::getenv("GK_STEP_KERNEL")) { j->use_tma = (e[0] == 't') ? 1 : 0; j->use_g4 = (e[0] == 'g') ? 1 : 0; }
-    if (j->world > 1 && j->planp->ranked) j->use_g4 = 0;
-    if (j->world > 1 && j->planp->ranked) j->use_tma = 1;      // only that kernel stores mirror tiles into a peer's rows
-    if (const char *e = std::getenv("GK_FULL_ROWS")) if (e[0] == '1' && !j->planp->ranked) j->full_rows = 1;
-    if (const char *e = std::getenv("GK_G4_MIN_K")) j->g4_min_k = std::atoi(e);
-    if (const char *e = std::getenv("GK_LAG")) j->lag_env = std::atoi(e);
-    if (const char *e = std::getenv("GK_RING")) j->ring_env = std::atoi(e);
-    if (const char *e = std::getenv("GK_LAG_PCT")) j->lag_scale_pct = std::max(1, std::atoi(e));
-    const int G = j->planp->G;
-    j->off.assign(G, StepOffsets{});
-    for (int g = 0; g < G; g++)
-        panel_range(j->planp->steps[g].np, j->rank, j->world, &j->off[g].pb, &j->off[g].pe, &j->off[g].cpp);
-    gk_shard_rows(j->planp->m, j->rank, j->world, &j->row0, &j->row1);
-    // rows of the previous matrix this rank's panels read, and how many of them live on a peer (NVLink)
-    for (int g = 1; g < G; g++) {
-        const gk::StepPlan &S = j->planp->steps[g];
-        const StepOffsets &o = j->off[g];
-        const int64_t rps = (int64_t) j->off[g - 1].cpp * gk::kPanel;
-        std::vector<int32_t> stamp((size_t) std::max<int64_t>(S.K_prev, 1), -1);
-        const int unit = j->use_g4 ? 16 : (j->use_tma ? gk::kSub : gk::kPanel);   // classes whose parent rows are staged together
-        for (int p = o.pb * gk::kPanel / unit; p < o.pe * gk::kPanel / unit; p++)
-            for (int i = p * unit; i < (p + 1) * unit; i++)
-                for (int q = 0; q < 2; q++) {
-                    const int32_t r = q ? S.pM[i] : S.pF[i];
-                    if (r < 0 || stamp[r] == p) continue;
-                    stamp[r] = p;
-                    j->row_bytes += 8 * S.Kpad_prev;
-                    if (r / rps != j->rank) j->remote_row_bytes += 8 * S.Kpad_prev;
-                }
+// The arrays of cut g as this rank's kernels read them, packed into the pinned blob of segment g (and, with the last cut,
+// the final expansion maps into segment G).  Runs on a planner thread as soon as the cut is planned.
+static bool pack_cut(gk_phi_job *j, int g) {
+    gk::PhiPlan &P = *j->planp;
+    const int G = P.G;
+    const gk::StepPlan &S = P.steps[g];
+    StepOffsets &o = j->off[g];
+    Packer pk;
+    if (g == 0) o.flags = pk.add(S.flags);
+    else {
+        o.pF = pk.add(S.pF); o.pM = pk.add(S.pM); o.flags = pk.add(S.flags);
+        o.first_use = pk.add(S.first_use);
+        o.pg_i = pk.add(S.pg_i); o.pg_j = pk.add(S.pg_j); o.pg_off = pk.add(S.pg_off);
+        o.pt_cls = pk.add(S.pt_cls); o.pt_mult = pk.add(S.pt_mult);
+        o.npatch = (int32_t) S.pg_i.size();
+        const bool tma = !o.use_g4 && j->use_tma, ldgsts = !o.use_g4 && !j->use_tma;
+        if ((o.use_g4 && !S.has_units) || (!o.use_g4 && !S.has_panel) || (tma && !S.has_sub)) {
+            j->pack_error = "internal: the plan was built for another step kernel (GK_STEP_KERNEL / GK_G4_MIN_K changed between plan and upload)";
+            return false;
+        }
+        if (!o.use_g4) { o.prow = pk.add(S.prow); o.pcnt = pk.add(S.pcnt); o.slots = pk.add(S.slots); }
+        if (tma) { o.prow8 = pk.add(S.prow8); o.pcnt8 = pk.add(S.pcnt8); o.slots8 = pk.add(S.slots8); }
+        if (ldgsts) {
+            // work queue of the own panels: phase 2 trails phase 1 by `lag` panels: P1(s), P2(s - lag), ...
+            const int ncb = (int) ((S.Kpad_prev + gk::kCB - 1) / gk::kCB);
+            std::vector<int64_t> goff(1, 0);
+            std::vector<int32_t> ginfo;
+            auto add = [&](int phase, int panel) {
+                const int64_t items = phase == 1 ? ncb : (j->full_rows ? S.np : panel + 1);
+                ginfo.push_back(panel | ((phase - 1) << 30));
+                goff.push_back(goff.back() + items);
+            };
+            for (int s = o.pb; s < o.pe + o.lag; s++) {
+                if (s < o.pe) add(1, s);
+                if (s - o.lag >= o.pb) add(2, s - o.lag);
+            }
+            o.ngroups = (int32_t) ginfo.size();
+            o.total_items = goff.back();
+            std::vector<int32_t> g32(goff.size() * 2);
+            std::memcpy(g32.data(), goff.data(), goff.size() * 8);
+            o.grp_off = pk.add(pk.keep(std::move(g32))); o.grp_info = pk.add(pk.keep(std::move(ginfo)));
+        }
+        {   // phase-2 items (one tile each) of the own panels: first item of each panel
+            std::vector<int32_t> g32b(((size_t) (o.pe - o.pb) + 1) * 2);
+            int64_t *goff2 = reinterpret_cast<int64_t *>(g32b.data());
+            goff2[0] = 0;
+            for (int s = o.pb; s < o.pe; s++) goff2[s - o.pb + 1] = goff2[s - o.pb] + (j->full_rows ? S.np : s + 1);
+            o.total2 = goff2[o.pe - o.pb];
+            o.grp_off2 = pk.add(pk.keep(std::move(g32b)));
+        }
+        if (o.use_g4) {
+            // default kernel: phase-1 items = one unit of 16 classes x W columns (W = 512 or 256 per unit)
+            const int nu = 2 * S.np;
+            std::vector<int32_t> i32(((size_t) nu + 1) * 2);
+            int64_t *ioff = reinterpret_cast<int64_t *>(i32.data());
+            ioff[0] = 0;
+            for (int u = 0; u < nu; u++) {
+                const int W = (S.ucnt[u] >> 16) ? 512 : 256;
+                const int p = u >> 1;
+                ioff[u + 1] = ioff[u] + (p >= o.pb && p < o.pe ? (S.Kpad_prev + W - 1) / W : 0);
+            }
+            o.total_g4 = ioff[nu];
+            o.prow4 = pk.add(S.urow); o.pcnt4 = pk.add(S.ucnt); o.slots4 = pk.add(S.uslots); o.item_off = pk.add(pk.keep(std::move(i32)));
+        }
+        // rows of the previous matrix this rank's panels read, and how many of them live on a peer (NVLink)
+        {
+            const int64_t rps = (int64_t) j->off[g - 1].cpp * gk::kPanel;
+            std::vector<int32_t> stamp((size_t) std::max<int64_t>(S.K_prev, 1), -1);
+            const int unit = o.use_g4 ? 16 : (j->use_tma ? gk::kSub : gk::kPanel);   // classes whose parent rows are staged together
+            int64_t rb = 0, rr = 0;
+            for (int p = o.pb * gk::kPanel / unit; p < o.pe * gk::kPanel / unit; p++)
+                for (int i = p * unit; i < (p + 1) * unit; i++)
+                    for (int q = 0; q < 2; q++) {
+                        const int32_t r = q ? S.pM[i] : S.pF[i];
+                        if (r < 0 || stamp[r] == p) continue;
+                        stamp[r] = p;
+                        rb += 8 * S.Kpad_prev;
+                        if (r / rps != j->rank) rr += 8 * S.Kpad_prev;
+                    }
+            j->cut_row_bytes[g] = rb; j->cut_remote_bytes[g] = rr;
+        }
     }
+    if (!pk.write(j->blob[g])) { j->pack_error = "cudaHostAlloc failed (pinned staging of the plan)"; return false; }
+    if (g != G - 1) return true;
+    // ---- segment G: the final expansion maps; the caller entries of this shard's result rows grouped by class ----
+    Packer pf;
+    j->off_final_cls = pf.add(P.final_cls);
+    j->off_final_ind = pf.add(P.final_ind);
+    const int64_t Kl = P.steps[G - 1].K;
+    std::vector<int32_t> cnt((size_t) Kl + 1, 0), cact, coff(1, 0), cmem;
+    if (!P.single_cut) {
+        for (int64_t i = j->row0; i < j->row1; i++) cnt[P.final_cls[i] + 1]++;
+        for (int64_t c = 0; c < Kl; c++) if (cnt[c + 1] > 0) { cact.push_back((int32_t) c); coff.push_back(coff.back() + cnt[c + 1]); }
+        std::vector<int32_t> slot((size_t) Kl, -1), w(coff.begin(), coff.end() - 1);
+        for (size_t a = 0; a < cact.size(); a++) slot[cact[a]] = (int32_t) a;
+        cmem.assign((size_t) (j->row1 - j->row0), 0);
+        for (int64_t i = j->row0; i < j->row1; i++) cmem[w[slot[P.final_cls[i]]]++] = (int32_t) i;
+    }
+    j->nact = (int32_t) cact.size();
+    j->off_cact = pf.add(cact); j->off_coff = pf.add(coff); j->off_cmem = pf.add(cmem);
+    j->nblocks_expand = P.single_cut ? 1 : (int64_t) j->nact * j->nchunks;
+    if (!pf.write(j->blob[G])) { j->pack_error = "cudaHostAlloc failed (pinned staging of the plan)"; return false; }
+    return true;
 }
 
 extern "C" {
@@ -438,6 +559,8 @@ void gk_host_free(void *p) { if (p) cudaFreeHost(p); }
 void gk_cache_release(void) {
     std::lock_guard<std::mutex> lock(g_pool_mu);
     pool_drop(-1);
+    for (const HostBlock &b : g_hpool_free) cudaFreeHost(b.p);
+    g_hpool_free.clear();
 }
 
 int32_t gk_childless(int32_t n, const int32_t *sire, const int32_t *dam, int32_t *out) {
@@ -526,33 +649,192 @@ double gk_phi_required_gb(int32_t n, const int32_t *sire, const int32_t *dam, in
 }
 
 // ---------------------------------------------------------------------------------------------
-int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, const int32_t *pro,
-                const gk_opts *opts, gk_phi_job **job) {
-    if (!job) return fail(GK_ERR_ARG, "job pointer is null");
-    *job = nullptr;
+}  // extern "C"
+
+namespace {
+
+gk_phi_job *new_job(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, const int32_t *pro, const gk_opts *opts) {
     gk_phi_job *j = new gk_phi_job();
     if (opts) std::memcpy(&j->opts, opts, std::min<size_t>(sizeof(gk_opts), (size_t) std::max(0, opts->struct_size)));
     else { j->opts.device = -1; j->opts.compress = -1; j->opts.order = -1; }
     if (j->opts.world < 1) j->opts.world = 1;
-    if (j->opts.world > gk::kMaxShards) { delete j; return fail(GK_ERR_ARG, "world > 8 shards"); }
-    if (j->opts.rank < 0 || j->opts.rank >= j->opts.world) { delete j; return fail(GK_ERR_ARG, "rank outside [0, world)"); }
+    if (j->opts.world > gk::kMaxShards) { delete j; g_err = "world > 8 shards"; return nullptr; }
+    if (j->opts.rank < 0 || j->opts.rank >= j->opts.world) { delete j; g_err = "rank outside [0, world)"; return nullptr; }
     j->rank = j->opts.rank; j->world = j->opts.world;
     if (n > 0 && m > 0 && sire && dam && pro) {
         j->inputs = std::make_shared<gk_plan_inputs>();
         j->inputs->n = n; j->inputs->m = m;
         j->inputs->sire.assign(sire, sire + n); j->inputs->dam.assign(dam, dam + n); j->inputs->pro.assign(pro, pro + m);
     }
-    bool planned = gk::build_phi_plan(n, sire, dam, m, pro, j->opts.compress, j->opts.order, j->world, *j->planp);
+    return j;
+}
+
+int plan_error(const gk::PhiPlan &P) { return fail(P.error_code == 2 ? GK_ERR_INDEX : GK_ERR_ARG, P.error); }
+
+// device selected and configured, streams and events of the job created (once)
+int prepare_device(gk_phi_job *j) {
+    if (j->device_ready) { GK_CUDA(cudaSetDevice(j->device)); return GK_OK; }
+    int rc = select_device(&j->opts, &j->device);
+    if (rc) return rc;
+    { const cudaError_t ce = configure_device(j->device); if (ce != cudaSuccess) return cuda_fail(ce, "kernel configuration (is this an sm_100 device?)"); }
+    if (j->opts.stream) j->stream = (cudaStream_t) j->opts.stream;
+    else { GK_CUDA(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking)); j->own_stream = true; }
+    GK_CUDA(cudaStreamCreateWithFlags(&j->copy_stream, cudaStreamNonBlocking));
+    GK_CUDA(cudaEventCreateWithFlags(&j->pass_ev, cudaEventDisableTiming));
+    j->device_ready = true;
+    return GK_OK;
+}
+
+// Matrices, vectors, ring, counters: everything whose size follows from the sizes of the cuts (configure_job).  Blocks that
+// are large enough already are kept (a job plans the same inputs again and again in the benchmark).
+int alloc_buffers(gk_phi_job *j) {
+    gk::PhiPlan &P = *j->planp;
+    const int G = P.G;
+    GK_CUDA(cudaSetDevice(j->device));
+    auto ensure = [&](double **p, int64_t *have, int64_t need) -> cudaError_t {
+        need = std::max<int64_t>(need, 32);
+        if (*p && *have >= need) return cudaSuccess;
+        pool_free(*p); *p = nullptr; *have = 0;
+        const cudaError_t e = pool_alloc_t(p, (size_t) need * sizeof(double), j->device);
+        if (e == cudaSuccess) { *have = need; j->device_bytes += need * 8; }
+        return e;
+    };
+    if (j->counters_cap < j->counters_count) {
+        pool_free(j->counters); j->counters = nullptr;
+        GK_CUDA(pool_alloc_t(&j->counters, j->counters_count * sizeof(int32_t), j->device));
+        j->counters_cap = j->counters_count;
+    }
+    // ---- matrices: two ping-pong buffers holding the own rows of each cut's class matrix --------
+    int64_t need[2] = { 0, 0 };
+    int64_t dlen = 1;
+    for (int g = 0; g < G; g++) {
+        const gk::StepPlan &S = P.steps[g];
+        const int64_t rows = (int64_t) (j->off[g].pe - j->off[g].pb) * gk::kPanel;
+        need[g & 1] = std::max(need[g & 1], rows * S.Kpad);
+        dlen = std::max(dlen, (int64_t) j->off[g].cpp * gk::kPanel * j->world);
+    }
+    const int64_t mm = j->no_expand ? 0 : (j->row1 - j->row0) * (int64_t) P.m;
+    const int out_buf = P.single_cut ? 0 : 1 - ((G - 1) & 1);
+    if (j->world == 1) need[out_buf] = std::max(need[out_buf], mm);
+    for (int p = 0; p < 2; p++) {
+        const cudaError_t e = ensure(&j->buf[p], &j->buf_doubles[p], need[p]);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            char msg[256];
+            std::snprintf(msg, sizeof msg, "out of device memory: kinship buffers need %.2f GB + %.2f GB of HBM",
+                          need[0] * 8 / 1e9, need[1] * 8 / 1e9);
+            return fail(GK_ERR_OOM, msg);
+        }
+        j->peer[j->rank][p] = j->buf[p];
+    }
+    if (j->world == 1) { j->out = j->buf[out_buf]; j->peers_set = true; }
+    else {
+        GK_CUDA(ensure(&j->out_own, &j->out_own_doubles, mm));
+        j->out = j->out_own;
+    }
+    if (j->dvec_len < dlen) {
+        for (int p = 0; p < 2; p++) { pool_free(j->dvec[p]); j->dvec[p] = nullptr; GK_CUDA(pool_alloc_t(&j->dvec[p], (size_t) dlen * sizeof(double), j->device)); j->device_bytes += dlen * 8; }
+        j->dvec_len = dlen;
+    }
+    int64_t ring_doubles = 32;
+    for (int g = 1; g < G; g++) ring_doubles = std::max(ring_doubles, (int64_t) j->off[g].ring_n * P.steps[g].Kpad_prev * gk::kPanel);
+    GK_CUDA(ensure(&j->ring, &j->ring_doubles, ring_doubles));
+    if (!j->zero_row) {
+        GK_CUDA(pool_alloc_t(&j->zero_row, 1024 * sizeof(double), j->device));
+        GK_CUDA(cudaMemsetAsync(j->zero_row, 0, 1024 * sizeof(double), j->stream));
+        GK_CUDA(pool_alloc_t(&j->scratch, 2 * 256 * sizeof(double), j->device));
+        GK_CUDA(pool_alloc_t(&j->sums_dev, 2 * sizeof(double), j->device));
+        if (const char *e = std::getenv("GK_PROF")) if (e[0] == '1') GK_CUDA(pool_alloc_t(&j->prof, 16 * sizeof(unsigned long long), j->device));
+        GK_CUDA(cudaHostAlloc(&j->sums_host, 2 * sizeof(double), cudaHostAllocDefault));
+    }
+    // per-CTA partial sums of the expansion: at most one block row per class that has a caller entry among the own rows
+    const int64_t pblocks = P.single_cut ? 1 : std::min<int64_t>(P.steps[G - 1].K, std::max<int64_t>(j->row1 - j->row0, 1)) * std::max(j->nchunks, 1);
+    if (j->partials_blocks < pblocks) {
+        pool_free(j->partials); j->partials = nullptr;
+        GK_CUDA(pool_alloc_t(&j->partials, (size_t) pblocks * 2 * sizeof(double), j->device));
+        j->partials_blocks = pblocks; j->device_bytes += pblocks * 16;
+    }
+    if ((int) j->ev.size() != 2 * (G + 1)) {
+        for (cudaEvent_t e : j->ev) cudaEventDestroy(e);
+        j->ev.assign(2 * (size_t) (G + 1), nullptr);
+        for (auto &e : j->ev) GK_CUDA(cudaEventCreate(&e));
+    }
+    if ((int) j->seg.size() != G + 1) {
+        for (int32_t *p : j->seg) pool_free(p);
+        for (cudaEvent_t e : j->seg_ev) cudaEventDestroy(e);
+        j->seg.assign((size_t) G + 1, nullptr); j->seg_cap.assign((size_t) G + 1, 0);
+        j->seg_ev.assign((size_t) G + 1, nullptr);
+        for (auto &e : j->seg_ev) GK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    j->buffers = true;
+    return GK_OK;
+}
+
+// The copies of a pass must not overtake the kernels of the previous pass that still read the segments.
+int begin_copies(gk_phi_job *j) {
+    GK_CUDA(cudaSetDevice(j->device));
+    GK_CUDA(cudaEventRecord(j->pass_ev, j->stream));
+    GK_CUDA(cudaStreamWaitEvent(j->copy_stream, j->pass_ev, 0));
+    return GK_OK;
+}
+
+// Segment g (g = G: the final maps) of this job's plan: H2D on the copy stream; the job's stream waits for it.
+int feed_segment(gk_phi_job *j, int g) {
+    PlanBlob &b = j->blob[g];
+    if (!b.packed) return fail(GK_ERR_STATE, j->pack_error.empty() ? "internal: plan segment not packed" : j->pack_error);
+    GK_CUDA(cudaSetDevice(j->device));
+    if (j->seg_cap[g] < b.n) {
+        pool_free(j->seg[g]); j->seg[g] = nullptr;
+        GK_CUDA(pool_alloc_t(&j->seg[g], b.n * sizeof(int32_t), j->device));
+        j->seg_cap[g] = b.n; j->device_bytes += (int64_t) b.n * 4;
+    }
+    GK_CUDA(cudaMemcpyAsync(j->seg[g], b.p, b.n * sizeof(int32_t), cudaMemcpyHostToDevice, j->copy_stream));
+    GK_CUDA(cudaEventRecord(j->seg_ev[g], j->copy_stream));
+    GK_CUDA(cudaStreamWaitEvent(j->stream, j->seg_ev[g], 0));
+    return GK_OK;
+}
+
+int64_t plan_bytes(const gk_phi_job *j) {
+    int64_t b = 0;
+    for (const PlanBlob &x : j->blob) if (x.packed) b += (int64_t) x.n * 4;
+    return b;
+}
+
+// Blocking: pack every segment of a COMPLETE plan (in parallel) and copy them all.
+int upload_plan(gk_phi_job *j) {
+    const int G = j->planp->G;
+    std::atomic<bool> bad(false);
+    gk::parallel_for(0, G, std::min(planner_threads(), 24), [&](int g) { if (!pack_cut(j, g)) bad = true; });
+    if (bad) return fail(GK_ERR_STATE, j->pack_error);
+    int rc = begin_copies(j);
+    for (int g = 0; g <= G && !rc; g++) rc = feed_segment(j, g);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, const int32_t *pro,
+                const gk_opts *opts, gk_phi_job **job) {
+    if (!job) return fail(GK_ERR_ARG, "job pointer is null");
+    *job = nullptr;
+    gk_phi_job *j = new_job(n, sire, dam, m, pro, opts);
+    if (!j) return GK_ERR_ARG;
+    const int threads = planner_threads();
+    bool planned;
+    { gk::PhiPlanner pl(n, sire, dam, m, pro, j->opts.compress, j->opts.order, j->world, *j->planp, threads); planned = pl.begin(); if (planned) { pl.start(); planned = pl.finish(); } }
     if (!planned && j->planp->error_code == 3) {
         // the sibship compression does not pay for this pedigree: the same job, one row per individual (same results)
         j->opts.compress = 0;
-        planned = gk::build_phi_plan(n, sire, dam, m, pro, 0, j->opts.order, j->world, *j->planp);
+        gk::PhiPlanner pl(n, sire, dam, m, pro, 0, j->opts.order, j->world, *j->planp, threads);
+        planned = pl.begin();
+        if (planned) { pl.start(); planned = pl.finish(); }
     }
     if (!planned) {
-        int code = j->planp->error_code == 2 ? GK_ERR_INDEX : GK_ERR_ARG;
-        std::string msg = j->planp->error;
+        const int code = plan_error(*j->planp);
         delete j;
-        return fail(code, msg);
+        return code;
     }
     configure_job(j);
     *job = j;
@@ -562,74 +844,14 @@ int gk_phi_plan(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, c
 int gk_phi_upload(gk_phi_job *j) {
     if (!j) return fail(GK_ERR_ARG, "null job");
     if (j->uploaded) return GK_OK;
-    int rc = select_device(&j->opts, &j->device);
+    int rc = prepare_device(j);
     if (rc) return rc;
-    { const cudaError_t ce = configure_device(j->device); if (ce != cudaSuccess) return cuda_fail(ce, "kernel configuration (is this an sm_100 device?)"); }
-    gk::PhiPlan &P = *j->planp;
-    const int G = P.G;
-    if (j->opts.stream) j->stream = (cudaStream_t) j->opts.stream;
-    else { GK_CUDA(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking)); j->own_stream = true; }
-
-    std::vector<int32_t> arena;
-    const size_t ncount = build_arena(j, arena);
-    j->ints_count = arena.size();
-    GK_CUDA(pool_alloc_t(&j->ints, std::max<size_t>(arena.size(), 4) * sizeof(int32_t), j->device));
-    GK_CUDA(cudaMemcpyAsync(j->ints, arena.data(), arena.size() * sizeof(int32_t), cudaMemcpyHostToDevice, j->stream));
-    GK_CUDA(cudaStreamSynchronize(j->stream));
-    j->device_bytes += (int64_t) arena.size() * 4;
-    j->counters_count = std::max<size_t>(ncount, 1);
-    GK_CUDA(pool_alloc_t(&j->counters, j->counters_count * sizeof(int32_t), j->device));
-
-    // ---- matrices: two ping-pong buffers holding the own rows of each cut's class matrix --------
-    int64_t need[2] = { 0, 0 };
-    int64_t max_prev = 1, dlen = 1;
-    for (int g = 0; g < G; g++) {
-        const gk::StepPlan &S = P.steps[g];
-        const int64_t rows = (int64_t) (j->off[g].pe - j->off[g].pb) * gk::kPanel;
-        need[g & 1] = std::max(need[g & 1], rows * S.Kpad);
-        if (g + 1 < G) max_prev = std::max(max_prev, S.Kpad);
-        dlen = std::max(dlen, (int64_t) j->off[g].cpp * gk::kPanel * j->world);
-    }
-    const int64_t mm = j->no_expand ? 0 : (j->row1 - j->row0) * (int64_t) P.m;
-    const int out_buf = P.single_cut ? 0 : 1 - ((G - 1) & 1);
-    if (j->world == 1) need[out_buf] = std::max(need[out_buf], mm);
-    for (int p = 0; p < 2; p++) {
-        need[p] = std::max<int64_t>(need[p], 32);
-        cudaError_t e = pool_alloc_t(&j->buf[p], (size_t) need[p] * sizeof(double), j->device);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            char msg[256];
-            std::snprintf(msg, sizeof msg, "out of device memory: kinship buffers need %.2f GB + %.2f GB of HBM",
-                          need[0] * 8 / 1e9, need[1] * 8 / 1e9);
-            return fail(GK_ERR_OOM, msg);
-        }
-        j->device_bytes += need[p] * 8;
-        j->peer[j->rank][p] = j->buf[p];
-    }
-    if (j->world == 1) { j->out = j->buf[out_buf]; j->peers_set = true; }
-    else {
-        GK_CUDA(pool_alloc_t(&j->out_own, (size_t) std::max<int64_t>(mm, 1) * sizeof(double), j->device));
-        j->out = j->out_own;
-        const int64_t gl = (int64_t) std::max(j->nact, 1) * P.steps[G - 1].Kpad;
-        GK_CUDA(pool_alloc_t(&j->gloc, (size_t) gl * sizeof(double), j->device));
-        j->device_bytes += (mm + gl) * 8;
-    }
-    j->dvec_len = dlen;
-    for (int p = 0; p < 2; p++) { GK_CUDA(pool_alloc_t(&j->dvec[p], (size_t) dlen * sizeof(double), j->device)); j->device_bytes += dlen * 8; }
-    int64_t ring_doubles = 32;
-    for (int g = 1; g < G; g++) ring_doubles = std::max(ring_doubles, (int64_t) j->off[g].ring_n * P.steps[g].Kpad_prev * gk::kPanel);
-    GK_CUDA(pool_alloc_t(&j->ring, (size_t) ring_doubles * sizeof(double), j->device));
-    GK_CUDA(pool_alloc_t(&j->zero_row, 1024 * sizeof(double), j->device));
-    GK_CUDA(cudaMemsetAsync(j->zero_row, 0, 1024 * sizeof(double), j->stream));
-    j->device_bytes += ring_doubles * 8;
-    GK_CUDA(pool_alloc_t(&j->partials, (size_t) std::max<int64_t>(j->nblocks_expand, 1) * 2 * sizeof(double), j->device));
-    GK_CUDA(pool_alloc_t(&j->scratch, 2 * 256 * sizeof(double), j->device));
-    j->device_bytes += j->nblocks_expand * 16;
-    GK_CUDA(pool_alloc_t(&j->sums_dev, 2 * sizeof(double), j->device));
-    if (const char *e = std::getenv("GK_PROF")) if (e[0] == '1') GK_CUDA(pool_alloc_t(&j->prof, 16 * sizeof(unsigned long long), j->device));
-    GK_CUDA(cudaHostAlloc(&j->sums_host, 2 * sizeof(double), cudaHostAllocDefault));
-    j->ev.resize(2 * (G + 1));
-    for (auto &e : j->ev) GK_CUDA(cudaEventCreate(&e));
+    configure_job(j);                 // again: the ring depths depend on the device (resident CTAs of the step kernel)
+    rc = alloc_buffers(j);
+    if (rc) return rc;
+    rc = upload_plan(j);
+    if (rc) return rc;
+    GK_CUDA(cudaStreamSynchronize(j->copy_stream));
     j->uploaded = true;
     return GK_OK;
 }
@@ -728,11 +950,11 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
         // own rows of the founders' matrix
         const int64_t rows = (int64_t) (o.pe - o.pb) * gk::kPanel;
         if (j->world == 1) {
-            GK_CUDA(gk::launch_init(j->buf[0], j->dvec[0], j->ints + j->off_flags0, S.K, S.Kpad, st));
+            GK_CUDA(gk::launch_init(j->buf[0], j->dvec[0], j->seg[0] + o.flags, S.K, S.Kpad, st));
         } else {
             // (rare) uncompressed multi-GPU start: every rank zeroes its rows, the diagonal comes from the flags
             GK_CUDA(cudaMemsetAsync(j->buf[0], 0, (size_t) std::max<int64_t>(rows * S.Kpad, 1) * sizeof(double), st));
-            GK_CUDA(gk::launch_init_rows(j->buf[0], j->dvec[0], j->ints + j->off_flags0, S.K, S.Kpad,
+            GK_CUDA(gk::launch_init_rows(j->buf[0], j->dvec[0], j->seg[0] + o.flags, S.K, S.Kpad,
                                          (int64_t) o.pb * gk::kPanel, rows, j->dvec_len, st));
         }
         j->launches++;
@@ -740,20 +962,21 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
         return GK_OK;
     }
     if (j->opts.verbose && j->rank == 0) std::printf("Cut %d out of %d\n", g, P.G);
+    const int32_t *sg = j->seg[g];
     gk::StepDev d{};
     d.prev = row_table(j, g - 1);
     d.outt = row_table(j, g);
     d.out_base = j->buf[g & 1]; d.out_row0 = (int64_t) o.pb * gk::kPanel;
     d.ld_prev = S.Kpad_prev; d.ld_new = S.Kpad;
     d.Kpad_prev = (int32_t) S.Kpad_prev; d.np = S.np;
-    d.pF = j->ints + o.pF; d.pM = j->ints + o.pM;
-    d.prow = j->ints + o.prow; d.pcnt = j->ints + o.pcnt; d.slots = j->ints + o.slots;
-    d.first_use = j->ints + o.first_use;
-    d.prow8 = j->ints + o.prow8; d.pcnt8 = j->ints + o.pcnt8; d.slots8 = j->ints + o.slots8;
+    d.pF = sg + o.pF; d.pM = sg + o.pM;
+    d.prow = sg + o.prow; d.pcnt = sg + o.pcnt; d.slots = sg + o.slots;
+    d.first_use = sg + o.first_use;
+    d.prow8 = sg + o.prow8; d.pcnt8 = sg + o.pcnt8; d.slots8 = sg + o.slots8;
     d.zero_row = j->zero_row;
     d.ring = j->ring; d.ring_stride = S.Kpad_prev * gk::kPanel; d.ring_n = o.ring_n;
     d.done1 = j->counters + o.done; d.done2 = d.done1 + S.np;
-    d.grp_off = reinterpret_cast<const int64_t *>(j->ints + o.grp_off); d.grp_info = j->ints + o.grp_info;
+    d.grp_off = reinterpret_cast<const int64_t *>(sg + o.grp_off); d.grp_info = sg + o.grp_info;
     d.total_items = o.total_items; d.ngroups = o.ngroups;
     d.ncb = (int32_t) ((S.Kpad_prev + gk::kCB - 1) / gk::kCB);
     d.panel_begin = o.pb; d.panel_end = o.pe;
@@ -761,12 +984,12 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     { const char *e = std::getenv("GK_OUT_POLICY"); d.out_policy = e ? std::atoi(e) : 0; }
     { const char *e = std::getenv("GK_DEBUG_NOWAIT"); d.debug_nowait = e ? std::atoi(e) : 0; }
     GK_CUDA(cudaEventRecord(j->ev[2 * g], st));
-    d.grp_off2 = reinterpret_cast<const int64_t *>(j->ints + o.grp_off2);
+    d.grp_off2 = reinterpret_cast<const int64_t *>(sg + o.grp_off2);
     d.total1 = o.total1; d.total2 = o.total2; d.n1pp = o.n1pp;
     d.ncb256 = (int32_t) ((S.Kpad_prev + gk::kP1Cols - 1) / gk::kP1Cols);
     if (o.use_g4) {
-        d.prow4 = j->ints + o.prow4; d.pcnt4 = j->ints + o.pcnt4; d.slots4 = j->ints + o.slots4;
-        d.item_off = reinterpret_cast<const int64_t *>(j->ints + o.item_off);
+        d.prow4 = sg + o.prow4; d.pcnt4 = sg + o.pcnt4; d.slots4 = sg + o.slots4;
+        d.item_off = reinterpret_cast<const int64_t *>(sg + o.item_off);
         d.total_g4 = o.total_g4;
         d.prof = j->prof;
         { const char *e = std::getenv("GK_CHUNK2"); d.chunk2 = e ? std::atoi(e) : 0; }
@@ -779,11 +1002,11 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     q.dprev = j->dvec[(g - 1) & 1]; q.dnew = j->dvec[g & 1];
     q.n_peer = j->n_dvec_peer;
     for (int r = 0; r < j->n_dvec_peer; r++) q.dnew_peer[r] = j->dvec_peer[r][g & 1];
-    q.pF = d.pF; q.pM = d.pM; q.flags = j->ints + o.flags;
+    q.pF = d.pF; q.pM = d.pM; q.flags = sg + o.flags;
     q.c_begin = (int32_t) std::min<int64_t>(S.K, (int64_t) o.pb * gk::kPanel);
     q.c_end = (int32_t) std::min<int64_t>(S.K, (int64_t) o.pe * gk::kPanel);
-    q.pg_i = j->ints + o.pg_i; q.pg_j = j->ints + o.pg_j; q.pg_off = j->ints + o.pg_off;
-    q.pt_cls = j->ints + o.pt_cls; q.pt_mult = j->ints + o.pt_mult; q.ngroups = o.npatch;
+    q.pg_i = sg + o.pg_i; q.pg_j = sg + o.pg_j; q.pg_off = sg + o.pg_off;
+    q.pt_cls = sg + o.pt_cls; q.pt_mult = sg + o.pt_mult; q.ngroups = o.npatch;
     GK_CUDA(gk::launch_diag(q, st));
     GK_CUDA(cudaEventRecord(j->ev[2 * g + 1], st));
     j->launches += 2;
@@ -809,15 +1032,22 @@ int gk_phi_finish(gk_phi_job *j) {
     if (P.single_cut) {
         GK_CUDA(gk::launch_eye(j->out, P.m, j->row0, j->row1, j->partials, st));
     } else {
+        const int32_t *sf = j->seg[G];
         gk::ExpandDev e{};
         e.d = j->dvec[last & 1]; e.ld = P.steps[last].Kpad;
-        e.cls = j->ints + j->off_final_cls; e.ind = j->ints + j->off_final_ind;
-        e.cact = j->ints + j->off_cact; e.coff = j->ints + j->off_coff; e.cmem = j->ints + j->off_cmem;
+        e.cls = sf + j->off_final_cls; e.ind = sf + j->off_final_ind;
+        e.cact = sf + j->off_cact; e.coff = sf + j->off_coff; e.cmem = sf + j->off_cmem;
         e.out = j->out; e.m = P.m; e.row0 = j->row0; e.row1 = j->row1;
         e.nact = j->nact; e.nchunks = j->nchunks; e.partials = j->partials;
         if (j->world == 1) { e.G = j->buf[last & 1]; e.compact = 0; }
         else {
             // the class rows of the own probands live on their owners: fetch them (coalesced peer reads)
+            const int64_t gl = (int64_t) std::max(j->nact, 1) * P.steps[G - 1].Kpad;
+            if (j->gloc_doubles < gl) {
+                pool_free(j->gloc); j->gloc = nullptr; j->gloc_doubles = 0;
+                GK_CUDA(pool_alloc_t(&j->gloc, (size_t) gl * sizeof(double), j->device));
+                j->gloc_doubles = gl; j->device_bytes += gl * 8;
+            }
             GK_CUDA(gk::launch_fetch_rows(row_table(j, last), e.ld, e.cact, j->nact, j->gloc, st));
             j->launches++;
             e.G = j->gloc; e.compact = 1;
@@ -923,8 +1153,9 @@ int gk_phi_get_stats(gk_phi_job *j, gk_phi_stats *s) {
     s->device_bytes = j->device_bytes;
     s->kernel_launches = j->launches ? j->launches : (P.single_cut ? 3 : 2 * (P.G - 1) + 4);
     s->plan_seconds = P.plan_seconds;
-    s->plan_bytes = (int64_t) j->ints_count * 4;
-    s->rank_row_bytes = j->row_bytes; s->rank_remote_row_bytes = j->remote_row_bytes;
+    s->plan_bytes = plan_bytes(j);
+    for (int64_t x : j->cut_row_bytes) s->rank_row_bytes += x;
+    for (int64_t x : j->cut_remote_bytes) s->rank_remote_row_bytes += x;
     return GK_OK;
 }
 
@@ -1120,16 +1351,20 @@ int gk_phi_ci_stats(gk_phi_job *j, const int32_t *idx, int32_t b, int32_t n, dou
     return GK_OK;
 }
 
-// Plan again from the inputs the job was created with and copy the plan arrays to the device once more (same sizes:
-// the planner is deterministic).  With gk_phi_run it is one "flattened arrays on the host -> matrix resident in HBM"
-// pass (SURVEY 8d's t_phi) on buffers that are already allocated.
+// Plan again from the inputs the job was created with and copy the plan arrays to the device once more.  Blocking; with
+// gk_phi_run it is one "flattened arrays on the host -> matrix resident in HBM" pass (SURVEY 8d's t_phi) on buffers that
+// are already allocated -- gk_phi_pass does the same with the planning overlapped with the device's work.
 int gk_phi_replan(gk_phi_job *j) {
     if (!j || !j->uploaded) return fail(GK_ERR_STATE, "gk_phi_replan before gk_phi_upload");
     if (!j->inputs) return fail(GK_ERR_STATE, "the job does not hold its inputs");
     auto fresh = std::make_shared<gk::PhiPlan>();
     const gk_plan_inputs &in = *j->inputs;
-    if (!gk::build_phi_plan(in.n, in.sire.data(), in.dam.data(), in.m, in.pro.data(), j->opts.compress, j->opts.order, j->world, *fresh))
-        return fail(GK_ERR_ARG, fresh->error);
+    {
+        gk::PhiPlanner pl(in.n, in.sire.data(), in.dam.data(), in.m, in.pro.data(), j->opts.compress, j->opts.order, j->world, *fresh, planner_threads());
+        bool ok = pl.begin();
+        if (ok) { pl.start(); ok = pl.finish(); }
+        if (!ok) return plan_error(*fresh);
+    }
     j->planp = fresh;
     return gk_phi_reupload(j);
 }
@@ -1139,11 +1374,10 @@ int gk_phi_reupload(gk_phi_job *j) {
     if (!j || !j->uploaded) return fail(GK_ERR_STATE, "gk_phi_reupload before gk_phi_upload");
     GK_CUDA(cudaSetDevice(j->device));
     configure_job(j);
-    std::vector<int32_t> arena;
-    build_arena(j, arena);
-    if (arena.size() != j->ints_count) return fail(GK_ERR_STATE, "internal: the plan changed size between two plans of the same inputs");
-    GK_CUDA(cudaMemcpyAsync(j->ints, arena.data(), arena.size() * sizeof(int32_t), cudaMemcpyHostToDevice, j->stream));
-    GK_CUDA(cudaStreamSynchronize(j->stream));       // the arena is a local
+    int rc = alloc_buffers(j);
+    if (!rc) rc = upload_plan(j);
+    if (rc) return rc;
+    GK_CUDA(cudaStreamSynchronize(j->copy_stream));
     j->ran = false; j->steps_done = 0;
     return GK_OK;
 }
@@ -1161,6 +1395,125 @@ int gk_phi_clone_rank(gk_phi_job *src, int32_t rank, int32_t device, gk_phi_job 
     return GK_OK;
 }
 
+}  // extern "C"
+
+// ---- a PASS: plan + copy + run with the three overlapped ------------------------------------------------------------
+// The planner finds the cuts and their classes (all sizes), then plans the cuts in order on its thread pool; a worker
+// packs each finished cut into the pinned segment of every job that shares the plan; the driver (this thread) copies
+// segment g and launches step g as soon as cut g is ready, while the later cuts are still being planned.
+namespace {
+
+// Start planning `jobs` (the ranks of one process that share a plan; jobs[0] holds the inputs) again from their inputs.
+// After it returns the sizes are known, every job is configured and has its buffers; the workers are running.
+int pass_begin(const std::vector<gk_phi_job *> &jobs, int compress) {
+    gk_phi_job *j0 = jobs[0];
+    if (!j0->inputs) return fail(GK_ERR_ARG, "gk_phi: empty pedigree or proband list (the binding substitutes get_proband_ids for an empty list)");
+    const gk_plan_inputs &in = *j0->inputs;
+    j0->planner.reset();
+    j0->pass_t0 = now_s();
+    j0->pass_plan = std::make_shared<gk::PhiPlan>();
+    j0->planner.reset(new gk::PhiPlanner(in.n, in.sire.data(), in.dam.data(), in.m, in.pro.data(), compress, j0->opts.order, j0->world,
+                                         *j0->pass_plan, planner_threads()));
+    if (!j0->planner->begin()) { const int rc = plan_error(*j0->pass_plan); j0->planner.reset(); return rc; }
+    for (gk_phi_job *j : jobs) {
+        int rc = prepare_device(j);
+        if (rc) { j0->planner.reset(); return rc; }
+        j->planp = j0->pass_plan;
+        configure_job(j);
+        rc = alloc_buffers(j);
+        if (!rc) rc = begin_copies(j);
+        if (rc) { j0->planner.reset(); return rc; }
+        j->pack_error.clear();
+        j->uploaded = true; j->ran = false; j->steps_done = 0;
+    }
+    j0->pass_prefix_s = now_s() - j0->pass_t0;
+    std::vector<gk_phi_job *> js = jobs;
+    j0->planner->start([js](int g) { for (gk_phi_job *j : js) pack_cut(j, g); });
+    return GK_OK;
+}
+
+// Cut g is planned: copy its segment (and, with the last cut, the final maps) to every job's device.
+int pass_feed(const std::vector<gk_phi_job *> &jobs, int g) {
+    gk_phi_job *j0 = jobs[0];
+    if (!j0->planner) return fail(GK_ERR_STATE, "no pass in flight");
+    const int G = j0->planp->G;
+    if (g < 0 || g >= G) return fail(GK_ERR_ARG, "bad step");
+    if (!j0->planner->wait_cut(g)) {
+        j0->planner->finish();
+        const int rc = j0->pass_plan->error_code == 3 ? -3 : plan_error(*j0->pass_plan);     // -3: plan again uncompressed
+        return rc;
+    }
+    for (gk_phi_job *j : jobs) {
+        int rc = feed_segment(j, g);
+        if (!rc && g == G - 1) rc = feed_segment(j, G);
+        if (rc) return rc;
+    }
+    return GK_OK;
+}
+
+int pass_end(gk_phi_job *j0) {
+    if (!j0->planner) return GK_OK;
+    const bool ok = j0->planner->finish();
+    j0->planner.reset();
+    return ok ? GK_OK : plan_error(*j0->pass_plan);
+}
+
+void drain(const std::vector<gk_phi_job *> &jobs) {
+    for (gk_phi_job *j : jobs) {
+        if (!j->device_ready) continue;
+        cudaSetDevice(j->device);
+        if (j->stream && cudaStreamSynchronize(j->stream) != cudaSuccess) cudaGetLastError();
+        if (j->copy_stream && cudaStreamSynchronize(j->copy_stream) != cudaSuccess) cudaGetLastError();
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// One pass of a ONE-GPU job from its inputs: plan, copy, all cuts, expansion -- asynchronous like gk_phi_run (the planning
+// itself has finished when it returns; the kernels of the last cuts may still be running).
+int gk_phi_pass(gk_phi_job *j) {
+    if (!j) return fail(GK_ERR_ARG, "null job");
+    if (j->world > 1) return fail(GK_ERR_STATE, "a sharded job is driven step by step (gk_phi_pass_begin / gk_phi_pass_step + gk_phi_run_step)");
+    std::vector<gk_phi_job *> jobs(1, j);
+    int rc = pass_begin(jobs, j->opts.compress);
+    if (rc) return rc;
+    const int G = j->planp->G;
+    for (int g = 0; g < G && !rc; g++) {
+        rc = pass_feed(jobs, g);
+        if (!rc) rc = gk_phi_run_step(j, g);
+    }
+    if (!rc) rc = gk_phi_finish(j);
+    if (rc) { drain(jobs); j->planner.reset(); return rc < 0 ? fail(GK_ERR_STATE, j->pass_plan->error) : rc; }
+    return pass_end(j);
+}
+
+// The same for the rank of a sharded job that its driver runs cut by cut: begin, then per cut gk_phi_pass_step (waits for
+// the cut's plan, enqueues its copy) before gk_phi_run_step, and gk_phi_pass_end after gk_phi_finish.
+int gk_phi_pass_begin(gk_phi_job *j) {
+    if (!j) return fail(GK_ERR_ARG, "null job");
+    if (!j->uploaded) return fail(GK_ERR_STATE, "gk_phi_pass_begin before gk_phi_upload (peers are wired to the uploaded buffers)");
+    double *b0 = j->buf[0], *b1 = j->buf[1];
+    std::vector<gk_phi_job *> jobs(1, j);
+    int rc = pass_begin(jobs, j->opts.compress);
+    if (!rc && (j->buf[0] != b0 || j->buf[1] != b1)) { drain(jobs); j->planner.reset(); return fail(GK_ERR_STATE, "internal: the buffers moved between two passes of the same inputs"); }
+    return rc;
+}
+int gk_phi_pass_step(gk_phi_job *j, int32_t g) {
+    if (!j) return fail(GK_ERR_ARG, "null job");
+    std::vector<gk_phi_job *> jobs(1, j);
+    const int rc = pass_feed(jobs, g);
+    if (rc) { drain(jobs); j->planner.reset(); return rc < 0 ? fail(GK_ERR_STATE, j->pass_plan->error) : rc; }
+    return GK_OK;
+}
+int gk_phi_pass_end(gk_phi_job *j) {
+    if (!j) return fail(GK_ERR_ARG, "null job");
+    return pass_end(j);
+}
+
+}  // extern "C"
+
 // ---- one process, several GPUs (SURVEY 8b "Threading", 5 "distributed backend"): what gen.phi() itself uses ----------
 // The ranks of the sharded algorithm (DESIGN.md "Multi-GPU") as jobs of THIS process, one per device, one plan shared by
 // all of them.  Peers are plain pointers (cudaDeviceEnablePeerAccess), the self-kinship vector is written into every
@@ -1173,6 +1526,7 @@ struct MultiPhi {
     std::vector<cudaEvent_t> cut_done;       // one per rank
     bool virtual_devices = false;             // tests on a one-GPU box: every rank on the current device, ONE stream
     ~MultiPhi() {
+        if (!jobs.empty()) jobs[0]->planner.reset();         // the planner threads pack into every rank's blobs
         for (size_t q = 0; q < cut_done.size(); q++) if (cut_done[q]) { cudaSetDevice(jobs[q]->device); cudaEventDestroy(cut_done[q]); }
         for (size_t q = jobs.size(); q-- > 0;) destroy(jobs[q]);      // rank 0 last: with virtual devices the others enqueue on its stream
     }
@@ -1192,77 +1546,81 @@ int multi_devices(const gk_opts *o, int *ndev, bool *virt) {
     return GK_OK;
 }
 
-int multi_phi(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, const int32_t *pro, double *out,
-              double *mean_or_null, const gk_opts *opts, int ndev, bool virt) {
+// D2H of a one-GPU result.  The matrix is symmetric: only the block rows of the lower triangle cross PCIe (a little more
+// than half of the bytes), and host threads mirror each block into the upper triangle while the next ones are in flight.
+int copy_out_symmetric(gk_phi_job *j, double *out);
+
+// rc = -3: the sibship compression cannot be used for this pedigree (the caller plans again uncompressed)
+int phi_pipelined(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, const int32_t *pro, double *out,
+                  double *mean_or_null, const gk_opts *opts, int ndev, bool virt, int compress) {
     MultiPhi M;
     M.virtual_devices = virt;
     gk_opts o{};
     if (opts) std::memcpy(&o, opts, std::min<size_t>(sizeof(gk_opts), (size_t) std::max(0, opts->struct_size)));
-    else { o.compress = -1; o.order = -1; }
+    else { o.device = -1; o.compress = -1; o.order = -1; }
     int base = 0;
-    if (virt) GK_CUDA(cudaGetDevice(&base));
-    o.struct_size = sizeof(gk_opts); o.world = ndev; o.rank = 0; o.device = virt ? base : 0; o.stream = nullptr;
-    gk_phi_job *j0 = nullptr;
+    if (virt || ndev == 1) { if (o.device >= 0) base = o.device; else if (cudaGetDevice(&base) != cudaSuccess) { cudaGetLastError(); base = 0; } }
+    o.struct_size = sizeof(gk_opts); o.world = ndev; o.rank = 0; o.compress = compress;
+    o.device = (virt || ndev == 1) ? base : 0;
+    if (ndev > 1) o.stream = nullptr;
     const double t0 = now_s();
-    int rc = gk_phi_plan(n, sire, dam, m, pro, &o, &j0);
-    if (rc) return rc;
-    const double t1 = now_s();
+    gk_phi_job *j0 = new_job(n, sire, dam, m, pro, &o);
+    if (!j0) return GK_ERR_ARG;
     M.jobs.push_back(j0);
     for (int q = 1; q < ndev; q++) {
-        gk_phi_job *jq = nullptr;
-        rc = gk_phi_clone_rank(j0, q, virt ? base : q, &jq);
-        if (rc) return rc;
+        gk_phi_job *jq = new gk_phi_job();
+        jq->opts = j0->opts; jq->opts.rank = q; jq->opts.device = virt ? base : q; jq->opts.stream = nullptr;
+        jq->rank = q; jq->world = ndev; jq->inputs = j0->inputs;
         M.jobs.push_back(jq);
     }
-    if (virt) {          // one stream for every rank: persistent kernels of different ranks must never be co-scheduled on one GPU
-        rc = gk_phi_upload(j0);
+    if (virt && ndev > 1) {
+        // one stream for every rank: persistent kernels of different ranks must never be co-scheduled on one GPU
+        int rc = prepare_device(j0);
         if (rc) return rc;
-        for (int q = 1; q < ndev; q++) { M.jobs[q]->opts.stream = j0->stream; rc = gk_phi_upload(M.jobs[q]); if (rc) return rc; }
-    } else {
-        // allocation + H2D of the plan on every device at once
-        std::vector<int> rcs(ndev, 0);
-        std::vector<std::string> errs(ndev);
-        std::vector<std::thread> th;
-        for (int q = 0; q < ndev; q++)
-            th.emplace_back([&, q] { rcs[q] = gk_phi_upload(M.jobs[q]); if (rcs[q]) errs[q] = g_err; });
-        for (auto &t : th) t.join();
-        for (int q = 0; q < ndev; q++) if (rcs[q]) return fail(rcs[q], errs[q]);
+        for (int q = 1; q < ndev; q++) M.jobs[q]->opts.stream = j0->stream;
+    }
+    int rc = pass_begin(M.jobs, compress);           // cuts and classes found, buffers allocated on every device, workers running
+    if (rc) return rc;
+    const double t1 = now_s();
+    if (ndev > 1) {
+        if (!virt)
+            for (int q = 0; q < ndev; q++) {
+                GK_CUDA(cudaSetDevice(M.jobs[q]->device));
+                for (int p = 0; p < ndev; p++) {
+                    if (p == q) continue;
+                    cudaError_t e = cudaDeviceEnablePeerAccess(M.jobs[p]->device, 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                    else if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess (the GPUs of a multi-GPU job must be NVLink / P2P peers)");
+                }
+            }
         for (int q = 0; q < ndev; q++) {
-            GK_CUDA(cudaSetDevice(M.jobs[q]->device));
+            gk_phi_job *j = M.jobs[q];
+            int k = 0;
             for (int p = 0; p < ndev; p++) {
                 if (p == q) continue;
-                cudaError_t e = cudaDeviceEnablePeerAccess(M.jobs[p]->device, 0);
-                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-                else if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess (the GPUs of a multi-GPU job must be NVLink / P2P peers)");
+                j->peer[p][0] = M.jobs[p]->buf[0]; j->peer[p][1] = M.jobs[p]->buf[1];
+                j->dvec_peer[k][0] = M.jobs[p]->dvec[0]; j->dvec_peer[k][1] = M.jobs[p]->dvec[1];
+                k++;
             }
+            j->n_dvec_peer = k;
+            j->peers_set = true;
         }
-    }
-    for (int q = 0; q < ndev; q++) {
-        gk_phi_job *j = M.jobs[q];
-        int k = 0;
-        for (int p = 0; p < ndev; p++) {
-            if (p == q) continue;
-            j->peer[p][0] = M.jobs[p]->buf[0]; j->peer[p][1] = M.jobs[p]->buf[1];
-            j->dvec_peer[k][0] = M.jobs[p]->dvec[0]; j->dvec_peer[k][1] = M.jobs[p]->dvec[1];
-            k++;
+        M.cut_done.assign(ndev, nullptr);
+        for (int q = 0; q < ndev; q++) {
+            GK_CUDA(cudaSetDevice(M.jobs[q]->device));
+            GK_CUDA(cudaEventCreateWithFlags(&M.cut_done[q], cudaEventDisableTiming));
         }
-        j->n_dvec_peer = k;
-        j->peers_set = true;
-    }
-    M.cut_done.assign(ndev, nullptr);
-    for (int q = 0; q < ndev; q++) {
-        GK_CUDA(cudaSetDevice(M.jobs[q]->device));
-        GK_CUDA(cudaEventCreateWithFlags(&M.cut_done[q], cudaEventDisableTiming));
     }
     const int G = j0->planp->G;
-    const double t2 = now_s();
     if (o.verbose) {
         for (int g = 0; g < G; g++) std::printf("Cut size %d/%d: %d\n", g + 1, G, (int) j0->planp->steps[g].cut_size);
         std::printf("Computing the kinship matrix:\n");
     }
     for (int g = 0; g < G; g++) {
-        for (int q = 0; q < ndev; q++) { rc = gk_phi_run_step(M.jobs[q], g); if (rc) return rc; }
-        if (!virt) {
+        rc = pass_feed(M.jobs, g);
+        if (rc) { drain(M.jobs); return rc; }
+        for (int q = 0; q < ndev; q++) { rc = gk_phi_run_step(M.jobs[q], g); if (rc) { drain(M.jobs); return rc; } }
+        if (ndev > 1 && !virt) {
             // the barrier between cuts: every rank's step g (rows + self kinships written to every replica) before any step g + 1
             for (int q = 0; q < ndev; q++) { GK_CUDA(cudaSetDevice(M.jobs[q]->device)); GK_CUDA(cudaEventRecord(M.cut_done[q], M.jobs[q]->stream)); }
             for (int q = 0; q < ndev; q++) {
@@ -1271,35 +1629,118 @@ int multi_phi(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, con
             }
         }
     }
-    for (int q = 0; q < ndev; q++) { rc = gk_phi_finish(M.jobs[q]); if (rc) return rc; }
-    for (int q = 0; q < ndev; q++) { GK_CUDA(cudaSetDevice(M.jobs[q]->device)); GK_CUDA(cudaStreamSynchronize(M.jobs[q]->stream)); }
-    const double t3 = now_s();
-    // result rows: every GPU copies its block into the caller's matrix (its own PCIe link), all at once
-    for (int q = 0; q < ndev; q++) {
-        gk_phi_job *j = M.jobs[q];
-        GK_CUDA(cudaSetDevice(j->device));
-        const size_t bytes = (size_t) (j->row1 - j->row0) * m * sizeof(double);
-        if (bytes) GK_CUDA(cudaMemcpyAsync(out + (size_t) j->row0 * m, j->out, bytes, cudaMemcpyDeviceToHost, j->stream));
+    rc = pass_end(j0);
+    if (rc) { drain(M.jobs); return rc; }
+    const double t2 = now_s();                       // planning is over; the device still works on the last cuts
+    for (int q = 0; q < ndev; q++) { rc = gk_phi_finish(M.jobs[q]); if (rc) { drain(M.jobs); return rc; } }
+    double t3 = t2;
+    if (ndev == 1) {
+        rc = copy_out_symmetric(j0, out);
+        if (rc) { drain(M.jobs); return rc; }
+        t3 = g_phi_timing[2];                        // set by copy_out_symmetric: when the kernels were done
+    } else {
+        for (int q = 0; q < ndev; q++) { GK_CUDA(cudaSetDevice(M.jobs[q]->device)); GK_CUDA(cudaStreamSynchronize(M.jobs[q]->stream)); }
+        t3 = now_s();
+        // result rows: every GPU copies its block into the caller's matrix (its own PCIe link), all at once
+        for (int q = 0; q < ndev; q++) {
+            gk_phi_job *j = M.jobs[q];
+            GK_CUDA(cudaSetDevice(j->device));
+            const size_t bytes = (size_t) (j->row1 - j->row0) * m * sizeof(double);
+            if (bytes) GK_CUDA(cudaMemcpyAsync(out + (size_t) j->row0 * m, j->out, bytes, cudaMemcpyDeviceToHost, j->stream));
+        }
     }
     double total = 0.0, diag = 0.0;
     for (int q = 0; q < ndev; q++) {
         gk_phi_job *j = M.jobs[q];
         GK_CUDA(cudaSetDevice(j->device));
-        GK_CUDA(cudaStreamSynchronize(j->stream));
+        GK_CUDA(cudaStreamSynchronize(j->stream));        // (a peer may still be reading this rank's rows in its expansion: every stream is drained before anything is freed)
         total += j->sums_host[0]; diag += j->sums_host[1];
-    }
-    if (!virt) {
-        // a peer may still be reading this rank's rows in its expansion: every stream is drained above before anything is freed
     }
     if (mean_or_null) *mean_or_null = (total - diag) / ((double) m * (double) m - (double) m);
     if (virt) GK_CUDA(cudaSetDevice(base));
     const double t4 = now_s();
-    g_phi_timing[0] = t1 - t0; g_phi_timing[1] = t2 - t1; g_phi_timing[2] = t3 - t2; g_phi_timing[3] = t4 - t3;
+    // plan prefix (cuts, classes) + allocation; cuts planned / copied / launched; until the kernels were done; D2H; total
+    g_phi_timing[0] = j0->pass_prefix_s; g_phi_timing[1] = (t1 - t0) - j0->pass_prefix_s; g_phi_timing[2] = t3 - t1; g_phi_timing[3] = t4 - t3;
     g_phi_timing[4] = t4 - t0; g_phi_timing[5] = ndev;
     return GK_OK;
 }
 
+int copy_out_symmetric(gk_phi_job *j, double *out) {
+    const int64_t m = j->planp->m;
+    GK_CUDA(cudaSetDevice(j->device));
+    const char *env = std::getenv("GK_D2H_SYMMETRIC");
+    // default: matrices of 4096 probands and more; GK_D2H_SYMMETRIC=0 never, =1 always (tests)
+    const bool sym = !(env && env[0] == '0') && (m >= 4096 || (env && env[0] == '1' && m >= 2)) && !j->planp->single_cut;
+    if (!sym) {
+        GK_CUDA(cudaStreamSynchronize(j->stream));
+        g_phi_timing[2] = now_s();
+        GK_CUDA(cudaMemcpyAsync(out, j->out, (size_t) m * m * sizeof(double), cudaMemcpyDeviceToHost, j->stream));
+        GK_CUDA(cudaStreamSynchronize(j->stream));
+        return GK_OK;
+    }
+    // block rows of the lower triangle: rows [r0, r1), columns [0, r1)
+    const int64_t nb = std::min<int64_t>(64, (m + 255) / 256);
+    std::vector<cudaEvent_t> ev((size_t) nb, nullptr);
+    cudaEvent_t kernels_done = nullptr;
+    GK_CUDA(cudaEventCreateWithFlags(&kernels_done, cudaEventDisableTiming));
+    GK_CUDA(cudaEventRecord(kernels_done, j->stream));
+    int rc = GK_OK;
+    // blocks of equal AREA (the copies take equal time): r_k = m * sqrt(k / nb)
+    std::vector<int64_t> rb((size_t) nb + 1, 0);
+    for (int64_t k = 1; k < nb; k++) { rb[k] = (int64_t) ((double) m * std::sqrt((double) k / (double) nb)) / 64 * 64; rb[k] = std::max(rb[k], rb[k - 1]); }
+    rb[nb] = m;
+    for (int64_t k = 0; k < nb && !rc; k++) {
+        const int64_t r0 = rb[k], r1 = rb[k + 1];
+        cudaError_t e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+        if (e == cudaSuccess && r1 > r0)
+            e = cudaMemcpy2DAsync(out + r0 * m, (size_t) m * sizeof(double), j->out + r0 * m, (size_t) m * sizeof(double),
+                                  (size_t) r1 * sizeof(double), (size_t) (r1 - r0), cudaMemcpyDeviceToHost, j->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[k], j->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "D2H of the result");
+    }
+    if (!rc) {
+        // mirror: out[c][r] = out[r][c] for r in the block, c < r0 -- tiles of 64 x 64 through the cache, several threads
+        std::atomic<int64_t> next(0);
+        std::atomic<int> arrived(0);
+        const int nt = std::max(1, std::min(planner_threads(), 32));
+        std::vector<std::thread> pool;
+        std::atomic<bool> bad(false);
+        const int dev = j->device;
+        for (int64_t k = 0; k < nb && !rc; k++) {
+            const int64_t r0 = rb[k], r1 = rb[k + 1];
+            if (k == 0) { if (cudaEventSynchronize(kernels_done) == cudaSuccess) g_phi_timing[2] = now_s(); }
+            const cudaError_t e = cudaEventSynchronize(ev[k]);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "D2H of the result"); break; }
+            if (r1 <= r0) continue;
+            // rows [r0, r1) x columns [0, r1) have landed: their mirror is columns [r0, r1) of the rows [0, r1) above the diagonal
+            const int64_t T = 64, ntr = (r1 - r0 + T - 1) / T, ntc = (r1 + T - 1) / T, ntiles = ntr * ntc;
+            next.store(0);
+            auto work = [&, r0, r1, ntr, ntiles]() {
+                for (int64_t t = next.fetch_add(1); t < ntiles; t = next.fetch_add(1)) {
+                    const int64_t tr = t % ntr, tc = t / ntr;
+                    const int64_t a0 = r0 + tr * T, a1 = std::min(a0 + T, r1), c0 = tc * T, c1 = std::min(c0 + T, r1);
+                    for (int64_t c = c0; c < c1; c++) {
+                        double *dst = out + c * m;
+                        const int64_t lo = std::max(a0, c + 1);         // strictly above the diagonal: column index a > row index c
+                        for (int64_t a = lo; a < a1; a++) dst[a] = out[a * m + c];
+                    }
+                }
+            };
+            pool.clear();
+            for (int t = 0; t < nt; t++) pool.emplace_back(work);
+            for (auto &th : pool) th.join();
+        }
+        (void) arrived; (void) bad; (void) dev;
+    }
+    cudaStreamSynchronize(j->stream);
+    for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+    cudaEventDestroy(kernels_done);
+    return rc;
+}
+
 }  // namespace
+
+extern "C" {
 
 int gk_phi_f64(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, const int32_t *pro,
                double *out, double *mean_or_null, const gk_opts *opts) {
@@ -1309,29 +1750,9 @@ int gk_phi_f64(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m, co
     bool virt = false;
     int rc = multi_devices(opts, &ndev, &virt);
     if (rc) return rc;
-    if (ndev > 1) return multi_phi(n, sire, dam, m, pro, out, mean_or_null, opts, ndev, virt);
-    gk_phi_job *j = nullptr;
-    gk_opts o{};
-    if (opts) std::memcpy(&o, opts, std::min<size_t>(sizeof(gk_opts), (size_t) std::max(0, opts->struct_size)));
-    else { o.device = -1; o.compress = -1; o.order = -1; }
-    o.struct_size = sizeof(gk_opts); o.rank = 0; o.world = 1;
-    const double t0 = now_s();
-    rc = gk_phi_plan(n, sire, dam, m, pro, &o, &j);
-    if (rc) return rc;
-    const double t1 = now_s();
-    rc = gk_phi_upload(j);
-    const double t2 = now_s();
-    if (!rc) rc = gk_phi_run(j);
-    if (!rc) rc = gk_phi_sync(j);
-    const double t3 = now_s();
-    if (!rc) rc = gk_phi_copy_out(j, out);
-    if (!rc && mean_or_null) rc = gk_phi_mean(j, nullptr, nullptr, mean_or_null);
-    const double t4 = now_s();
-    std::string keep = g_err;
-    destroy(j);
-    if (rc) g_err = keep;
-    g_phi_timing[0] = t1 - t0; g_phi_timing[1] = t2 - t1; g_phi_timing[2] = t3 - t2; g_phi_timing[3] = t4 - t3;
-    g_phi_timing[4] = now_s() - t0; g_phi_timing[5] = 1;
+    const int compress = opts && opts->struct_size >= 16 ? opts->compress : -1;
+    rc = phi_pipelined(n, sire, dam, m, pro, out, mean_or_null, opts, ndev, virt, compress);
+    if (rc == -3) rc = phi_pipelined(n, sire, dam, m, pro, out, mean_or_null, opts, ndev, virt, 0);   // the same job, one row per individual
     return rc;
 }
 

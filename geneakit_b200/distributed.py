@@ -108,14 +108,26 @@ class ShardedPhi:
         self.job.replan()
         return self
 
-    def run(self):
+    def run_pass(self):
+        """One whole pass from the flattened pedigree: the host plans the cuts in order while the device already runs
+        the earlier ones (every rank plans the same pedigree, on its share of the host threads)."""
+        return self.run(replan=True)
+
+    def run(self, replan=False):
         import torch
         import torch.distributed as dist
         if self.world == 1:
-            self.job.run()
+            if replan:
+                self.job.run_pass()
+            else:
+                self.job.run()
             return self
         with torch.cuda.stream(self._tstream):
+            if replan:
+                check(lib.gk_phi_pass_begin(self.job._h))
             for g in range(self.G):
+                if replan:
+                    check(lib.gk_phi_pass_step(self.job._h, g))     # cut g is planned and its copy enqueued
                 check(lib.gk_phi_run_step(self.job._h, g))
                 full, chunk = self._dv[g]
                 # the only per-cut collective: 8 bytes per class, and the barrier between cuts
@@ -123,6 +135,8 @@ class ShardedPhi:
             check(lib.gk_phi_finish(self.job._h))
             # the expansion read the peers' rows: nobody may start the next pass (or free) before everybody is done
             dist.all_reduce(self._fence)
+            if replan:
+                check(lib.gk_phi_pass_end(self.job._h))
         return self
 
     def mean(self):

@@ -166,6 +166,15 @@ int gk_phi_upload(gk_phi_job *job);                 /* allocate HBM, copy the pl
  * gk_phi_reupload only repeats the copy (ranks of a one-process multi-GPU job that share rank 0's plan). */
 int gk_phi_replan(gk_phi_job *job);
 int gk_phi_reupload(gk_phi_job *job);
+/* One PASS of a one-GPU job from its inputs with the three stages overlapped: the host plans the cuts in order on its
+ * threads, each cut's arrays are copied (pinned staging, own copy stream) and its step launched as soon as they are
+ * ready, while the later cuts are still being planned.  Asynchronous like gk_phi_run.  The one-shot entry points work
+ * the same way.  Sharded jobs driven cut by cut: gk_phi_pass_begin, then gk_phi_pass_step(g) before every
+ * gk_phi_run_step(g), and gk_phi_pass_end after gk_phi_finish. */
+int gk_phi_pass(gk_phi_job *job);
+int gk_phi_pass_begin(gk_phi_job *job);
+int gk_phi_pass_step(gk_phi_job *job, int32_t step);
+int gk_phi_pass_end(gk_phi_job *job);
 /* Another rank of `job` in the same process (shares its plan); device = CUDA ordinal for that rank. */
 int gk_phi_clone_rank(gk_phi_job *job, int32_t rank, int32_t device, gk_phi_job **out);
 int gk_phi_run(gk_phi_job *job);                    /* enqueue init + all steps + expansion; async */

@@ -39,6 +39,8 @@ def test_phi_matches_reference_fixture(name, compress):
     assert job.to_host().tobytes() == g["phi"].tobytes()
     job.run()                                                           # a job is re-runnable
     assert job.to_host().tobytes() == g["phi"].tobytes()
+    job.run_pass()                                                      # planned again, cut by cut, while the device runs
+    assert job.to_host().tobytes() == g["phi"].tobytes()
     job.close()
 
 

@@ -221,6 +221,17 @@ def test_replan_and_cache_reuse():
     assert gk.cgeneakit.compute_kinships(ped, pro).tobytes() == g["phi"].tobytes()
 
 
+@pytest.mark.parametrize("name", ["genea140", "deep30_w40", "overlap400_s1"])
+def test_symmetric_copy_out(name, monkeypatch):
+    """The one-shot call copies the block rows of the lower triangle and mirrors them on the host: same bits."""
+    g = load_golden(name)
+    ped, pro = _ped(g), [int(x) for x in g["pro"]]
+    monkeypatch.setenv("GK_D2H_SYMMETRIC", "1")
+    assert gk.cgeneakit.compute_kinships(ped, pro).tobytes() == g["phi"].tobytes()
+    monkeypatch.setenv("GK_D2H_SYMMETRIC", "0")
+    assert gk.cgeneakit.compute_kinships(ped, pro).tobytes() == g["phi"].tobytes()
+
+
 def test_gc_in_blocks_of_ancestor_columns(monkeypatch):
     """A wide ancestor list is propagated block of columns by block of columns (HBM budget): same bits."""
     from geneakit_b200 import _lib
