@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <emmintrin.h>
 #include <functional>
 #include <list>
 #include <memory>
@@ -1678,59 +1679,100 @@ int copy_out_symmetric(gk_phi_job *j, double *out) {
         GK_CUDA(cudaStreamSynchronize(j->stream));
         return GK_OK;
     }
-    // block rows of the lower triangle: rows [r0, r1), columns [0, r1)
-    const int64_t nb = std::min<int64_t>(64, (m + 255) / 256);
+    // Rows [0, split) arrive as block rows of the lower triangle (rows [r0, r1), columns [0, r1)) and get their upper part from
+    // the host mirror; rows [split, m) arrive whole (GK_D2H_MIRROR_ROWS = split / m).  Measured on two 16-core hosts (c4, 80 GB):
+    // whole matrix over the link 1.40 - 1.56 s; split 0.5 .. 0.8: 1.07 - 1.22 s; everything mirrored: 0.95 - 1.05 s (the link
+    // and the mirror threads share the host's memory system, a split does not help) -> 1.0.  Blocks of equal copied AREA.
+    double frac = 1.0;
+    if (const char *e = std::getenv("GK_D2H_MIRROR_ROWS")) frac = std::min(1.0, std::max(0.0, std::atof(e)));
+    const int64_t split = std::min<int64_t>(m, (int64_t) (frac * (double) m) / 64 * 64);
+    const int64_t nb_want = std::min<int64_t>(64, (m + 255) / 256);
+    std::vector<int64_t> rb(1, 0);
+    {
+        const double area = 0.5 * (double) split * (double) split + (double) (m - split) * (double) m, per = area / (double) nb_want;
+        const int64_t nlow = split > 0 ? std::max<int64_t>(1, (int64_t) (0.5 * (double) split * (double) split / per + 0.5)) : 0;
+        for (int64_t k = 1; k < nlow; k++) {
+            const int64_t r = (int64_t) ((double) split * std::sqrt((double) k / (double) nlow)) / 64 * 64;
+            if (r > rb.back()) rb.push_back(r);
+        }
+        if (split > rb.back()) rb.push_back(split);
+        const int64_t nhigh = m > split ? std::max<int64_t>(1, nb_want - nlow) : 0;
+        for (int64_t k = 1; k <= nhigh; k++) {
+            const int64_t r = k == nhigh ? m : split + (m - split) * k / nhigh / 64 * 64;
+            if (r > rb.back()) rb.push_back(r);
+        }
+    }
+    const int64_t nb = (int64_t) rb.size() - 1;
     std::vector<cudaEvent_t> ev((size_t) nb, nullptr);
     cudaEvent_t kernels_done = nullptr;
     GK_CUDA(cudaEventCreateWithFlags(&kernels_done, cudaEventDisableTiming));
     GK_CUDA(cudaEventRecord(kernels_done, j->stream));
     int rc = GK_OK;
-    // blocks of equal AREA (the copies take equal time): r_k = m * sqrt(k / nb)
-    std::vector<int64_t> rb((size_t) nb + 1, 0);
-    for (int64_t k = 1; k < nb; k++) { rb[k] = (int64_t) ((double) m * std::sqrt((double) k / (double) nb)) / 64 * 64; rb[k] = std::max(rb[k], rb[k - 1]); }
-    rb[nb] = m;
     for (int64_t k = 0; k < nb && !rc; k++) {
-        const int64_t r0 = rb[k], r1 = rb[k + 1];
+        const int64_t r0 = rb[k], r1 = rb[k + 1], width = r0 >= split ? m : r1;
         cudaError_t e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
-        if (e == cudaSuccess && r1 > r0)
+        if (e == cudaSuccess)
             e = cudaMemcpy2DAsync(out + r0 * m, (size_t) m * sizeof(double), j->out + r0 * m, (size_t) m * sizeof(double),
-                                  (size_t) r1 * sizeof(double), (size_t) (r1 - r0), cudaMemcpyDeviceToHost, j->stream);
+                                  (size_t) width * sizeof(double), (size_t) (r1 - r0), cudaMemcpyDeviceToHost, j->stream);
         if (e == cudaSuccess) e = cudaEventRecord(ev[k], j->stream);
         if (e != cudaSuccess) rc = cuda_fail(e, "D2H of the result");
     }
     if (!rc) {
-        // mirror: out[c][r] = out[r][c] for r in the block, c < r0 -- tiles of 64 x 64 through the cache, several threads
-        std::atomic<int64_t> next(0);
-        std::atomic<int> arrived(0);
+        // mirror: out[c][a] = out[a][c] for the rows a of a landed block and c < a.  Worker threads take tiles of 64 x 64: the
+        // tile is transposed into a thread-local buffer (contiguous 512-byte reads) and leaves as 512-byte runs of streaming
+        // stores (no read-for-ownership of the destination lines).  The threads live for the whole copy; block k's tiles
+        // are released when its copy has completed.
         const int nt = std::max(1, std::min(planner_threads(), 32));
-        std::vector<std::thread> pool;
-        std::atomic<bool> bad(false);
-        const int dev = j->device;
-        for (int64_t k = 0; k < nb && !rc; k++) {
-            const int64_t r0 = rb[k], r1 = rb[k + 1];
-            if (k == 0) { if (cudaEventSynchronize(kernels_done) == cudaSuccess) g_phi_timing[2] = now_s(); }
-            const cudaError_t e = cudaEventSynchronize(ev[k]);
-            if (e != cudaSuccess) { rc = cuda_fail(e, "D2H of the result"); break; }
-            if (r1 <= r0) continue;
-            // rows [r0, r1) x columns [0, r1) have landed: their mirror is columns [r0, r1) of the rows [0, r1) above the diagonal
-            const int64_t T = 64, ntr = (r1 - r0 + T - 1) / T, ntc = (r1 + T - 1) / T, ntiles = ntr * ntc;
-            next.store(0);
-            auto work = [&, r0, r1, ntr, ntiles]() {
-                for (int64_t t = next.fetch_add(1); t < ntiles; t = next.fetch_add(1)) {
-                    const int64_t tr = t % ntr, tc = t / ntr;
-                    const int64_t a0 = r0 + tr * T, a1 = std::min(a0 + T, r1), c0 = tc * T, c1 = std::min(c0 + T, r1);
-                    for (int64_t c = c0; c < c1; c++) {
-                        double *dst = out + c * m;
-                        const int64_t lo = std::max(a0, c + 1);         // strictly above the diagonal: column index a > row index c
-                        for (int64_t a = lo; a < a1; a++) dst[a] = out[a * m + c];
+        const bool skip = std::getenv("GK_D2H_DEBUG_NOMIRROR") != nullptr;       // timing experiments only (wrong upper triangle)
+        std::unique_ptr<std::atomic<int64_t>[]> next(new std::atomic<int64_t>[(size_t) nb]);
+        std::unique_ptr<std::atomic<int>[]> landed(new std::atomic<int>[(size_t) nb]);
+        for (int64_t k = 0; k < nb; k++) { next[k].store(0); landed[k].store(0); }
+        constexpr int64_t T = 64;
+        auto work = [&]() {
+            alignas(64) double loc[T * T];
+            for (int64_t k = 0; k < nb; k++) {
+                int spins = 0, st;
+                while ((st = landed[k].load(std::memory_order_acquire)) == 0) { if (++spins < 256) std::this_thread::yield(); else std::this_thread::sleep_for(std::chrono::microseconds(50)); }
+                if (st < 0) return;
+                const int64_t r0 = rb[k], r1 = rb[k + 1];
+                const int64_t cmax = std::min(r1, split);                 // destination rows: above the split the rows arrive whole
+                if (r1 <= r0 || cmax <= 0 || skip) continue;
+                const int64_t ntr = (r1 - r0 + T - 1) / T, ntc = (cmax + T - 1) / T, ntiles = ntr * ntc;
+                for (int64_t t = next[k].fetch_add(1); t < ntiles; t = next[k].fetch_add(1)) {
+                    const int64_t tr = t % ntr, tc = t / ntr;             // consecutive tiles: the same 64 destination rows
+                    const int64_t a0 = r0 + tr * T, a1 = std::min(a0 + T, r1), c0 = tc * T, c1 = std::min(c0 + T, cmax);
+                    if (c0 >= a1) continue;                               // entirely on the other side of the diagonal
+                    const int64_t na = a1 - a0, nc = c1 - c0;
+                    for (int64_t a = 0; a < na; a++) {
+                        const double *src = out + (a0 + a) * m + c0;
+                        for (int64_t c = 0; c < nc; c++) loc[c * T + a] = src[c];
+                    }
+                    if (c1 <= a0 && na == T && (((uintptr_t) (out + c0 * m + a0)) & 15) == 0 && (m & 1) == 0) {
+                        for (int64_t c = 0; c < nc; c++) {
+                            double *dst = out + (c0 + c) * m + a0;
+                            const double *l = loc + c * T;
+                            for (int64_t a = 0; a < T; a += 2) _mm_stream_pd(dst + a, _mm_load_pd(l + a));
+                        }
+                    } else {
+                        for (int64_t c = 0; c < nc; c++) {
+                            double *dst = out + (c0 + c) * m;
+                            const int64_t lo = std::max(a0, c0 + c + 1);      // strictly above the diagonal: column a > row c
+                            for (int64_t a = lo; a < a1; a++) dst[a] = loc[c * T + (a - a0)];
+                        }
                     }
                 }
-            };
-            pool.clear();
-            for (int t = 0; t < nt; t++) pool.emplace_back(work);
-            for (auto &th : pool) th.join();
+                _mm_sfence();
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; t++) pool.emplace_back(work);
+        for (int64_t k = 0; k < nb; k++) {
+            if (k == 0) { if (cudaEventSynchronize(kernels_done) == cudaSuccess) g_phi_timing[2] = now_s(); }
+            const cudaError_t e = cudaEventSynchronize(ev[k]);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "D2H of the result"); for (int64_t q = k; q < nb; q++) landed[q].store(-1, std::memory_order_release); break; }
+            landed[k].store(1, std::memory_order_release);
         }
-        (void) arrived; (void) bad; (void) dev;
+        for (auto &th : pool) th.join();
     }
     cudaStreamSynchronize(j->stream);
     for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);

@@ -26,7 +26,10 @@ def main():
         sp = ShardedPhi(ped, pro, rank=rank, world=world, device=local, stream=stream.cuda_stream).upload()
         for _ in range(2):
             sp.run()
+        first = np.asarray(sp.to_host()).copy()
+        sp.run_pass()                                  # planned again, cut by cut, while the device runs
         mine = np.asarray(sp.to_host())
+        assert mine.tobytes() == first.tobytes(), "run_pass differs from run"
         mean = sp.mean()
         one = gk.cgeneakit.DevicePhi(ped, pro, device=local).upload().run()
         want = np.asarray(one.to_host())
