@@ -117,8 +117,11 @@ def _load():
     L.gk_phi_dvec_copy_from.argtypes = [vp, vp, i32]
     L.gk_phi_free.argtypes = [vp]; L.gk_phi_free.restype = None
     L.gk_f_f64.argtypes = [i32, _I, _I, i32, _I, vp, OP]
-    for name in ("gk_phi_replan", "gk_phi_reupload", "gk_phi_pass", "gk_phi_pass_begin", "gk_phi_pass_end"):
+    for name in ("gk_phi_replan", "gk_phi_reupload", "gk_phi_pass", "gk_phi_pass_begin", "gk_phi_pass_end", "gk_phi_pass_begin_all"):
         getattr(L, name).argtypes = [vp]
+    L.gk_phi_seg_count.argtypes = [vp, C.POINTER(i32)]
+    L.gk_phi_seg_ipc_export.argtypes = [vp, i32, vp, C.POINTER(i64)]
+    L.gk_phi_seg_ipc_open.argtypes = [vp, i32, i32, vp, i64]
     L.gk_phi_pass_step.argtypes = [vp, i32]
     L.gk_phi_clone_rank.argtypes = [vp, i32, i32, C.POINTER(vp)]
     L.gk_phi_diag.argtypes = [vp, vp]
@@ -145,7 +148,7 @@ EXPORTS = [
     "gk_phi_ipc_export", "gk_phi_ipc_open", "gk_phi_local_buffers", "gk_phi_set_peer", "gk_phi_peers_ready",
     "gk_phi_run_step", "gk_phi_finish", "gk_phi_dvec", "gk_phi_dvec_copy_from",
     "gk_phi_debug_prof", "gk_cache_release", "gk_gc_last_stats",
-    "gk_opts_init", "gk_phi_last_timing", "gk_f_f64", "gk_phi_stream", "gk_phi_set_stream", "gk_phi_replan", "gk_phi_reupload", "gk_phi_pass", "gk_phi_pass_begin", "gk_phi_pass_step", "gk_phi_pass_end", "gk_phi_clone_rank", "gk_phi_diag", "gk_phi_f",
+    "gk_opts_init", "gk_phi_last_timing", "gk_f_f64", "gk_phi_stream", "gk_phi_set_stream", "gk_phi_replan", "gk_phi_reupload", "gk_phi_pass", "gk_phi_pass_begin", "gk_phi_pass_step", "gk_phi_pass_end", "gk_phi_pass_begin_all", "gk_phi_seg_count", "gk_phi_seg_ipc_export", "gk_phi_seg_ipc_open", "gk_phi_clone_rank", "gk_phi_diag", "gk_phi_f",
     "gk_phi_over", "gk_phi_over_fetch", "gk_phi_sparse", "gk_phi_sparse_fetch", "gk_phi_ci_stats",
 ]
 

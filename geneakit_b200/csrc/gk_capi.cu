@@ -262,6 +262,12 @@ struct gk_phi_job {
     std::unique_ptr<gk::PhiPlanner> planner;
     std::shared_ptr<gk::PhiPlan> pass_plan;
     double pass_t0 = 0.0, pass_prefix_s = 0.0;
+    // one process per GPU, rank 0 plans for everybody (gk_phi_pass_begin_all): host-only jobs of the other ranks (their
+    // views of the plan are packed here) and CUDA-IPC mappings of those ranks' plan segments (the copies go straight there)
+    bool shadow = false;
+    std::vector<gk_phi_job *> shadows;
+    std::vector<std::vector<int32_t *>> peer_seg;     // [rank][segment]
+    std::vector<std::vector<size_t>> peer_seg_cap;    // int32 entries
 };
 
 namespace {
@@ -269,6 +275,12 @@ namespace {
 void destroy(gk_phi_job *j) {
     if (!j) return;
     j->planner.reset();               // joins the planner threads (they pack into this job's blobs)
+    for (gk_phi_job *sh : j->shadows) destroy(sh);
+    j->shadows.clear();
+    if (!j->peer_seg.empty() && j->device_ready) {
+        cudaSetDevice(j->device);
+        for (auto &v : j->peer_seg) for (int32_t *p : v) if (p) cudaIpcCloseMemHandle(p);
+    }
     if (j->device_ready) cudaSetDevice(j->device);
     for (int q = 0; q < gk::kMaxShards; q++)
         for (int p = 0; p < 2; p++)
@@ -1413,10 +1425,13 @@ int pass_begin(const std::vector<gk_phi_job *> &jobs, int compress) {
     j0->planner.reset();
     j0->pass_t0 = now_s();
     j0->pass_plan = std::make_shared<gk::PhiPlan>();
+    // (a rank that plans for every rank of a process-per-GPU job has the host to itself: the others do not plan)
+    const int threads = j0->shadows.empty() ? planner_threads() : (int) std::max(1u, std::thread::hardware_concurrency());
     j0->planner.reset(new gk::PhiPlanner(in.n, in.sire.data(), in.dam.data(), in.m, in.pro.data(), compress, j0->opts.order, j0->world,
-                                         *j0->pass_plan, planner_threads()));
+                                         *j0->pass_plan, threads));
     if (!j0->planner->begin()) { const int rc = plan_error(*j0->pass_plan); j0->planner.reset(); return rc; }
     for (gk_phi_job *j : jobs) {
+        if (j->shadow) { j->planp = j0->pass_plan; configure_job(j); j->pack_error.clear(); continue; }
         int rc = prepare_device(j);
         if (rc) { j0->planner.reset(); return rc; }
         j->planp = j0->pass_plan;
@@ -1444,7 +1459,19 @@ int pass_feed(const std::vector<gk_phi_job *> &jobs, int g) {
         const int rc = j0->pass_plan->error_code == 3 ? -3 : plan_error(*j0->pass_plan);     // -3: plan again uncompressed
         return rc;
     }
+    // the other ranks' views, straight into their devices (before this rank's own segment: its event covers them all)
+    for (gk_phi_job *sh : j0->shadows)
+        for (int sg = g; sg <= (g == G - 1 ? G : g); sg++) {
+            const PlanBlob &b = sh->blob[sg];
+            if (!b.packed) return fail(GK_ERR_STATE, sh->pack_error.empty() ? "internal: plan segment not packed" : sh->pack_error);
+            if ((int) j0->peer_seg.size() <= sh->rank || (int) j0->peer_seg[sh->rank].size() <= sg || !j0->peer_seg[sh->rank][sg] ||
+                j0->peer_seg_cap[sh->rank][sg] < b.n)
+                return fail(GK_ERR_STATE, "a peer's plan segment is not mapped or too small (gk_phi_seg_ipc_open)");
+            GK_CUDA(cudaSetDevice(j0->device));
+            GK_CUDA(cudaMemcpyAsync(j0->peer_seg[sh->rank][sg], b.p, b.n * sizeof(int32_t), cudaMemcpyDefault, j0->copy_stream));
+        }
     for (gk_phi_job *j : jobs) {
+        if (j->shadow) continue;
         int rc = feed_segment(j, g);
         if (!rc && g == G - 1) rc = feed_segment(j, G);
         if (rc) return rc;
@@ -1504,6 +1531,7 @@ int gk_phi_pass_begin(gk_phi_job *j) {
 int gk_phi_pass_step(gk_phi_job *j, int32_t g) {
     if (!j) return fail(GK_ERR_ARG, "null job");
     std::vector<gk_phi_job *> jobs(1, j);
+    jobs.insert(jobs.end(), j->shadows.begin(), j->shadows.end());
     const int rc = pass_feed(jobs, g);
     if (rc) { drain(jobs); j->planner.reset(); return rc < 0 ? fail(GK_ERR_STATE, j->pass_plan->error) : rc; }
     return GK_OK;
@@ -1511,6 +1539,57 @@ int gk_phi_pass_step(gk_phi_job *j, int32_t g) {
 int gk_phi_pass_end(gk_phi_job *j) {
     if (!j) return fail(GK_ERR_ARG, "null job");
     return pass_end(j);
+}
+
+// One process per GPU, ONE planner: rank 0 plans every pass for all the ranks (the box's host threads plan once, not
+// `world` times) and copies each rank's view of a cut straight into that rank's device segments (CUDA-IPC mappings of the
+// segments the ranks allocated at upload).  The other ranks only enqueue their kernels; what orders a copy before the
+// kernel that reads it is the per-cut collective (see geneakit_b200/distributed.py).
+int gk_phi_seg_count(gk_phi_job *j, int32_t *n) {
+    if (!j || !j->uploaded || !n) return fail(GK_ERR_STATE, "job not uploaded");
+    *n = (int32_t) j->seg.size();
+    return GK_OK;
+}
+int gk_phi_seg_ipc_export(gk_phi_job *j, int32_t g, void *handle, int64_t *cap_ints) {
+    if (!j || !j->uploaded || !handle || g < 0 || g >= (int) j->seg.size() || !j->seg[g]) return fail(GK_ERR_STATE, "no such plan segment");
+    GK_CUDA(cudaSetDevice(j->device));
+    GK_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle), j->seg[g]));
+    if (cap_ints) *cap_ints = (int64_t) j->seg_cap[g];
+    return GK_OK;
+}
+int gk_phi_seg_ipc_open(gk_phi_job *j, int32_t q, int32_t g, const void *handle, int64_t cap_ints) {
+    if (!j || !j->uploaded || !handle) return fail(GK_ERR_STATE, "job not uploaded");
+    if (q < 0 || q >= j->world || q == j->rank || g < 0 || g >= (int) j->seg.size()) return fail(GK_ERR_ARG, "bad peer rank or segment");
+    GK_CUDA(cudaSetDevice(j->device));
+    if (j->peer_seg.empty()) {
+        j->peer_seg.assign((size_t) j->world, std::vector<int32_t *>(j->seg.size(), nullptr));
+        j->peer_seg_cap.assign((size_t) j->world, std::vector<size_t>(j->seg.size(), 0));
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    void *ptr = nullptr;
+    GK_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    j->peer_seg[q][g] = static_cast<int32_t *>(ptr);
+    j->peer_seg_cap[q][g] = (size_t) cap_ints;
+    return GK_OK;
+}
+int gk_phi_pass_begin_all(gk_phi_job *j) {
+    if (!j) return fail(GK_ERR_ARG, "null job");
+    if (!j->uploaded || j->world < 2) return fail(GK_ERR_STATE, "gk_phi_pass_begin_all: an uploaded rank of a sharded job");
+    if (j->shadows.empty())
+        for (int q = 0; q < j->world; q++) {
+            if (q == j->rank) continue;
+            gk_phi_job *sh = new gk_phi_job();
+            sh->inputs = j->inputs; sh->opts = j->opts; sh->opts.rank = q; sh->opts.stream = nullptr;
+            sh->rank = q; sh->world = j->world; sh->shadow = true;
+            j->shadows.push_back(sh);
+        }
+    double *b0 = j->buf[0], *b1 = j->buf[1];
+    std::vector<gk_phi_job *> jobs(1, j);
+    jobs.insert(jobs.end(), j->shadows.begin(), j->shadows.end());
+    int rc = pass_begin(jobs, j->opts.compress);
+    if (!rc && (j->buf[0] != b0 || j->buf[1] != b1)) { drain(jobs); j->planner.reset(); return fail(GK_ERR_STATE, "internal: the buffers moved between two passes of the same inputs"); }
+    return rc;
 }
 
 }  // extern "C"

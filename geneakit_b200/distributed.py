@@ -11,6 +11,7 @@ class: the "diagonal inputs" of the next cut), which also is the barrier that ma
 readable by the peers' next step.  phiMean adds one all-reduce of two doubles.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -78,6 +79,7 @@ class ShardedPhi:
         self.G = self.job.stats()["n_cuts"]
         self._dv = None
         self._fence = None
+        self._shared_plan = False
 
     def upload(self):
         """Allocate, then make every rank's matrix buffers addressable by every rank (CUDA IPC)."""
@@ -100,6 +102,23 @@ class ShardedPhi:
                 p, chunk, total = _dvec(self.job, g)
                 self._dv.append((torch.as_tensor(_DevArray(p, total), device="cuda"), chunk))
             self._fence = torch.zeros(1, dtype=torch.int32, device="cuda")
+            # ONE planner per box: rank 0 maps every rank's plan segments (CUDA IPC) so that run_pass() can plan once and
+            # copy each rank's view straight into that rank's HBM (GK_SHARED_PLAN=0: every rank plans for itself)
+            self._shared_plan = os.environ.get("GK_SHARED_PLAN", "1") != "0"
+            if self._shared_plan:
+                nseg = C.c_int32()
+                check(lib.gk_phi_seg_count(self.job._h, C.byref(nseg)))
+                mine = []
+                for g in range(nseg.value):
+                    h, cap = (C.c_ubyte * 64)(), C.c_int64()
+                    check(lib.gk_phi_seg_ipc_export(self.job._h, g, h, C.byref(cap)))
+                    mine.append((bytes(h), cap.value))
+                everybody = [None] * self.world
+                dist.all_gather_object(everybody, mine)
+                if self.rank == 0:
+                    for q in range(1, self.world):
+                        for g, (h, cap) in enumerate(everybody[q]):
+                            check(lib.gk_phi_seg_ipc_open(self.job._h, q, g, (C.c_ubyte * 64).from_buffer_copy(h), cap))
             dist.barrier()
         return self
 
@@ -122,20 +141,31 @@ class ShardedPhi:
             else:
                 self.job.run()
             return self
+        shared = replan and self._shared_plan
         with torch.cuda.stream(self._tstream):
-            if replan:
+            if shared:
+                # rank 0 plans for everybody.  Its copies of cut g + 1 (into every rank's segments) are enqueued BEFORE the
+                # all-gather that ends cut g, so that collective -- no rank leaves it before rank 0 has entered it -- orders
+                # them before the peers' step g + 1; a fence collective does the same for cut 0.
+                if self.rank == 0:
+                    check(lib.gk_phi_pass_begin_all(self.job._h))
+                    check(lib.gk_phi_pass_step(self.job._h, 0))
+                dist.all_reduce(self._fence)
+            elif replan:
                 check(lib.gk_phi_pass_begin(self.job._h))
             for g in range(self.G):
-                if replan:
+                if replan and not shared:
                     check(lib.gk_phi_pass_step(self.job._h, g))     # cut g is planned and its copy enqueued
                 check(lib.gk_phi_run_step(self.job._h, g))
+                if shared and self.rank == 0 and g + 1 < self.G:
+                    check(lib.gk_phi_pass_step(self.job._h, g + 1))
                 full, chunk = self._dv[g]
                 # the only per-cut collective: 8 bytes per class, and the barrier between cuts
                 dist.all_gather_into_tensor(full, full[self.rank * chunk:(self.rank + 1) * chunk])
             check(lib.gk_phi_finish(self.job._h))
             # the expansion read the peers' rows: nobody may start the next pass (or free) before everybody is done
             dist.all_reduce(self._fence)
-            if replan:
+            if replan and (not shared or self.rank == 0):
                 check(lib.gk_phi_pass_end(self.job._h))
         return self
 

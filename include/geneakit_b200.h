@@ -175,6 +175,15 @@ int gk_phi_pass(gk_phi_job *job);
 int gk_phi_pass_begin(gk_phi_job *job);
 int gk_phi_pass_step(gk_phi_job *job, int32_t step);
 int gk_phi_pass_end(gk_phi_job *job);
+/* One process per GPU with ONE planner: rank 0 calls gk_phi_pass_begin_all instead of gk_phi_pass_begin and plans every
+ * pass for all the ranks; gk_phi_pass_step(g) then also copies every other rank's view of cut g straight into that
+ * rank's device segments (mapped once with gk_phi_seg_ipc_export on the owner / gk_phi_seg_ipc_open on rank 0, one
+ * 64-byte handle per segment, gk_phi_seg_count segments).  The other ranks only enqueue kernels; the per-cut collective
+ * of the driver orders a copy before the kernel that reads it (geneakit_b200/distributed.py). */
+int gk_phi_pass_begin_all(gk_phi_job *job);
+int gk_phi_seg_count(gk_phi_job *job, int32_t *n_segments);
+int gk_phi_seg_ipc_export(gk_phi_job *job, int32_t segment, void *handle /* 64 bytes */, int64_t *capacity_ints);
+int gk_phi_seg_ipc_open(gk_phi_job *job, int32_t peer_rank, int32_t segment, const void *handle, int64_t capacity_ints);
 /* Another rank of `job` in the same process (shares its plan); device = CUDA ordinal for that rank. */
 int gk_phi_clone_rank(gk_phi_job *job, int32_t rank, int32_t device, gk_phi_job **out);
 int gk_phi_run(gk_phi_job *job);                    /* enqueue init + all steps + expansion; async */
