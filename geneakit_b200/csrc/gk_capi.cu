@@ -761,7 +761,8 @@ int alloc_buffers(gk_phi_job *j) {
         GK_CUDA(cudaHostAlloc(&j->sums_host, 2 * sizeof(double), cudaHostAllocDefault));
     }
     // per-CTA partial sums of the expansion: at most one block row per class that has a caller entry among the own rows
-    const int64_t pblocks = P.single_cut ? 1 : std::min<int64_t>(P.steps[G - 1].K, std::max<int64_t>(j->row1 - j->row0, 1)) * std::max(j->nchunks, 1);
+    int64_t pblocks = P.single_cut ? 1 : std::min<int64_t>(P.steps[G - 1].K, std::max<int64_t>(j->row1 - j->row0, 1)) * std::max(j->nchunks, 1);
+    if (!P.single_cut && j->world == 1) pblocks = std::max(pblocks, gk::expand_sym_blocks((int32_t) P.steps[G - 1].K, P.m));
     if (j->partials_blocks < pblocks) {
         pool_free(j->partials); j->partials = nullptr;
         GK_CUDA(pool_alloc_t(&j->partials, (size_t) pblocks * 2 * sizeof(double), j->device));
@@ -1042,6 +1043,7 @@ int gk_phi_finish(gk_phi_job *j) {
         j->ran = true;
         return GK_OK;
     }
+    int64_t nblk = j->nblocks_expand;
     if (P.single_cut) {
         GK_CUDA(gk::launch_eye(j->out, P.m, j->row0, j->row1, j->partials, st));
     } else {
@@ -1065,9 +1067,15 @@ int gk_phi_finish(gk_phi_job *j) {
             j->launches++;
             e.G = j->gloc; e.compact = 1;
         }
-        GK_CUDA(gk::launch_expand(e, st));
+        // one GPU and every class of the last cut has a caller entry (always, unless the driver shards the result rows):
+        // the expansion that reads 64-byte segments of the symmetric matrix (GK_EXPAND=old: the gather kernel)
+        const char *env = std::getenv("GK_EXPAND");
+        const bool sym = j->world == 1 && j->nact == (int32_t) P.steps[last].K && !(env && env[0] == 'o') && (P.m & 1) == 0 &&
+                         gk::expand_sym_blocks(j->nact, P.m) <= j->partials_blocks;
+        if (sym) { nblk = gk::expand_sym_blocks(j->nact, P.m); GK_CUDA(gk::launch_expand_sym(e, st)); }
+        else GK_CUDA(gk::launch_expand(e, st));
     }
-    GK_CUDA(gk::launch_mean_finish(j->partials, j->nblocks_expand, j->scratch, j->sums_dev, st));
+    GK_CUDA(gk::launch_mean_finish(j->partials, nblk, j->scratch, j->sums_dev, st));
     GK_CUDA(cudaEventRecord(j->ev[1], st));
     j->launches += 3;
     GK_CUDA(cudaMemcpyAsync(j->sums_host, j->sums_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1806,9 +1814,11 @@ int copy_out_symmetric(gk_phi_job *j, double *out) {
         std::unique_ptr<std::atomic<int64_t>[]> next(new std::atomic<int64_t>[(size_t) nb]);
         std::unique_ptr<std::atomic<int>[]> landed(new std::atomic<int>[(size_t) nb]);
         for (int64_t k = 0; k < nb; k++) { next[k].store(0); landed[k].store(0); }
-        constexpr int64_t T = 64;
+        // tile = 16 landed rows x 256 columns: 2 KB sequential reads, 128-byte runs of streaming stores (measured on the host:
+        // 3 - 6 x the rate of 64 x 64 tiles, whose transposed writes into the local buffer collide on a few L1 sets)
+        constexpr int64_t TA = 16, TC = 256;
         auto work = [&]() {
-            alignas(64) double loc[T * T];
+            alignas(64) double loc[TA * TC];
             for (int64_t k = 0; k < nb; k++) {
                 int spins = 0, st;
                 while ((st = landed[k].load(std::memory_order_acquire)) == 0) { if (++spins < 256) std::this_thread::yield(); else std::this_thread::sleep_for(std::chrono::microseconds(50)); }
@@ -1816,27 +1826,27 @@ int copy_out_symmetric(gk_phi_job *j, double *out) {
                 const int64_t r0 = rb[k], r1 = rb[k + 1];
                 const int64_t cmax = std::min(r1, split);                 // destination rows: above the split the rows arrive whole
                 if (r1 <= r0 || cmax <= 0 || skip) continue;
-                const int64_t ntr = (r1 - r0 + T - 1) / T, ntc = (cmax + T - 1) / T, ntiles = ntr * ntc;
+                const int64_t ntr = (r1 - r0 + TA - 1) / TA, ntc = (cmax + TC - 1) / TC, ntiles = ntr * ntc;
                 for (int64_t t = next[k].fetch_add(1); t < ntiles; t = next[k].fetch_add(1)) {
-                    const int64_t tr = t % ntr, tc = t / ntr;             // consecutive tiles: the same 64 destination rows
-                    const int64_t a0 = r0 + tr * T, a1 = std::min(a0 + T, r1), c0 = tc * T, c1 = std::min(c0 + T, cmax);
+                    const int64_t tr = t % ntr, tc = t / ntr;             // consecutive tiles: the same 256 destination rows
+                    const int64_t a0 = r0 + tr * TA, a1 = std::min(a0 + TA, r1), c0 = tc * TC, c1 = std::min(c0 + TC, cmax);
                     if (c0 >= a1) continue;                               // entirely on the other side of the diagonal
                     const int64_t na = a1 - a0, nc = c1 - c0;
                     for (int64_t a = 0; a < na; a++) {
                         const double *src = out + (a0 + a) * m + c0;
-                        for (int64_t c = 0; c < nc; c++) loc[c * T + a] = src[c];
+                        for (int64_t c = 0; c < nc; c++) loc[c * TA + a] = src[c];
                     }
-                    if (c1 <= a0 && na == T && (((uintptr_t) (out + c0 * m + a0)) & 15) == 0 && (m & 1) == 0) {
+                    if (c1 <= a0 && na == TA && (((uintptr_t) (out + c0 * m + a0)) & 15) == 0 && (m & 1) == 0) {
                         for (int64_t c = 0; c < nc; c++) {
                             double *dst = out + (c0 + c) * m + a0;
-                            const double *l = loc + c * T;
-                            for (int64_t a = 0; a < T; a += 2) _mm_stream_pd(dst + a, _mm_load_pd(l + a));
+                            const double *l = loc + c * TA;
+                            for (int64_t a = 0; a < TA; a += 2) _mm_stream_pd(dst + a, _mm_load_pd(l + a));
                         }
                     } else {
                         for (int64_t c = 0; c < nc; c++) {
                             double *dst = out + (c0 + c) * m;
                             const int64_t lo = std::max(a0, c0 + c + 1);      // strictly above the diagonal: column a > row c
-                            for (int64_t a = lo; a < a1; a++) dst[a] = loc[c * T + (a - a0)];
+                            for (int64_t a = lo; a < a1; a++) dst[a] = loc[c * TA + (a - a0)];
                         }
                     }
                 }

@@ -996,6 +996,110 @@ __global__ void __launch_bounds__(256) expand_kernel(const ExpandDev e) {
     }
 }
 
+// The same expansion for ONE GPU, where every class row is local: the class matrix is symmetric, so the eight values
+// G[a0 .. a0 + 7][cls_j] that eight consecutive classes need for column j are ONE contiguous 64-byte segment of row cls_j --
+// G[cls_j][a0 .. a0 + 7].  A CTA = 8 classes x kExpandSymCols result columns; lane = (column j, 16-byte part of the segment):
+// a warp load touches 8 segments instead of 32 scattered 8-byte words (the gather rate, one divergent line per clock per
+// SM, was the bound of the kernel above), and every result row of those classes is written in 64-byte pieces.  CTAs of the
+// same 8 classes are adjacent in the grid: the 64-byte column block they read stays in L2 (2.8 MB at c4).
+constexpr int kExpSymMembers = 32;             // result rows per class staged in shared memory
+constexpr int kExpSymIter = 256;               // columns per iteration: two pairs per thread
+constexpr int kExpSymCols = 2048;              // result columns per CTA
+__global__ void __launch_bounds__(256, 3) expand_sym_kernel(const ExpandDev e) {
+    __shared__ int s_n[8], s_q0[8];
+    __shared__ int s_i[8][kExpSymMembers], s_u[8][kExpSymMembers];
+    const int nchunks = (int) ((e.m + kExpSymCols - 1) / kExpSymCols);
+    const int A = blockIdx.x / nchunks, chunk = blockIdx.x - A * nchunks;
+    const int a0 = A * 8, K = e.nact;
+    if (threadIdx.x < 8) {
+        const int c = a0 + threadIdx.x;
+        s_q0[threadIdx.x] = c < K ? e.coff[c] : 0;
+        s_n[threadIdx.x] = c < K ? e.coff[c + 1] - e.coff[c] : 0;
+    }
+    __syncthreads();
+    double sum = 0.0, dsum = 0.0;
+    {
+        // warp = class: its result rows (and their individuals) into shared memory; the diagonal entries out[i][i] that fall
+        // into this CTA's columns are the self kinship of the class
+        const int cl = threadIdx.x >> 5;
+        for (int k = threadIdx.x & 31; k < s_n[cl]; k += 32) {
+            const int i = e.cmem[s_q0[cl] + k];
+            if (k < kExpSymMembers) { s_i[cl][k] = i; s_u[cl][k] = e.ind[i]; }
+            if (i / kExpSymCols == chunk) dsum += e.d[a0 + cl];
+        }
+    }
+    __syncthreads();
+    // lane = (pair of adjacent columns, 16-byte part of the segment): the 8 lanes of a class pair write 128 contiguous bytes of
+    // a result row per instruction (m is even: the rows are 16-byte aligned)
+    const int r = threadIdx.x & 3, q = threadIdx.x >> 2;
+    const int ca = 2 * r, cb = 2 * r + 1;                                // this thread's two classes (within the block of 8)
+    const double da = a0 + ca < K ? e.d[a0 + ca] : 0.0, db = a0 + cb < K ? e.d[a0 + cb] : 0.0;
+    const long long jbase = (long long) chunk * kExpSymCols + 2 * q;
+    constexpr int U = kExpSymIter / 128, NIT = kExpSymCols / kExpSymIter;
+    struct Batch { int uj[U][2]; double2 v[U][2]; };
+    auto load = [&](Batch &b, const int it) {
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const long long j = jbase + (long long) it * kExpSymIter + u * 128 + h;
+                const bool ok = j < e.m;
+                b.uj[u][h] = ok ? e.ind[j] : -2;
+                const int c = ok ? e.cls[j] : 0;
+                b.v[u][h] = __ldcg(reinterpret_cast<const double2 *>(e.G + (long long) c * e.ld + a0 + ca));
+            }
+    };
+    auto store = [&](const Batch &b, const int it) {
+        const long long j0 = jbase + (long long) it * kExpSymIter;
+        const long long left = e.m - j0;                                 // even: a pair of columns is inside or outside together
+        const int nu = left <= 0 ? 0 : (int) (left + 127 < 128LL * U ? (left + 127) / 128 : U);
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int cl = half ? cb : ca;
+            const double dc = half ? db : da;
+            const int nm = s_n[cl];
+            for (int k = 0; k < nm; k++) {
+                long long i; int ui;
+                if (k < kExpSymMembers) { i = s_i[cl][k]; ui = s_u[cl][k]; } else { i = e.cmem[s_q0[cl] + k]; ui = e.ind[i]; }
+                double2 *rowp = reinterpret_cast<double2 *>(e.out + (i - e.row0) * e.m + j0);
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (u < nu) {
+                        double2 val;
+                        val.x = (b.uj[u][0] == ui) ? dc : (half ? b.v[u][0].y : b.v[u][0].x);
+                        val.y = (b.uj[u][1] == ui) ? dc : (half ? b.v[u][1].y : b.v[u][1].x);
+                        __stcs(rowp + u * 64, val);
+                        sum += val.x + val.y;
+                    }
+            }
+        }
+    };
+    // the segments of the next 256 columns are in flight while the current ones are written
+    Batch b0, b1;
+    load(b0, 0);
+#pragma unroll 1
+    for (int it = 0; it < NIT; it += 2) {
+        load(b1, it + 1);
+        store(b0, it);
+        if (it + 2 < NIT) load(b0, it + 2);
+        store(b1, it + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    }
+    __shared__ double ws[8], wd[8];
+    if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = sum; wd[threadIdx.x >> 5] = dsum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x = 0.0, y = 0.0;
+        for (int w = 0; w < 8; w++) { x += ws[w]; y += wd[w]; }
+        e.partials[2 * (long long) blockIdx.x] = x;
+        e.partials[2 * (long long) blockIdx.x + 1] = y;
+    }
+}
+
 // All probands are top founders (single cut): 0.5*I, even for duplicated probands
 // (lib/compute.cpp:655-661).  partials[0..1] = (sum, diagonal sum) of the local rows.
 __global__ void eye_kernel(double *out, long long m, long long row0, long long row1, double *partials) {
@@ -1197,6 +1301,14 @@ cudaError_t launch_fetch_rows(const RowTable &t, int64_t ld, const int32_t *rows
 cudaError_t launch_expand(const ExpandDev &e, cudaStream_t st) {
     if (e.nact <= 0) return cudaSuccess;
     expand_kernel<<<(unsigned) ((long long) e.nact * e.nchunks), 256, 0, st>>>(e);
+    return cudaGetLastError();
+}
+
+int64_t expand_sym_blocks(int32_t nact, int64_t m) { return (int64_t) ((nact + 7) / 8) * ((m + kExpSymCols - 1) / kExpSymCols); }
+
+cudaError_t launch_expand_sym(const ExpandDev &e, cudaStream_t st) {
+    if (e.nact <= 0) return cudaSuccess;
+    expand_sym_kernel<<<(unsigned) expand_sym_blocks(e.nact, e.m), 256, 0, st>>>(e);
     return cudaGetLastError();
 }
 

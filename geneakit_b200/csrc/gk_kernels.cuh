@@ -115,6 +115,9 @@ cudaError_t launch_init_rows(double *G0, double *d0, const int32_t *flags, int64
 cudaError_t launch_fetch_rows(const RowTable &t, int64_t ld, const int32_t *rows, int32_t nrows, double *dst, cudaStream_t st);
 constexpr int kExpandCols = 2048;     // result columns per CTA of the expansion kernel
 cudaError_t launch_expand(const ExpandDev &e, cudaStream_t st);
+// one GPU, every class active (cact = identity): 8 classes x 1024 columns per CTA, 64-byte segments of the symmetric matrix
+cudaError_t launch_expand_sym(const ExpandDev &e, cudaStream_t st);
+int64_t expand_sym_blocks(int32_t nact, int64_t m);     // its grid = its (sum, diagonal sum) partials
 cudaError_t launch_eye(double *out, int64_t m, int64_t row0, int64_t row1, double *partials, cudaStream_t st);
 // two-stage deterministic reduction of the per-CTA partials: scratch holds 2*256 doubles
 cudaError_t launch_mean_finish(const double *partials, int64_t nblocks, double *scratch, double *sums /*2*/, cudaStream_t st);
