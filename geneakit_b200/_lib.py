@@ -112,6 +112,7 @@ def _load():
     L.gk_phi_set_peer.argtypes = [vp, i32, vp, vp]
     L.gk_phi_peers_ready.argtypes = [vp]
     L.gk_phi_run_step.argtypes = [vp, i32]
+    L.gk_phi_run_pull.argtypes = [vp, i32]
     L.gk_phi_finish.argtypes = [vp]
     L.gk_phi_dvec.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
     L.gk_phi_dvec_copy_from.argtypes = [vp, vp, i32]
@@ -146,7 +147,7 @@ EXPORTS = [
     "gk_phi_device_result", "gk_phi_copy_rows", "gk_phi_get_stats", "gk_phi_cut_sizes", "gk_phi_class_sizes",
     "gk_phi_step_times", "gk_phi_step_bytes", "gk_phi_free", "gk_phi_step_view", "gk_phi_final_view",
     "gk_phi_ipc_export", "gk_phi_ipc_open", "gk_phi_local_buffers", "gk_phi_set_peer", "gk_phi_peers_ready",
-    "gk_phi_run_step", "gk_phi_finish", "gk_phi_dvec", "gk_phi_dvec_copy_from",
+    "gk_phi_run_step", "gk_phi_run_pull", "gk_phi_finish", "gk_phi_dvec", "gk_phi_dvec_copy_from",
     "gk_phi_debug_prof", "gk_cache_release", "gk_gc_last_stats",
     "gk_opts_init", "gk_phi_last_timing", "gk_f_f64", "gk_phi_stream", "gk_phi_set_stream", "gk_phi_replan", "gk_phi_reupload", "gk_phi_pass", "gk_phi_pass_begin", "gk_phi_pass_step", "gk_phi_pass_end", "gk_phi_pass_begin_all", "gk_phi_seg_count", "gk_phi_seg_ipc_export", "gk_phi_seg_ipc_open", "gk_phi_clone_rank", "gk_phi_diag", "gk_phi_f",
     "gk_phi_over", "gk_phi_over_fetch", "gk_phi_sparse", "gk_phi_sparse_fetch", "gk_phi_ci_stats",

@@ -1028,6 +1028,22 @@ int gk_phi_run_step(gk_phi_job *j, int32_t g) {
     return GK_OK;
 }
 
+// Ranked (deep) sharded jobs only, after the barrier that follows gk_phi_run_step(job, g) and before a second barrier: pull
+// the mirror tiles of this rank's rows out of the rows of the higher ranks (see pull_mirror_kernel).  A no-op for every
+// other job.
+int gk_phi_run_pull(gk_phi_job *j, int32_t g) {
+    if (!j || !j->uploaded) return fail(GK_ERR_STATE, "job not uploaded");
+    gk::PhiPlan &P = *j->planp;
+    if (g < 0 || g >= P.G) return fail(GK_ERR_ARG, "bad step");
+    if (j->world < 2 || !P.ranked || g == 0 || P.single_cut) return GK_OK;
+    GK_CUDA(cudaSetDevice(j->device));
+    const StepOffsets &o = j->off[g];
+    const gk::StepPlan &S = P.steps[g];
+    GK_CUDA(gk::launch_pull_mirror(row_table(j, g), S.Kpad, o.pb, o.pe, S.np, j->buf[g & 1], (int64_t) o.pb * gk::kPanel, j->stream));
+    j->launches++;
+    return GK_OK;
+}
+
 // Final expansion to the caller's proband order + the fused phiMean partial sums of the own rows.
 int gk_phi_finish(gk_phi_job *j) {
     if (!j || !j->uploaded) return fail(GK_ERR_STATE, "job not uploaded");
@@ -1708,12 +1724,16 @@ int phi_pipelined(int32_t n, const int32_t *sire, const int32_t *dam, int32_t m,
         rc = pass_feed(M.jobs, g);
         if (rc) { drain(M.jobs); return rc; }
         for (int q = 0; q < ndev; q++) { rc = gk_phi_run_step(M.jobs[q], g); if (rc) { drain(M.jobs); return rc; } }
-        if (ndev > 1 && !virt) {
-            // the barrier between cuts: every rank's step g (rows + self kinships written to every replica) before any step g + 1
-            for (int q = 0; q < ndev; q++) { GK_CUDA(cudaSetDevice(M.jobs[q]->device)); GK_CUDA(cudaEventRecord(M.cut_done[q], M.jobs[q]->stream)); }
-            for (int q = 0; q < ndev; q++) {
-                GK_CUDA(cudaSetDevice(M.jobs[q]->device));
-                for (int p = 0; p < ndev; p++) if (p != q) GK_CUDA(cudaStreamWaitEvent(M.jobs[q]->stream, M.cut_done[p], 0));
+        // the barrier between cuts: every rank's step g (rows + self kinships written to every replica) before any step g + 1;
+        // ranked jobs then pull their mirror tiles out of the higher ranks' rows, and a second barrier completes the cut
+        for (int round = 0; round < (ndev > 1 && j0->planp->ranked && g > 0 ? 2 : 1); round++) {
+            if (round == 1) for (int q = 0; q < ndev; q++) { rc = gk_phi_run_pull(M.jobs[q], g); if (rc) { drain(M.jobs); return rc; } }
+            if (ndev > 1 && !virt) {
+                for (int q = 0; q < ndev; q++) { GK_CUDA(cudaSetDevice(M.jobs[q]->device)); GK_CUDA(cudaEventRecord(M.cut_done[q], M.jobs[q]->stream)); }
+                for (int q = 0; q < ndev; q++) {
+                    GK_CUDA(cudaSetDevice(M.jobs[q]->device));
+                    for (int p = 0; p < ndev; p++) if (p != q) GK_CUDA(cudaStreamWaitEvent(M.jobs[q]->stream, M.cut_done[p], 0));
+                }
             }
         }
     }

@@ -407,7 +407,9 @@ __global__ void __launch_bounds__(kThreadsTma, 1) phi_step_tma_kernel(const Step
             cp_async_wait_all();
             __syncwarp();
             if (J != I || s.full_rows) {
-                if (!s.full_rows) {
+                // (tile J of another rank -- a ranked multi-GPU job evaluates J <= I only -- is not stored by this rank: its
+                // owner pulls the transposed piece out of this rank's rows afterwards, pull_mirror_kernel)
+                if (!s.full_rows && J >= s.panel_begin) {
 #pragma unroll 8
                     for (int j = 0; j < T; j++) {
                         const int sl = __shfl_sync(0xffffffffu, slots, j);
@@ -925,6 +927,29 @@ __global__ void init_rows_kernel(double *G0, double *d0, const int32_t *flags, l
     for (long long i = t0; i < dlen; i += stride) d0[i] = 0.5;
 }
 
+// Ranked multi-GPU jobs evaluate the tiles J <= I only (the reference's rounding order) and every rank stores into its OWN
+// rows.  The tiles (J own, I of a higher rank) of this rank's rows are the transposes of tiles the owners of I computed into
+// THEIR rows: read them out of the owners' HBM (256-byte row segments over NVLink), transpose through shared memory, store
+// into the own rows.  One warp per tile; runs after the barrier that follows the step, and a second barrier follows it.
+__global__ void __launch_bounds__(128) pull_mirror_kernel(const RowTable t, long long ld, int pb, int pe, int np, double *own, long long own_row0) {
+    __shared__ double tile[4][T][T + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long per = np - pe, ntiles = (long long) (pe - pb) * per;
+    for (long long w = blockIdx.x * 4LL + warp; w < ntiles; w += gridDim.x * 4LL) {
+        const int Jp = pb + (int) (w / per), Ip = pe + (int) (w % per);
+        double v[T];
+#pragma unroll
+        for (int k = 0; k < T; k++) v[k] = __ldcg(row_ptr(t, Ip * T + k, ld) + (long long) Jp * T + lane);
+#pragma unroll
+        for (int k = 0; k < T; k++) tile[warp][k][lane] = v[k];
+        __syncwarp();
+        double *dst = own + ((long long) Jp * T - own_row0) * ld + (long long) Ip * T + lane;
+#pragma unroll 8
+        for (int k = 0; k < T; k++) __stcs(dst + (long long) k * ld, tile[warp][lane][k]);
+        __syncwarp();
+    }
+}
+
 // Multi-GPU expansion: copy the class rows this rank's probands need from their owners (peer
 // reads over NVLink, 16-byte vectorised, one CTA per row) into a compact local matrix.
 __global__ void __launch_bounds__(256) fetch_rows_kernel(const RowTable t, long long ld, const int32_t *rows, double *dst) {
@@ -1295,6 +1320,12 @@ cudaError_t launch_init_rows(double *G0, double *d0, const int32_t *flags, int64
 cudaError_t launch_fetch_rows(const RowTable &t, int64_t ld, const int32_t *rows, int32_t nrows, double *dst, cudaStream_t st) {
     if (nrows <= 0) return cudaSuccess;
     fetch_rows_kernel<<<(unsigned) nrows, 256, 0, st>>>(t, ld, rows, dst);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pull_mirror(const RowTable &t, int64_t ld, int32_t pb, int32_t pe, int32_t np, double *own, int64_t own_row0, cudaStream_t st) {
+    if (pe <= pb || np <= pe) return cudaSuccess;
+    pull_mirror_kernel<<<148 * 8, 128, 0, st>>>(t, ld, pb, pe, np, own, own_row0);
     return cudaGetLastError();
 }
 

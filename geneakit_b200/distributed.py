@@ -77,6 +77,7 @@ class ShardedPhi:
         self.m = self.job.m
         self.row0, self.row1 = self.job.row0, self.job.row1
         self.G = self.job.stats()["n_cuts"]
+        self._ranked = bool(self.job.stats()["ranked"])
         self._dv = None
         self._fence = None
         self._shared_plan = False
@@ -162,6 +163,11 @@ class ShardedPhi:
                 full, chunk = self._dv[g]
                 # the only per-cut collective: 8 bytes per class, and the barrier between cuts
                 dist.all_gather_into_tensor(full, full[self.rank * chunk:(self.rank + 1) * chunk])
+                if self._ranked and g > 0:
+                    # deep pedigrees (rank-ordered rounding): tiles J <= I only, every rank stored into its own rows; now pull
+                    # the mirror tiles out of the higher ranks' rows, and fence before anybody reads this cut's rows
+                    check(lib.gk_phi_run_pull(self.job._h, g))
+                    dist.all_reduce(self._fence)
             check(lib.gk_phi_finish(self.job._h))
             # the expansion read the peers' rows: nobody may start the next pass (or free) before everybody is done
             dist.all_reduce(self._fence)
@@ -239,6 +245,10 @@ class VirtualShardedPhi:
             for j in self.jobs:
                 for src in self.jobs:
                     check(lib.gk_phi_dvec_copy_from(j._h, src._h, g))
+            for j in self.jobs:
+                j.sync()
+            for j in self.jobs:                # ranked jobs: the mirror tiles of the own rows, out of the higher ranks' rows
+                check(lib.gk_phi_run_pull(j._h, g))
             for j in self.jobs:
                 j.sync()
         for j in self.jobs:

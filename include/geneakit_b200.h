@@ -245,6 +245,11 @@ int gk_phi_local_buffers(gk_phi_job *job, void **buf0, void **buf1);
 int gk_phi_set_peer(gk_phi_job *job, int32_t peer_rank, void *buf0, void *buf1);
 int gk_phi_peers_ready(gk_phi_job *job);
 int gk_phi_run_step(gk_phi_job *job, int32_t step);      /* step 0 = founders' matrix, 1 .. G-1 = recurrence */
+/* RANKED (deeper than 26 generations) sharded jobs evaluate the tiles J <= I only and every rank stores into its own rows;
+ * after the collective that follows gk_phi_run_step(job, g) every rank calls gk_phi_run_pull(job, g) -- its tiles (J own,
+ * I of a higher rank) are read out of the owners' rows over NVLink and transposed -- and a second stream-ordered collective
+ * must follow before the next step.  A no-op for every other job. */
+int gk_phi_run_pull(gk_phi_job *job, int32_t step);
 int gk_phi_finish(gk_phi_job *job);                      /* expansion to caller order + phiMean partial sums */
 /* Self kinship per class of cut `step` (device pointer, replicated on every rank): rank r writes
  * doubles [r*chunk, (r+1)*chunk) and the driver all-gathers the `total` = world*chunk doubles. */
