@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) phi_step_kernel(const StepDev s) 
             cp_async_wait_all();
             __syncwarp();
             if (J != I || s.full_rows) {
-                if (!s.full_rows) {
+                if (!s.full_rows && J >= s.panel_begin) {     // (a tile J of another rank is pulled by its owner: pull_mirror_kernel)
                     // direct: lane = class i of the panel, row j: B[j][i] = 1/2 (N^T[F_j][i] + N^T[M_j][i])
 #pragma unroll 8
                     for (int j = 0; j < T; j++) {
@@ -789,6 +789,9 @@ __global__ void __launch_bounds__(kThreadsG4, 1) phi_step_g4_kernel(const StepDe
                 }
                 double *drow = out + ((long long) J * T - s.out_row0) * ldn + I * T + lane;    // row j of tile J, columns of panel I
                 double *mrow = out + ((long long) I * T - s.out_row0) * ldn + J * T;           // row i of panel I, columns of tile J
+                // rows of tile J are stored only if they are this rank's: a sharded job stores its own rows (the transposed pieces);
+                // ranked sharded jobs evaluate J <= I and the owner of J pulls the piece out of this rank's rows (pull_mirror_kernel)
+                const bool own_j = !s.full_rows && J >= s.panel_begin;
                 if (J != I || s.full_rows) {
                     // (a rank of a sharded job evaluates every tile J for its own panels and stores only its own rows: the
                     // transposed pieces)
@@ -809,7 +812,7 @@ __global__ void __launch_bounds__(kThreadsG4, 1) phi_step_g4_kernel(const StepDe
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
                             const double v = 0.5 * (x[i] + y[i]);
-                            if (!nostore && !s.full_rows) st_hint(drow + (long long) (8 * bt + i) * ldn, v, pol_out);
+                            if (!nostore && own_j) st_hint(drow + (long long) (8 * bt + i) * ldn, v, pol_out);
                             scr[((8 * bt + i) & 15) * G4SCRP + lane] = v;
                         }
                     };
@@ -934,19 +937,27 @@ __global__ void init_rows_kernel(double *G0, double *d0, const int32_t *flags, l
 __global__ void __launch_bounds__(128) pull_mirror_kernel(const RowTable t, long long ld, int pb, int pe, int np, double *own, long long own_row0) {
     __shared__ double tile[4][T][T + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long per = np - pe, ntiles = (long long) (pe - pb) * per;
-    for (long long w = blockIdx.x * 4LL + warp; w < ntiles; w += gridDim.x * 4LL) {
-        const int Jp = pb + (int) (w / per), Ip = pe + (int) (w % per);
-        double v[T];
+    // unit of work = one panel I of a higher rank x 8 consecutive own panels J: the warp walks along the 32 source rows
+    // (sequential 256-byte pieces of the same remote pages), and the warps of a CTA share those rows
+    constexpr int kRun = 8;
+    const long long runs = (pe - pb + kRun - 1) / kRun, nunits = (long long) (np - pe) * runs;
+    for (long long u = blockIdx.x * 4LL + warp; u < nunits; u += gridDim.x * 4LL) {
+        const int Ip = pe + (int) (u / runs), J0 = pb + (int) (u % runs) * kRun, J1 = min(J0 + kRun, pe);
+        const double *src[T];
 #pragma unroll
-        for (int k = 0; k < T; k++) v[k] = __ldcg(row_ptr(t, Ip * T + k, ld) + (long long) Jp * T + lane);
+        for (int k = 0; k < T; k++) src[k] = row_ptr(t, Ip * T + k, ld) + lane;
+        for (int Jp = J0; Jp < J1; Jp++) {
+            double v[T];
 #pragma unroll
-        for (int k = 0; k < T; k++) tile[warp][k][lane] = v[k];
-        __syncwarp();
-        double *dst = own + ((long long) Jp * T - own_row0) * ld + (long long) Ip * T + lane;
+            for (int k = 0; k < T; k++) v[k] = __ldcg(src[k] + (long long) Jp * T);
+#pragma unroll
+            for (int k = 0; k < T; k++) tile[warp][k][lane] = v[k];
+            __syncwarp();
+            double *dst = own + ((long long) Jp * T - own_row0) * ld + (long long) Ip * T + lane;
 #pragma unroll 8
-        for (int k = 0; k < T; k++) __stcs(dst + (long long) k * ld, tile[warp][lane][k]);
-        __syncwarp();
+            for (int k = 0; k < T; k++) __stcs(dst + (long long) k * ld, tile[warp][lane][k]);
+            __syncwarp();
+        }
     }
 }
 

@@ -144,13 +144,12 @@ struct ClassRec {
 // Which step kernel a job runs per cut decides which plan arrays that cut needs (gk_capi.cu reads the same choice).
 struct KernelChoice {
     int use_g4 = 1;        // default step kernel for large cuts (TMA bulk-copy phase 1, L2-direct phase 2)
-    int use_tma = 0;       // sharded jobs: the kernel with TMA phase 1 on 8-class items (small cuts; ranked multi-GPU jobs always)
+    int use_tma = 0;       // sharded jobs: the kernel with TMA phase 1 on 8-class items (small cuts)
     int g4_min_k = 8192;   // smallest previous-cut matrix the default kernel is used for
     static KernelChoice resolve(int world, bool ranked) {
         KernelChoice k;
         k.use_tma = world > 1 ? 1 : 0;
         if (const char *e = std::getenv("GK_STEP_KERNEL")) { k.use_tma = (e[0] == 't') ? 1 : 0; k.use_g4 = (e[0] == 'g') ? 1 : 0; }
-        if (world > 1 && ranked) { k.use_g4 = 0; k.use_tma = 1; }      // only that kernel stores mirror tiles into a peer's rows
         if (const char *e = std::getenv("GK_G4_MIN_K")) { const int v = std::atoi(e); if (v > 0) k.g4_min_k = v; }
         return k;
     }

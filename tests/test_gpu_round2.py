@@ -100,6 +100,20 @@ def test_c5_tenth_width_replica_matches_the_oracle():
     assert abs(got.sum() - len(pro)) < 1e-9              # every proband's founders contribute 1 in total
 
 
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("name", ["deep45_shuffled", "deep30_w40"])
+def test_ranked_sharded_ranks_through_the_default_kernel(name, world, monkeypatch):
+    """Deep (ranked) sharded jobs run the default step kernel too: tiles J <= I, own rows only, mirror tiles pulled."""
+    from geneakit_b200.distributed import VirtualShardedPhi
+    monkeypatch.setenv("GK_STEP_KERNEL", "g4")
+    monkeypatch.setenv("GK_G4_MIN_K", "32")
+    g = load_golden(name)
+    v = VirtualShardedPhi(_ped(g), [int(x) for x in g["pro"]], world=world).upload().run()
+    assert v.jobs[0].stats()["ranked"] == 1
+    assert v.to_host().tobytes() == g["phi"].tobytes()
+    v.close()
+
+
 # ---- one process, several GPUs, behind the one-shot entry point --------------------------------------------------------
 @pytest.mark.parametrize("gpus", [2, 3, 8])
 @pytest.mark.parametrize("name", ["overlap400_s1", "geneaJi_dup_anc", "founders_only", "deep45_shuffled", "genea140"])
