@@ -250,6 +250,7 @@ struct gk_phi_job {
     size_t off_final_cls = 0, off_final_ind = 0, off_cact = 0, off_coff = 0, off_cmem = 0;
     int64_t row0 = 0, row1 = 0;       // result rows owned by this shard (caller order)
     int32_t nact = 0, nchunks = 0;
+    int32_t fetch_first = 0;          // world > 1: position in the list of active classes of the first row the NEXT rank owns
     int64_t nblocks_expand = 0;
     double *scratch = nullptr;
     unsigned long long *prof = nullptr;   // GK_PROF=1: role cycle counters of the gather4 step kernel, summed over the steps
@@ -540,6 +541,11 @@ static bool pack_cut(gk_phi_job *j, int g) {
         for (int64_t i = j->row0; i < j->row1; i++) cmem[w[slot[P.final_cls[i]]]++] = (int32_t) i;
     }
     j->nact = (int32_t) cact.size();
+    {
+        const int64_t next_row0 = (int64_t) ((j->rank + 1) % j->world) * j->off[G - 1].cpp * gk::kPanel;
+        j->fetch_first = (int32_t) (std::lower_bound(cact.begin(), cact.end(), (int32_t) std::min<int64_t>(next_row0, INT32_MAX)) - cact.begin());
+        if (j->fetch_first >= j->nact) j->fetch_first = 0;
+    }
     j->off_cact = pf.add(cact); j->off_coff = pf.add(coff); j->off_cmem = pf.add(cmem);
     j->nblocks_expand = P.single_cut ? 1 : (int64_t) j->nact * j->nchunks;
     if (!pf.write(j->blob[G])) { j->pack_error = "cudaHostAlloc failed (pinned staging of the plan)"; return false; }
@@ -1079,7 +1085,8 @@ int gk_phi_finish(gk_phi_job *j) {
                 GK_CUDA(pool_alloc_t(&j->gloc, (size_t) gl * sizeof(double), j->device));
                 j->gloc_doubles = gl; j->device_bytes += gl * 8;
             }
-            GK_CUDA(gk::launch_fetch_rows(row_table(j, last), e.ld, e.cact, j->nact, j->gloc, st));
+            // (start with the rows of the NEXT rank: every rank walks the owners in its own order)
+            GK_CUDA(gk::launch_fetch_rows(row_table(j, last), e.ld, e.cact, j->nact, j->gloc, j->fetch_first, st));
             j->launches++;
             e.G = j->gloc; e.compact = 1;
         }

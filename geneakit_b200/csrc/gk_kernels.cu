@@ -963,9 +963,12 @@ __global__ void __launch_bounds__(128) pull_mirror_kernel(const RowTable t, long
 
 // Multi-GPU expansion: copy the class rows this rank's probands need from their owners (peer
 // reads over NVLink, 16-byte vectorised, one CTA per row) into a compact local matrix.
-__global__ void __launch_bounds__(256) fetch_rows_kernel(const RowTable t, long long ld, const int32_t *rows, double *dst) {
-    const double2 *src = reinterpret_cast<const double2 *>(row_ptr(t, rows[blockIdx.x], ld));
-    double2 *out = reinterpret_cast<double2 *>(dst + (long long) blockIdx.x * ld);
+__global__ void __launch_bounds__(256) fetch_rows_kernel(const RowTable t, long long ld, const int32_t *rows, double *dst, int rot) {
+    // (the ranks walk the owners in different orders -- rank q starts with the rows of rank q + 1 -- instead of all of them
+    // queueing on rank 0's links first, then on rank 1's, ...)
+    const int a = (int) ((blockIdx.x + (unsigned) rot) % gridDim.x);
+    const double2 *src = reinterpret_cast<const double2 *>(row_ptr(t, rows[a], ld));
+    double2 *out = reinterpret_cast<double2 *>(dst + (long long) a * ld);
     for (long long c = threadIdx.x; c < ld / 2; c += 256) out[c] = src[c];
 }
 
@@ -1328,9 +1331,9 @@ cudaError_t launch_init_rows(double *G0, double *d0, const int32_t *flags, int64
     return cudaGetLastError();
 }
 
-cudaError_t launch_fetch_rows(const RowTable &t, int64_t ld, const int32_t *rows, int32_t nrows, double *dst, cudaStream_t st) {
+cudaError_t launch_fetch_rows(const RowTable &t, int64_t ld, const int32_t *rows, int32_t nrows, double *dst, int32_t first, cudaStream_t st) {
     if (nrows <= 0) return cudaSuccess;
-    fetch_rows_kernel<<<(unsigned) nrows, 256, 0, st>>>(t, ld, rows, dst);
+    fetch_rows_kernel<<<(unsigned) nrows, 256, 0, st>>>(t, ld, rows, dst, first);
     return cudaGetLastError();
 }
 

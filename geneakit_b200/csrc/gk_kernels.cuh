@@ -114,7 +114,7 @@ cudaError_t launch_init_rows(double *G0, double *d0, const int32_t *flags, int64
                              int64_t row_begin, int64_t rows, int64_t dlen, cudaStream_t st);
 // ranked multi-GPU jobs: this rank's tiles (J own, I >= panel_end) = transposes of the tiles in the rows of I's owners
 cudaError_t launch_pull_mirror(const RowTable &t, int64_t ld, int32_t pb, int32_t pe, int32_t np, double *own, int64_t own_row0, cudaStream_t st);
-cudaError_t launch_fetch_rows(const RowTable &t, int64_t ld, const int32_t *rows, int32_t nrows, double *dst, cudaStream_t st);
+cudaError_t launch_fetch_rows(const RowTable &t, int64_t ld, const int32_t *rows, int32_t nrows, double *dst, int32_t first /* list position fetched first */, cudaStream_t st);
 constexpr int kExpandCols = 2048;     // result columns per CTA of the expansion kernel
 cudaError_t launch_expand(const ExpandDev &e, cudaStream_t st);
 // one GPU, every class active (cact = identity): 8 classes x 1024 columns per CTA, 64-byte segments of the symmetric matrix
