@@ -214,6 +214,7 @@ struct gk_phi_job {
     cudaStream_t copy_stream = nullptr;               // H2D of the plan segments (overlaps the step kernels of earlier cuts)
     cudaEvent_t pass_ev = nullptr;                    // everything enqueued before the current pass (the copies must not overtake it)
     std::vector<cudaEvent_t> seg_ev;                  // segment g is on the device
+    std::vector<cudaEvent_t> fetch_ev;                // sharded jobs: chunk k of the expansion's class rows has been fetched
     double *buf[2] = { nullptr, nullptr };            // own rows of the class matrices, ping-pong by step parity
     int64_t buf_doubles[2] = { 0, 0 };
     double *peer[gk::kMaxShards][2] = {};             // every rank's buffers (own entry = buf); IPC mappings for the others
@@ -303,6 +304,7 @@ void destroy(gk_phi_job *j) {
     pool_free(j->counters);
     for (cudaEvent_t e : j->ev) cudaEventDestroy(e);
     for (cudaEvent_t e : j->seg_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : j->fetch_ev) cudaEventDestroy(e);
     if (j->pass_ev) cudaEventDestroy(j->pass_ev);
     if (j->copy_stream) cudaStreamDestroy(j->copy_stream);
     if (j->own_stream && j->stream) cudaStreamDestroy(j->stream);
@@ -782,6 +784,7 @@ int alloc_buffers(gk_phi_job *j) {
     if ((int) j->seg.size() != G + 1) {
         for (int32_t *p : j->seg) pool_free(p);
         for (cudaEvent_t e : j->seg_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : j->fetch_ev) cudaEventDestroy(e);
         j->seg.assign((size_t) G + 1, nullptr); j->seg_cap.assign((size_t) G + 1, 0);
         j->seg_ev.assign((size_t) G + 1, nullptr);
         for (auto &e : j->seg_ev) GK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1078,25 +1081,65 @@ int gk_phi_finish(gk_phi_job *j) {
         e.nact = j->nact; e.nchunks = j->nchunks; e.partials = j->partials;
         if (j->world == 1) { e.G = j->buf[last & 1]; e.compact = 0; }
         else {
-            // the class rows of the own probands live on their owners: fetch them (coalesced peer reads)
-            const int64_t gl = (int64_t) std::max(j->nact, 1) * P.steps[G - 1].Kpad;
+            // the class rows of the own probands live on their owners: fetch them (peer reads over NVLink)
+            const int64_t ldt = gk::round_up(std::max(j->nact, 1), 32);
+            const int64_t gl = ldt * P.steps[G - 1].Kpad;
             if (j->gloc_doubles < gl) {
                 pool_free(j->gloc); j->gloc = nullptr; j->gloc_doubles = 0;
                 GK_CUDA(pool_alloc_t(&j->gloc, (size_t) gl * sizeof(double), j->device));
                 j->gloc_doubles = gl; j->device_bytes += gl * 8;
             }
-            // (start with the rows of the NEXT rank: every rank walks the owners in its own order)
-            GK_CUDA(gk::launch_fetch_rows(row_table(j, last), e.ld, e.cact, j->nact, j->gloc, j->fetch_first, st));
-            j->launches++;
+            const char *envx = std::getenv("GK_EXPAND");
+            // even m: the rows are fetched TRANSPOSED and expanded by the kernel that reads 64-byte segments (the gather
+            // kernel is bound by its 8-byte gathers: 26 ms for HALF of c4's rows at two GPUs)
+            const bool symw = (P.m & 1) == 0 && !(envx && envx[0] == 'o') && gk::expand_sym_blocks(j->nact, P.m) <= j->partials_blocks;
             e.G = j->gloc; e.compact = 1;
+            if (symw) { e.ld = ldt; nblk = gk::expand_sym_blocks(j->nact, P.m); }
+            // Fetch and expand in chunks of the active classes (blocks of 32): the fetch of chunk k + 1 (copy stream, NVLink
+            // reads) runs while chunk k is expanded (HBM writes).  The chunks start with the rows of the NEXT rank: every rank
+            // walks the owners in its own order instead of all of them queueing on rank 0's links first, then on rank 1's, ...
+            const int64_t nb32 = (j->nact + 31) / 32;
+            const int nchunk = (int) std::max<int64_t>(1, std::min<int64_t>(8, nb32 / 16));
+            if ((int) j->fetch_ev.size() < nchunk + 1) {
+                const size_t have = j->fetch_ev.size();
+                j->fetch_ev.resize((size_t) nchunk + 1, nullptr);
+                for (size_t k = have; k < j->fetch_ev.size(); k++) GK_CUDA(cudaEventCreateWithFlags(&j->fetch_ev[k], cudaEventDisableTiming));
+            }
+            GK_CUDA(cudaEventRecord(j->fetch_ev[nchunk], st));                       // the last cut is complete (on every rank: the driver's collective precedes)
+            GK_CUDA(cudaStreamWaitEvent(j->copy_stream, j->fetch_ev[nchunk], 0));
+            const gk::RowTable rt = row_table(j, last);
+            const int64_t Kpad_last = P.steps[last].Kpad;
+            for (int k = 0; k < nchunk && j->nact > 0; k++) {
+                const int64_t p0 = nb32 * k / nchunk, p1 = nb32 * (k + 1) / nchunk;
+                // blocks [p0, p1) of the ROTATED list = at most two runs of the list
+                const int64_t s0 = (j->fetch_first / 32 + p0) % nb32, len = p1 - p0, run1 = std::min<int64_t>(len, nb32 - s0);
+                const int64_t runs[2][2] = { { s0, run1 }, { 0, len - run1 } };
+                for (int r = 0; r < 2; r++) {
+                    const int32_t a_begin = (int32_t) (runs[r][0] * 32);
+                    const int32_t a_count = (int32_t) std::min<int64_t>(runs[r][1] * 32, j->nact - a_begin);
+                    if (runs[r][1] <= 0 || a_count <= 0) continue;
+                    if (symw) GK_CUDA(gk::launch_fetch_rows_t(rt, Kpad_last, e.cact, a_begin, a_count, j->nact, (int32_t) (Kpad_last / 32), j->gloc, ldt, j->copy_stream));
+                    else GK_CUDA(gk::launch_fetch_rows(rt, Kpad_last, e.cact, a_begin, a_count, j->gloc, j->copy_stream));
+                }
+                GK_CUDA(cudaEventRecord(j->fetch_ev[k], j->copy_stream));
+                GK_CUDA(cudaStreamWaitEvent(st, j->fetch_ev[k], 0));
+                for (int r = 0; r < 2; r++) {
+                    const int32_t a_begin = (int32_t) (runs[r][0] * 32);
+                    const int32_t a_count = (int32_t) std::min<int64_t>(runs[r][1] * 32, j->nact - a_begin);
+                    if (runs[r][1] <= 0 || a_count <= 0) continue;
+                    if (symw) GK_CUDA(gk::launch_expand_sym(e, a_begin, a_count, st));
+                    else GK_CUDA(gk::launch_expand(e, a_begin, a_count, st));
+                }
+                j->launches += 2;
+            }
         }
         // one GPU and every class of the last cut has a caller entry (always, unless the driver shards the result rows):
         // the expansion that reads 64-byte segments of the symmetric matrix (GK_EXPAND=old: the gather kernel)
         const char *env = std::getenv("GK_EXPAND");
         const bool sym = j->world == 1 && j->nact == (int32_t) P.steps[last].K && !(env && env[0] == 'o') && (P.m & 1) == 0 &&
                          gk::expand_sym_blocks(j->nact, P.m) <= j->partials_blocks;
-        if (sym) { nblk = gk::expand_sym_blocks(j->nact, P.m); GK_CUDA(gk::launch_expand_sym(e, st)); }
-        else GK_CUDA(gk::launch_expand(e, st));
+        if (sym) { nblk = gk::expand_sym_blocks(j->nact, P.m); GK_CUDA(gk::launch_expand_sym(e, 0, j->nact, st)); }
+        else if (j->world == 1) GK_CUDA(gk::launch_expand(e, 0, j->nact, st));
     }
     GK_CUDA(gk::launch_mean_finish(j->partials, nblk, j->scratch, j->sums_dev, st));
     GK_CUDA(cudaEventRecord(j->ev[1], st));

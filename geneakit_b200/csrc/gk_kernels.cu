@@ -961,12 +961,42 @@ __global__ void __launch_bounds__(128) pull_mirror_kernel(const RowTable t, long
     }
 }
 
+// Multi-GPU expansion, even m: the class rows this rank's probands need, fetched from their owners TRANSPOSED --
+// GT[c][a] = G[rows[a]][c] for the active classes a in [a_begin, a_begin + a_count) and every class column c -- so that
+// expand_sym_kernel finds the values of 8 consecutive active classes for a column in one 64-byte segment.  Same access
+// order as pull_mirror_kernel: a warp walks 8 column panels along its 32 source rows.
+__global__ void __launch_bounds__(128) fetch_rows_t_kernel(const RowTable t, long long ld, const int32_t *rows, int a_begin, int a_count,
+                                                           int nact, int ncp /* column panels */, double *GT, long long ldt) {
+    __shared__ double tile[4][T][T + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kRun = 8;
+    const long long runs = (ncp + kRun - 1) / kRun, nblk = (a_count + T - 1) / T, nunits = nblk * runs;
+    for (long long u = blockIdx.x * 4LL + warp; u < nunits; u += gridDim.x * 4LL) {
+        const int ab = a_begin + (int) (u / runs) * T, J0 = (int) (u % runs) * kRun, J1 = min(J0 + kRun, ncp);
+        const double *src[T];
+#pragma unroll
+        for (int k = 0; k < T; k++) src[k] = row_ptr(t, rows[min(ab + k, nact - 1)], ld) + lane;     // (past the end: any valid row, never used)
+        for (int Jp = J0; Jp < J1; Jp++) {
+            double v[T];
+#pragma unroll
+            for (int k = 0; k < T; k++) v[k] = __ldcg(src[k] + (long long) Jp * T);
+#pragma unroll
+            for (int k = 0; k < T; k++) tile[warp][k][lane] = v[k];
+            __syncwarp();
+            double *dst = GT + (long long) Jp * T * ldt + ab + lane;
+            if (ab + lane < a_begin + a_count) {
+#pragma unroll 8
+                for (int k = 0; k < T; k++) dst[(long long) k * ldt] = tile[warp][lane][k];
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // Multi-GPU expansion: copy the class rows this rank's probands need from their owners (peer
 // reads over NVLink, 16-byte vectorised, one CTA per row) into a compact local matrix.
-__global__ void __launch_bounds__(256) fetch_rows_kernel(const RowTable t, long long ld, const int32_t *rows, double *dst, int rot) {
-    // (the ranks walk the owners in different orders -- rank q starts with the rows of rank q + 1 -- instead of all of them
-    // queueing on rank 0's links first, then on rank 1's, ...)
-    const int a = (int) ((blockIdx.x + (unsigned) rot) % gridDim.x);
+__global__ void __launch_bounds__(256) fetch_rows_kernel(const RowTable t, long long ld, const int32_t *rows, double *dst, int first) {
+    const int a = first + (int) blockIdx.x;             // position in the list of active classes
     const double2 *src = reinterpret_cast<const double2 *>(row_ptr(t, rows[a], ld));
     double2 *out = reinterpret_cast<double2 *>(dst + (long long) a * ld);
     for (long long c = threadIdx.x; c < ld / 2; c += 256) out[c] = src[c];
@@ -982,7 +1012,7 @@ constexpr int kExpCPT = kExpandCols / 256;     // result columns per thread
 constexpr int kExpMembers = 64;                // result rows of a class whose (row, individual) are staged in shared memory
 __global__ void __launch_bounds__(256) expand_kernel(const ExpandDev e) {
     __shared__ int mem_i[kExpMembers], mem_u[kExpMembers];
-    const int a = blockIdx.x / e.nchunks, chunk = blockIdx.x - a * e.nchunks;
+    const int a = e.a_begin + blockIdx.x / e.nchunks, chunk = blockIdx.x % e.nchunks;     // (a launch covers a range of the active classes)
     const int c = e.cact[a];
     const long long j0 = (long long) chunk * kExpandCols + threadIdx.x;
     const int q0 = e.coff[a], nm = e.coff[a + 1] - q0;
@@ -1030,8 +1060,8 @@ __global__ void __launch_bounds__(256) expand_kernel(const ExpandDev e) {
     if (threadIdx.x == 0) {
         double x = 0.0, y = 0.0;
         for (int w = 0; w < 8; w++) { x += ws[w]; y += wd[w]; }
-        e.partials[2 * (long long) blockIdx.x] = x;
-        e.partials[2 * (long long) blockIdx.x + 1] = y;
+        e.partials[2 * ((long long) a * e.nchunks + chunk)] = x;
+        e.partials[2 * ((long long) a * e.nchunks + chunk) + 1] = y;
     }
 }
 
@@ -1048,7 +1078,7 @@ __global__ void __launch_bounds__(256, 3) expand_sym_kernel(const ExpandDev e) {
     __shared__ int s_n[8], s_q0[8];
     __shared__ int s_i[8][kExpSymMembers], s_u[8][kExpSymMembers];
     const int nchunks = (int) ((e.m + kExpSymCols - 1) / kExpSymCols);
-    const int A = blockIdx.x / nchunks, chunk = blockIdx.x - A * nchunks;
+    const int A = e.a_begin / 8 + blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;      // (a launch covers a range of the active classes)
     const int a0 = A * 8, K = e.nact;
     if (threadIdx.x < 8) {
         const int c = a0 + threadIdx.x;
@@ -1064,7 +1094,7 @@ __global__ void __launch_bounds__(256, 3) expand_sym_kernel(const ExpandDev e) {
         for (int k = threadIdx.x & 31; k < s_n[cl]; k += 32) {
             const int i = e.cmem[s_q0[cl] + k];
             if (k < kExpSymMembers) { s_i[cl][k] = i; s_u[cl][k] = e.ind[i]; }
-            if (i / kExpSymCols == chunk) dsum += e.d[a0 + cl];
+            if (i / kExpSymCols == chunk) dsum += e.d[e.cact[a0 + cl]];
         }
     }
     __syncthreads();
@@ -1072,7 +1102,7 @@ __global__ void __launch_bounds__(256, 3) expand_sym_kernel(const ExpandDev e) {
     // a result row per instruction (m is even: the rows are 16-byte aligned)
     const int r = threadIdx.x & 3, q = threadIdx.x >> 2;
     const int ca = 2 * r, cb = 2 * r + 1;                                // this thread's two classes (within the block of 8)
-    const double da = a0 + ca < K ? e.d[a0 + ca] : 0.0, db = a0 + cb < K ? e.d[a0 + cb] : 0.0;
+    const double da = a0 + ca < K ? e.d[e.cact[a0 + ca]] : 0.0, db = a0 + cb < K ? e.d[e.cact[a0 + cb]] : 0.0;
     const long long jbase = (long long) chunk * kExpSymCols + 2 * q;
     constexpr int U = kExpSymIter / 128, NIT = kExpSymCols / kExpSymIter;
     struct Batch { int uj[U][2]; double2 v[U][2]; };
@@ -1134,8 +1164,8 @@ __global__ void __launch_bounds__(256, 3) expand_sym_kernel(const ExpandDev e) {
     if (threadIdx.x == 0) {
         double x = 0.0, y = 0.0;
         for (int w = 0; w < 8; w++) { x += ws[w]; y += wd[w]; }
-        e.partials[2 * (long long) blockIdx.x] = x;
-        e.partials[2 * (long long) blockIdx.x + 1] = y;
+        e.partials[2 * ((long long) A * nchunks + chunk)] = x;
+        e.partials[2 * ((long long) A * nchunks + chunk) + 1] = y;
     }
 }
 
@@ -1331,9 +1361,9 @@ cudaError_t launch_init_rows(double *G0, double *d0, const int32_t *flags, int64
     return cudaGetLastError();
 }
 
-cudaError_t launch_fetch_rows(const RowTable &t, int64_t ld, const int32_t *rows, int32_t nrows, double *dst, int32_t first, cudaStream_t st) {
-    if (nrows <= 0) return cudaSuccess;
-    fetch_rows_kernel<<<(unsigned) nrows, 256, 0, st>>>(t, ld, rows, dst, first);
+cudaError_t launch_fetch_rows(const RowTable &t, int64_t ld, const int32_t *rows, int32_t first, int32_t count, double *dst, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    fetch_rows_kernel<<<(unsigned) count, 256, 0, st>>>(t, ld, rows, dst, first);
     return cudaGetLastError();
 }
 
@@ -1343,17 +1373,28 @@ cudaError_t launch_pull_mirror(const RowTable &t, int64_t ld, int32_t pb, int32_
     return cudaGetLastError();
 }
 
-cudaError_t launch_expand(const ExpandDev &e, cudaStream_t st) {
-    if (e.nact <= 0) return cudaSuccess;
-    expand_kernel<<<(unsigned) ((long long) e.nact * e.nchunks), 256, 0, st>>>(e);
+cudaError_t launch_expand(const ExpandDev &e, int32_t a_begin, int32_t a_count, cudaStream_t st) {
+    if (a_count <= 0) return cudaSuccess;
+    ExpandDev x = e;
+    x.a_begin = a_begin;
+    expand_kernel<<<(unsigned) ((long long) a_count * e.nchunks), 256, 0, st>>>(x);
     return cudaGetLastError();
 }
 
 int64_t expand_sym_blocks(int32_t nact, int64_t m) { return (int64_t) ((nact + 7) / 8) * ((m + kExpSymCols - 1) / kExpSymCols); }
 
-cudaError_t launch_expand_sym(const ExpandDev &e, cudaStream_t st) {
-    if (e.nact <= 0) return cudaSuccess;
-    expand_sym_kernel<<<(unsigned) expand_sym_blocks(e.nact, e.m), 256, 0, st>>>(e);
+cudaError_t launch_expand_sym(const ExpandDev &e, int32_t a_begin, int32_t a_count, cudaStream_t st) {
+    if (a_count <= 0) return cudaSuccess;
+    ExpandDev x = e;
+    x.a_begin = a_begin;                                   // a multiple of 8
+    expand_sym_kernel<<<(unsigned) expand_sym_blocks(a_count, e.m), 256, 0, st>>>(x);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fetch_rows_t(const RowTable &t, int64_t ld, const int32_t *rows, int32_t a_begin, int32_t a_count, int32_t nact,
+                                int32_t column_panels, double *GT, int64_t ldt, cudaStream_t st) {
+    if (a_count <= 0) return cudaSuccess;
+    fetch_rows_t_kernel<<<148 * 8, 128, 0, st>>>(t, ld, rows, a_begin, a_count, nact, column_panels, GT, ldt);
     return cudaGetLastError();
 }
 

@@ -89,7 +89,7 @@ struct DiagDev {
 };
 
 struct ExpandDev {
-    const double *G;         // K_last x ld last class matrix
+    const double *G;         // K_last x ld last class matrix (expand_sym_kernel of a sharded job: the fetched rows TRANSPOSED, Kpad x ld)
     const double *d;         // self kinship per class
     int64_t ld;
     const int32_t *cls;      // m: class row of caller entry j
@@ -100,6 +100,7 @@ struct ExpandDev {
     double *out;             // (row1 - row0) x m, row-major, caller order
     int64_t m, row0, row1;
     int32_t nact, nchunks;
+    int32_t a_begin;         // first active class of this launch
     int32_t compact;         // 1: G holds only the active classes' rows, row a <-> cact[a] (multi-GPU)
     double *partials;        // nact*nchunks*2 : per-CTA (sum all, sum diag)
 };
@@ -114,11 +115,14 @@ cudaError_t launch_init_rows(double *G0, double *d0, const int32_t *flags, int64
                              int64_t row_begin, int64_t rows, int64_t dlen, cudaStream_t st);
 // ranked multi-GPU jobs: this rank's tiles (J own, I >= panel_end) = transposes of the tiles in the rows of I's owners
 cudaError_t launch_pull_mirror(const RowTable &t, int64_t ld, int32_t pb, int32_t pe, int32_t np, double *own, int64_t own_row0, cudaStream_t st);
-cudaError_t launch_fetch_rows(const RowTable &t, int64_t ld, const int32_t *rows, int32_t nrows, double *dst, int32_t first /* list position fetched first */, cudaStream_t st);
+cudaError_t launch_fetch_rows(const RowTable &t, int64_t ld, const int32_t *rows, int32_t first, int32_t count /* positions in the list */, double *dst, cudaStream_t st);
 constexpr int kExpandCols = 2048;     // result columns per CTA of the expansion kernel
-cudaError_t launch_expand(const ExpandDev &e, cudaStream_t st);
+cudaError_t launch_expand(const ExpandDev &e, int32_t a_begin, int32_t a_count /* range of the active classes */, cudaStream_t st);
 // one GPU, every class active (cact = identity): 8 classes x 1024 columns per CTA, 64-byte segments of the symmetric matrix
-cudaError_t launch_expand_sym(const ExpandDev &e, cudaStream_t st);
+cudaError_t launch_expand_sym(const ExpandDev &e, int32_t a_begin /* multiple of 8 */, int32_t a_count, cudaStream_t st);
+// sharded jobs: GT[c][a] = G[rows[a]][c], the active classes' rows fetched from their owners and transposed (G of expand_sym_kernel, ld = ldt)
+cudaError_t launch_fetch_rows_t(const RowTable &t, int64_t ld, const int32_t *rows, int32_t a_begin, int32_t a_count, int32_t nact,
+                                int32_t column_panels, double *GT, int64_t ldt, cudaStream_t st);
 int64_t expand_sym_blocks(int32_t nact, int64_t m);     // its grid = its (sum, diagonal sum) partials
 cudaError_t launch_eye(double *out, int64_t m, int64_t row0, int64_t row1, double *partials, cudaStream_t st);
 // two-stage deterministic reduction of the per-CTA partials: scratch holds 2*256 doubles

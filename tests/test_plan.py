@@ -103,3 +103,24 @@ def test_correction_overflow_falls_back_to_one_row_per_individual():
     small = gk.cgeneakit.DevicePhi(gk.cgeneakit.Pedigree(ids2, sire2, dam2, np.ones(len(sire2))), [int(x) for x in ids2[4 + few:]])
     assert small.stats()["compressed"] == 1 and small.stats()["corrections"] > 0
     small.close()
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_planner_does_not_depend_on_the_thread_count(world, monkeypatch):
+    """The cuts are planned in order on a pool of host threads (a cut waits for the order of the previous one): the plan
+    must be the same arrays whatever the number of threads, for one-GPU and for sharded (lineage-grouped) jobs."""
+    from plan_emulator import step_view
+    ped, pro = gk.synthetic_pedigree(30000, 10, 1500, seed=7)
+    plans = []
+    for threads in ("1", "3", "16"):
+        monkeypatch.setenv("GK_PLAN_THREADS", threads)
+        job = gk.cgeneakit.DevicePhi(ped, pro, rank=0, world=world)
+        G = job.stats()["n_cuts"]
+        plans.append([step_view(job, g) for g in range(G)])
+        job.close()
+    for other in plans[1:]:
+        assert len(other) == len(plans[0])
+        for a, b in zip(plans[0], other):
+            assert a["K"] == b["K"] and a["panel_rows"] == b["panel_rows"]
+            for key in ("pF", "pM", "flags", "cls_ind", "cls_size", "pg_i", "pg_j", "pg_off", "pt_cls", "pt_mult"):
+                assert np.array_equal(a[key], b[key]), key
