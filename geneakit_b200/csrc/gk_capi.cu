@@ -490,7 +490,10 @@ static bool pack_cut(gk_phi_job *j, int g) {
             std::vector<int32_t> g32b(((size_t) (o.pe - o.pb) + 1) * 2);
             int64_t *goff2 = reinterpret_cast<int64_t *>(g32b.data());
             goff2[0] = 0;
-            for (int s = o.pb; s < o.pe; s++) goff2[s - o.pb + 1] = goff2[s - o.pb] + (j->full_rows ? S.np : s + 1);
+            // (a rank of a sharded job evaluates every tile J for its panels -- except, with the default kernel, the tiles of
+            // its OWN panels above the diagonal: inside its own block it works like one GPU, J <= I and both pieces stored)
+            for (int s = o.pb; s < o.pe; s++)
+                goff2[s - o.pb + 1] = goff2[s - o.pb] + (j->full_rows ? (o.use_g4 ? S.np - (o.pe - 1 - s) : S.np) : s + 1);
             o.total2 = goff2[o.pe - o.pb];
             o.grp_off2 = pk.add(pk.keep(std::move(g32b)));
         }

@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(kThreadsG4, 1) phi_step_g4_kernel(const StepDe
                     if (I != checked_panel) {              // first item of a panel here: its ring slot must have been drained
                         const int old = I - s.ring_n;
                         const long long c0 = clock64();
-                        if (old >= s.panel_begin && !(s.debug_nowait & 1)) wait_count(s.done2 + old, s.full_rows ? s.np : old + 1);
+                        if (old >= s.panel_begin && !(s.debug_nowait & 1)) wait_count(s.done2 + old, s.full_rows ? s.np - (s.panel_end - 1 - old) : old + 1);
                         p_ring += clock64() - c0;
                     }
                 }
@@ -768,7 +768,11 @@ __global__ void __launch_bounds__(kThreadsG4, 1) phi_step_g4_kernel(const StepDe
             const long long q_end = (cq + 1) * CH < total2 ? (cq + 1) * CH : total2;
             for (long long q = cq * CH; q < q_end; q++) {
                 while (q >= s.grp_off2[g + 1]) ++g;
-                const int I = s.panel_begin + g, J = (int) (q - s.grp_off2[g]);
+                const int I = s.panel_begin + g;
+                int J = (int) (q - s.grp_off2[g]);
+                // a rank of a sharded job: every tile J except those of its own panels above the diagonal (tile (I, J < I) of the
+                // own block stores both pieces, as on one GPU)
+                if (s.full_rows && J > I) J += s.panel_end - 1 - I;
                 const double *buf = s.ring + (long long) ((I - s.panel_begin) % s.ring_n) * s.ring_stride + lane;
                 const int pf = s.pF[J * T + lane], pm = s.pM[J * T + lane];
                 if (I != sig_panel && sig_count > 0) {    // the chunk crosses into the next panel: publish the tiles of the previous one
@@ -789,9 +793,10 @@ __global__ void __launch_bounds__(kThreadsG4, 1) phi_step_g4_kernel(const StepDe
                 }
                 double *drow = out + ((long long) J * T - s.out_row0) * ldn + I * T + lane;    // row j of tile J, columns of panel I
                 double *mrow = out + ((long long) I * T - s.out_row0) * ldn + J * T;           // row i of panel I, columns of tile J
-                // rows of tile J are stored only if they are this rank's: a sharded job stores its own rows (the transposed pieces);
-                // ranked sharded jobs evaluate J <= I and the owner of J pulls the piece out of this rank's rows (pull_mirror_kernel)
-                const bool own_j = !s.full_rows && J >= s.panel_begin;
+                // rows of tile J are stored only if they are this rank's: a sharded job stores the transposed pieces into its own rows
+                // and, inside its own block (J < I), the rows of tile J as well; ranked sharded jobs evaluate J <= I and the owner
+                // of another rank's J pulls the piece out of this rank's rows (pull_mirror_kernel)
+                const bool own_j = J >= s.panel_begin && (!s.full_rows || J < I);
                 if (J != I || s.full_rows) {
                     // (a rank of a sharded job evaluates every tile J for its own panels and stores only its own rows: the
                     // transposed pieces)

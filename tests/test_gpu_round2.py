@@ -100,6 +100,20 @@ def test_c5_tenth_width_replica_matches_the_oracle():
     assert abs(got.sum() - len(pro)) < 1e-9              # every proband's founders contribute 1 in total
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("name", ["overlap400_s1", "genea140", "overlap400_s3"])
+def test_sharded_ranks_through_the_default_kernel(name, world, monkeypatch):
+    """The default step kernel in sharded jobs (every tile J of another rank's panels, J <= I inside the own block)."""
+    from geneakit_b200.distributed import VirtualShardedPhi
+    monkeypatch.setenv("GK_STEP_KERNEL", "g4")
+    monkeypatch.setenv("GK_G4_MIN_K", "32")
+    g = load_golden(name)
+    for compress in (0, 1):
+        v = VirtualShardedPhi(_ped(g), [int(x) for x in g["pro"]], world=world, compress=compress).upload().run()
+        assert v.to_host().tobytes() == g["phi"].tobytes()
+        v.close()
+
+
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("name", ["deep45_shuffled", "deep30_w40"])
 def test_ranked_sharded_ranks_through_the_default_kernel(name, world, monkeypatch):
@@ -289,3 +303,25 @@ def test_phi_gc_f_do_not_depend_on_the_rank_order(seed):
     assert np.array_equal(np.round(gk.phi(a, pro=pro).values, 12), np.round(gk.phi(b, pro=pro).values, 12))
     assert np.array_equal(np.round(gk.gc(a, pro=pro).values, 12), np.round(gk.gc(b, pro=pro).values, 12))
     assert np.array_equal(np.round(gk.f(a, pro=pro).values, 12), np.round(gk.f(b, pro=pro).values, 12))
+
+
+def test_one_shot_call_falls_back_to_one_row_per_individual_mid_pass():
+    """An individual of a two-member sibship with 17 000 mates: the sibship compression would need a quadratic correction
+    list.  The one-shot call finds out while it already runs the first cuts (the cuts are planned while the device works),
+    drains, and runs again with one row per individual -- the caller sees nothing but the right matrix: half sibs 1/8,
+    the child of the other sib 1/16 with all of them, 1/2 on the diagonal."""
+    mates = 17000
+    sire = [-1, -1, 0, 0] + [-1] * mates + [2] * (mates - 1) + [3]
+    dam = [-1, -1, 1, 1] + [-1] * mates + list(range(4, 4 + mates))
+    n = len(sire)
+    ids = np.arange(1, n + 1)
+    ped = gk.cgeneakit.Pedigree(ids, sire, dam, np.ones(n))
+    pro = [int(x) for x in ids[4 + mates:]]
+    got = gk.cgeneakit.compute_kinships(ped, pro)
+    m = len(pro)
+    assert got.shape == (m, m)
+    assert np.all(np.diag(got) == 0.5)
+    assert np.all(got[-1, :-1] == 0.0625) and np.all(got[:-1, -1] == 0.0625)
+    block = got[:2000, :2000]
+    assert np.all(block[~np.eye(2000, dtype=bool)] == 0.125)
+    assert np.array_equal(got[5000:5100], got[:, 5000:5100].T)
