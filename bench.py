@@ -371,7 +371,7 @@ def main():
     step_ms, step_bytes = sum(t_ms[:nstep]), sum(b[:nstep]) / world      # a rank produces 1/world of every cut's matrix
     peak, peak_src = peaks()
     achieved = step_bytes / (step_ms * 1e-3) / 1e9 if step_ms > 0 else 0.0
-    kernel = "phi_step_g4_kernel" if world == 1 and max(job.class_sizes()) >= 8192 else ("phi_step_tma_kernel" if world > 1 else "phi_step_kernel")
+    kernel = "phi_step_g4_kernel" if max(job.class_sizes()) >= 8192 else ("phi_step_tma_kernel" if world > 1 else "phi_step_kernel")
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "launches": nstep, "bytes_per_launch_avg": step_bytes / max(nstep, 1),
