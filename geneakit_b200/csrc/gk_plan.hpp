@@ -341,6 +341,7 @@ inline bool PhiPlanner::begin() {
     // ---- min / max ancestral path length from a proband (one reverse-topological sweep) ----
     pl_.assign(2 * (size_t) n, -1);
     int32_t *pl = pl_.data();
+    mark("  (path-length array)");
     for (int32_t i = 0; i < m; i++) { pl[2 * (size_t) pro[i]] = 0; pl[2 * (size_t) pro[i] + 1] = std::max(pl[2 * (size_t) pro[i] + 1], 0); }
     int32_t top = 0;
     for (int32_t x = n - 1; x >= 0; x--) {
