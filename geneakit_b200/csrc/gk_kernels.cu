@@ -1312,6 +1312,16 @@ cudaError_t configure_kernels() {
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phi_step_kernel, kThreads, kStepSmem))) return e;
     if ((e = cudaFuncSetAttribute(phi_step_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kStepSmemTma))) return e;
     if ((e = cudaFuncSetAttribute(phi_step_g4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kStepSmemG4))) return e;
+    // the three step kernels are launched with the same persistent grid, and their waits rely on every CTA being resident:
+    // the grid is sized by the kernel that fits the fewest CTAs per SM
+    {
+        int occ_tma = 0, occ_g4 = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tma, phi_step_tma_kernel, kThreadsTma, kStepSmemTma))) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_g4, phi_step_g4_kernel, kThreadsG4, kStepSmemG4))) return e;
+        occ = occ < occ_tma ? occ : occ_tma;
+        occ = occ < occ_g4 ? occ : occ_g4;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+    }
     const char *env = getenv("GK_CTAS_PER_SM");
     if (env && atoi(env) > 0 && atoi(env) < occ) occ = atoi(env);
     g_step_grid = sms * (occ > 0 ? occ : 1);     // persistent: one wave, every CTA resident (the waits rely on it)
